@@ -1,0 +1,53 @@
+// fx3d_internal.cuh -- shared host-side plumbing of libfx3d_cuda: error reporting, launch macro, layout rules.
+#pragma once
+#include "../../include/fx3d.h"
+#include "lbm_kernels.cuh"
+#include <atomic>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace fx3d {
+
+void set_error(const std::string& msg);       // stores the thread-local text returned by fx3d_last_error()
+extern std::atomic<uint64_t> g_launches;      // kernels launched so far (fx3d_launch_count)
+extern std::atomic<int> g_variant;            // 0 auto, 1 force the general one-cell-per-thread kernels
+
+#if defined(FX3D_HOST_EMULATION)
+// test-only build (tests/emul): kernels run as OS threads on host pointers; there is no device to select
+#define FX3D_LAUNCH(kernel, grid, block, stream, ...) do { ::fx3d::g_launches++; ::emul::launch((grid), (block), [&]() { kernel(__VA_ARGS__); }); } while(0)
+inline int use_device(int) { return FX3D_OK; }
+inline int check_launch(const char*) { return FX3D_OK; }
+#else
+#define FX3D_LAUNCH(kernel, grid, block, stream, ...) do { ::fx3d::g_launches++; kernel<<<(grid), (block), 0, (cudaStream_t)(stream)>>>(__VA_ARGS__); } while(0)
+int use_device(int device);                   // cudaSetDevice with error translation
+int check_launch(const char* what);           // cudaGetLastError with error translation
+int cuda_fail(cudaError_t e, const char* what);
+#endif
+
+// DDF layout rules (see lbm_kernels.cuh): pitch multiple of 64 elements, x offset 7 when the x axis has a halo so that
+// the first non-halo cell (x=1) lands on element 8 of its row
+inline bool make_lattice(const fx3d_lattice* in, uint64_t t, float fx, float fy, float fz, Lattice& L) {
+	if(!in) { set_error("lattice is null"); return false; }
+	if(in->Nx==0u||in->Ny==0u||in->Nz==0u) { set_error("lattice size is 0"); return false; }
+	if(in->velocity_set!=19u&&in->velocity_set!=27u) { set_error("velocity_set must be 19 or 27 (D3Q19 / D3Q27)"); return false; }
+	if(in->collision>1u||in->storage>2u||in->Dx==0u||in->Dy==0u||in->Dz==0u) { set_error("invalid collision/storage/domain count"); return false; }
+	L.Nx = in->Nx; L.Ny = in->Ny; L.Nz = in->Nz;
+	L.Hx = in->Dx>1u; L.Hy = in->Dy>1u; L.Hz = in->Dz>1u;
+	if((L.Hx&&in->Nx<3u)||(L.Hy&&in->Ny<3u)||(L.Hz&&in->Nz<3u)) { set_error("a decomposed axis needs at least 3 cells (halo + 1 + halo)"); return false; }
+	L.xo = L.Hx ? 7u : 0u;
+	L.px = ((in->Nx+L.xo+63u)/64u)*64u;
+	L.slot = (uint64_t)L.px*in->Ny*in->Nz;
+	L.fi = in->fi; L.rho = in->rho; L.u = in->u; L.flags = in->flags;
+	L.w = in->w; L.fx = fx; L.fy = fy; L.fz = fz;
+	L.odd = (uint32_t)(t&1ull);
+	L.eb = (in->features&FX3D_EQUILIBRIUM_BOUNDARIES) ? 1u : 0u;
+	L.upd = (in->features&FX3D_UPDATE_FIELDS) ? 1u : 0u;
+	return true;
+}
+inline size_t elem_bytes(uint32_t storage) { return storage==FX3D_FP32 ? 4u : 2u; }
+
+// stream_collide instantiations live in one translation unit per (velocity set, storage), see sc_inst.cu
+template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, bool vector4, int collision, bool volume_force, void* stream);
+
+} // namespace fx3d

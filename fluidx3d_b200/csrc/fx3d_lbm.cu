@@ -1,0 +1,226 @@
+// fx3d_lbm.cu -- C-ABI entry points for the LBM kernels (include/fx3d.h): argument checking, region decomposition,
+// template dispatch. Replaces the Kernel objects LBM_Domain binds and launches (FluidX3D v3.7 src/lbm.cpp:127-129,
+// 178-191, 1317-1354) and the launch glue of src/opencl.hpp:658-679.
+#define FX3D_TU_LBM
+#include "fx3d_internal.cuh"
+#include <cstring>
+#include <cstdlib>
+#include <algorithm>
+
+namespace fx3d {
+
+static thread_local std::string t_error;
+void set_error(const std::string& msg) { t_error = msg; }
+std::atomic<uint64_t> g_launches{0ull};
+std::atomic<int> g_variant{0};
+
+// interior (non-halo) extent and the shell / interior split used to overlap the halo exchange with computation.
+// The shell is every non-halo cell within one cell (one 4-cell group along x for the vector kernel) of a halo layer.
+static void regions_of(const Lattice& L, int region, bool vector4, std::vector<Region>& out) {
+	const uint32_t K = vector4 ? 4u : 1u;
+	const uint32_t gx0 = vector4 ? 0u : L.Hx, gx1 = vector4 ? (L.Nx-2u*L.Hx)/K : L.Nx-L.Hx;
+	const uint32_t y0 = L.Hy, y1 = L.Ny-L.Hy, z0 = L.Hz, z1 = L.Nz-L.Hz;
+	if(region==FX3D_REGION_ALL || (L.Hx|L.Hy|L.Hz)==0u) {
+		if(region!=FX3D_REGION_SHELL) out.push_back(Region{ gx0, gx1, y0, y1, z0, z1 });
+		return;
+	}
+	// interior box: shrink by one layer (group) on every decomposed axis; empty if the domain is too thin
+	const uint32_t ix0 = gx0+L.Hx, ix1 = gx1>=gx0+2u*L.Hx ? gx1-L.Hx : gx0+L.Hx;
+	const uint32_t iy0 = y0+L.Hy, iy1 = y1>=y0+2u*L.Hy ? y1-L.Hy : y0+L.Hy;
+	const uint32_t iz0 = z0+L.Hz, iz1 = z1>=z0+2u*L.Hz ? z1-L.Hz : z0+L.Hz;
+	const bool has_interior = ix1>ix0 && iy1>iy0 && iz1>iz0;
+	if(region==FX3D_REGION_INTERIOR) {
+		if(has_interior) out.push_back(Region{ ix0, ix1, iy0, iy1, iz0, iz1 });
+		return;
+	}
+	if(!has_interior) { out.push_back(Region{ gx0, gx1, y0, y1, z0, z1 }); return; } // everything is shell
+	if(L.Hz) { out.push_back(Region{ gx0, gx1, y0, y1, z0, iz0 }); out.push_back(Region{ gx0, gx1, y0, y1, iz1, z1 }); }
+	if(L.Hy) { out.push_back(Region{ gx0, gx1, y0, iy0, iz0, iz1 }); out.push_back(Region{ gx0, gx1, iy1, y1, iz0, iz1 }); }
+	if(L.Hx) { out.push_back(Region{ gx0, ix0, iy0, iy1, iz0, iz1 }); out.push_back(Region{ ix1, gx1, iy0, iy1, iz0, iz1 }); }
+}
+
+static inline dim3 cell_block(uint32_t nx) { uint32_t bx = 1u; while(bx<nx && bx<128u) bx <<= 1; return dim3(bx, 128u/bx, 1u); }
+static inline dim3 cell_grid(const Region& R, const dim3& b) { return dim3((R.g1-R.g0+b.x-1u)/b.x, (R.y1-R.y0+b.y-1u)/b.y, R.z1-R.z0); }
+static inline Region all_cells(const Lattice& L) { return Region{ L.Hx, L.Nx-L.Hx, L.Hy, L.Ny-L.Hy, L.Hz, L.Nz-L.Hz }; }
+
+#define FX3D_DISPATCH_Q_ST(Qv, STv, BODY) \
+	if(Qv==19u) { if(STv==FX3D_FP32) { constexpr int Q = 19, ST = ST_FP32; BODY } else if(STv==FX3D_FP16S) { constexpr int Q = 19, ST = ST_FP16S; BODY } else { constexpr int Q = 19, ST = ST_FP16C; BODY } } \
+	else        { if(STv==FX3D_FP32) { constexpr int Q = 27, ST = ST_FP32; BODY } else if(STv==FX3D_FP16S) { constexpr int Q = 27, ST = ST_FP16S; BODY } else { constexpr int Q = 27, ST = ST_FP16C; BODY } }
+
+static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int region, void* stream) {
+	const bool vector4 = g_variant.load()!=1 && ((L.Nx-2u*L.Hx)&3u)==0u && L.Nx-2u*L.Hx>=4u;
+	std::vector<Region> regs;
+	regions_of(L, region, vector4, regs);
+	const bool vf = (lat->features&FX3D_VOLUME_FORCE)!=0u;
+	for(const Region& R : regs) {
+		int rc;
+		FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, vector4, (int)lat->collision, vf, stream); })
+		if(rc!=FX3D_OK) return rc;
+	}
+	return FX3D_OK;
+}
+
+} // namespace fx3d
+using namespace fx3d;
+
+extern "C" {
+
+const char* fx3d_last_error(void) { return t_error.c_str(); }
+int fx3d_set_kernel_variant(int variant) { if(variant<0||variant>1) { set_error("variant must be 0 or 1"); return FX3D_ERR_INVALID; } g_variant = variant; return FX3D_OK; }
+int fx3d_launch_count(uint64_t* launches) { if(!launches) return FX3D_ERR_INVALID; *launches = g_launches.load(); return FX3D_OK; }
+
+size_t fx3d_fi_bytes(const fx3d_lattice* lat) {
+	Lattice L;
+	if(!make_lattice(lat, 0ull, 0.0f, 0.0f, 0.0f, L)) return 0u;
+	return (size_t)(L.slot*lat->velocity_set*elem_bytes(lat->storage));
+}
+uint32_t fx3d_bytes_per_cell_per_step(const fx3d_lattice* lat) { // src/lbm.cpp:52-57
+	if(!lat) return 0u;
+	return lat->velocity_set*2u*(uint32_t)elem_bytes(lat->storage)+1u+((lat->features&FX3D_UPDATE_FIELDS) ? 16u : 0u);
+}
+float fx3d_relaxation_rate(float nu) {
+	// def_w = to_string(1.0f/tau)+"f" (src/lbm.cpp:367): the reference formats 1/tau with 1+8 significant decimal digits in
+	// float arithmetic (split_float, src/utilities.hpp:2599-2630) and the OpenCL compiler parses that literal back
+	float x = 1.0f/(3.0f*nu+0.5f);
+	if(!(x>0.0f) || x>3.4e38f) return x;
+	int exponent = 0;
+	if(x>=10.0f) {
+		if(x>=1E32f) { x *= 1E-32f; exponent += 32; } if(x>=1E16f) { x *= 1E-16f; exponent += 16; } if(x>=1E8f) { x *= 1E-8f; exponent += 8; }
+		if(x>=1E4f) { x *= 1E-4f; exponent += 4; } if(x>=1E2f) { x *= 1E-2f; exponent += 2; } if(x>=1E1f) { x *= 1E-1f; exponent += 1; }
+	}
+	if(x>0.0f && x<=1.0f) {
+		if(x<1E-31f) { x *= 1E32f; exponent -= 32; } if(x<1E-15f) { x *= 1E16f; exponent -= 16; } if(x<1E-7f) { x *= 1E8f; exponent -= 8; }
+		if(x<1E-3f) { x *= 1E4f; exponent -= 4; } if(x<1E-1f) { x *= 1E2f; exponent -= 2; } if(x<1E0f) { x *= 1E1f; exponent -= 1; }
+	}
+	uint32_t integral = (uint32_t)x;
+	const float remainder = (x-(float)integral)*1E8f;
+	uint32_t decimal = (uint32_t)remainder;
+	if(remainder-(float)decimal>=0.5f) { decimal++; if(decimal>=100000000u) { decimal = 0u; integral++; if(integral>=10u) { integral = 1u; exponent++; } } }
+	char s[48];
+	std::snprintf(s, sizeof(s), "%u.%08uE%d", integral, decimal, exponent);
+	return std::strtof(s, nullptr);
+}
+
+int fx3d_initialize(const fx3d_lattice* lat, fx3d_stream stream) {
+	Lattice L;
+	if(!make_lattice(lat, 1ull, 0.0f, 0.0f, 0.0f, L)) return FX3D_ERR_INVALID;
+	if(int rc = use_device(lat->device)) return rc;
+	const Region R = all_cells(L);
+	const dim3 b = cell_block(R.g1-R.g0), g = cell_grid(R, b);
+	FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { FX3D_LAUNCH((k_initialize<Q, ST>), g, b, stream, L, R); })
+	return check_launch("initialize");
+}
+int fx3d_stream_collide(const fx3d_lattice* lat, uint64_t t, float fx, float fy, float fz, int region, fx3d_stream stream) {
+	Lattice L;
+	if(!make_lattice(lat, t, fx, fy, fz, L)) return FX3D_ERR_INVALID;
+	if(region<0||region>2) { set_error("invalid region"); return FX3D_ERR_INVALID; }
+	if(int rc = use_device(lat->device)) return rc;
+	return stream_collide_impl(lat, L, region, stream);
+}
+int fx3d_run_steps(const fx3d_lattice* lat, uint64_t t0, uint64_t steps, float fx, float fy, float fz, fx3d_stream stream) {
+	Lattice L;
+	if(!make_lattice(lat, t0, fx, fy, fz, L)) return FX3D_ERR_INVALID;
+	if(lat->Dx*lat->Dy*lat->Dz!=1u) { set_error("fx3d_run_steps is for a single non-decomposed domain"); return FX3D_ERR_INVALID; }
+	if(int rc = use_device(lat->device)) return rc;
+	for(uint64_t s=0ull; s<steps; s++) {
+		L.odd = (uint32_t)((t0+s)&1ull);
+		if(int rc = stream_collide_impl(lat, L, FX3D_REGION_ALL, stream)) return rc;
+	}
+	return FX3D_OK;
+}
+int fx3d_update_fields(const fx3d_lattice* lat, uint64_t t, float fx, float fy, float fz, fx3d_stream stream) {
+	Lattice L;
+	if(!make_lattice(lat, t, fx, fy, fz, L)) return FX3D_ERR_INVALID;
+	if(int rc = use_device(lat->device)) return rc;
+	const Region R = all_cells(L);
+	const dim3 b = cell_block(R.g1-R.g0), g = cell_grid(R, b);
+	if(lat->features&FX3D_VOLUME_FORCE) { FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { FX3D_LAUNCH((k_update_fields<Q, ST, true>), g, b, stream, L, R); }) }
+	else { FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { FX3D_LAUNCH((k_update_fields<Q, ST, false>), g, b, stream, L, R); }) }
+	return check_launch("update_fields");
+}
+
+static bool face_setup(const fx3d_lattice* lat, uint32_t axis, uint64_t t, Lattice& L, dim3& g, dim3& b) {
+	if(!make_lattice(lat, t, 0.0f, 0.0f, 0.0f, L)) return false;
+	if(axis>2u) { set_error("axis must be 0, 1 or 2"); return false; }
+	if((axis==0u&&L.Nx<3u)||(axis==1u&&L.Ny<3u)||(axis==2u&&L.Nz<3u)) { set_error("axis too thin for a halo transfer"); return false; }
+	const uint64_t A = axis==0u ? (uint64_t)L.Ny*L.Nz : axis==1u ? (uint64_t)L.Nz*L.Nx : (uint64_t)L.Nx*L.Ny;
+	if(A>0xFFFFFFFFull) { set_error("face too large"); return false; }
+	b = dim3(128u, 1u, 1u); g = dim3((uint32_t)((A+127ull)/128ull), 1u, 1u);
+	return true;
+}
+size_t fx3d_transfer_bytes(const fx3d_lattice* lat) { // src/lbm.cpp:1309-1315
+	if(!lat) return 0u;
+	uint64_t Amax = 0ull;
+	if(lat->Dx>1u) Amax = std::max(Amax, (uint64_t)lat->Ny*lat->Nz);
+	if(lat->Dy>1u) Amax = std::max(Amax, (uint64_t)lat->Nz*lat->Nx);
+	if(lat->Dz>1u) Amax = std::max(Amax, (uint64_t)lat->Nx*lat->Ny);
+	const uint64_t per = std::max<uint64_t>((lat->velocity_set==19u ? 5u : 9u)*elem_bytes(lat->storage), 17u);
+	return (size_t)(Amax*per);
+}
+int fx3d_transfer_extract_fi(const fx3d_lattice* lat, uint32_t axis, uint64_t t, void* bp, void* bm, fx3d_stream stream) {
+	Lattice L; dim3 g, b;
+	if(!face_setup(lat, axis, t, L, g, b)) return FX3D_ERR_INVALID;
+	if(int rc = use_device(lat->device)) return rc;
+	FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { FX3D_LAUNCH((k_transfer_fi<Q, ST, true>), g, b, stream, L, axis, bp, bm); })
+	return check_launch("transfer_extract_fi");
+}
+int fx3d_transfer_insert_fi(const fx3d_lattice* lat, uint32_t axis, uint64_t t, const void* bp, const void* bm, fx3d_stream stream) {
+	Lattice L; dim3 g, b;
+	if(!face_setup(lat, axis, t, L, g, b)) return FX3D_ERR_INVALID;
+	if(int rc = use_device(lat->device)) return rc;
+	FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { FX3D_LAUNCH((k_transfer_fi<Q, ST, false>), g, b, stream, L, axis, const_cast<void*>(bp), const_cast<void*>(bm)); })
+	return check_launch("transfer_insert_fi");
+}
+int fx3d_transfer_extract_rho_u_flags(const fx3d_lattice* lat, uint32_t axis, uint64_t t, void* bp, void* bm, fx3d_stream stream) {
+	Lattice L; dim3 g, b;
+	if(!face_setup(lat, axis, t, L, g, b)) return FX3D_ERR_INVALID;
+	if(int rc = use_device(lat->device)) return rc;
+	FX3D_LAUNCH((k_transfer_rho_u_flags<true>), g, b, stream, L, axis, bp, bm);
+	return check_launch("transfer_extract_rho_u_flags");
+}
+int fx3d_transfer_insert_rho_u_flags(const fx3d_lattice* lat, uint32_t axis, uint64_t t, const void* bp, const void* bm, fx3d_stream stream) {
+	Lattice L; dim3 g, b;
+	if(!face_setup(lat, axis, t, L, g, b)) return FX3D_ERR_INVALID;
+	if(int rc = use_device(lat->device)) return rc;
+	FX3D_LAUNCH((k_transfer_rho_u_flags<false>), g, b, stream, L, axis, const_cast<void*>(bp), const_cast<void*>(bm));
+	return check_launch("transfer_insert_rho_u_flags");
+}
+int fx3d_exchange_fi(const fx3d_lattice* lat, uint32_t axis, uint64_t t, const void* fi_plus, const void* fi_minus, fx3d_stream stream) {
+	Lattice L; dim3 g, b;
+	if(!face_setup(lat, axis, t, L, g, b)) return FX3D_ERR_INVALID;
+	if(!fi_plus||!fi_minus) { set_error("neighbour DDF buffers are null"); return FX3D_ERR_INVALID; }
+	if(int rc = use_device(lat->device)) return rc;
+	FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { FX3D_LAUNCH((k_exchange_fi<Q, ST>), g, b, stream, L, axis, fi_plus, fi_minus); })
+	return check_launch("exchange_fi");
+}
+int fx3d_exchange_rho_u_flags(const fx3d_lattice* lat, uint32_t axis, const float* rho_plus, const float* u_plus, const uint8_t* flags_plus,
+	const float* rho_minus, const float* u_minus, const uint8_t* flags_minus, fx3d_stream stream) {
+	Lattice L; dim3 g, b;
+	if(!face_setup(lat, axis, 0ull, L, g, b)) return FX3D_ERR_INVALID;
+	if(!rho_plus||!u_plus||!flags_plus||!rho_minus||!u_minus||!flags_minus) { set_error("neighbour field buffers are null"); return FX3D_ERR_INVALID; }
+	if(int rc = use_device(lat->device)) return rc;
+	const PeerFields plus{ rho_plus, u_plus, flags_plus }, minus{ rho_minus, u_minus, flags_minus };
+	FX3D_LAUNCH(k_exchange_rho_u_flags, g, b, stream, L, axis, plus, minus);
+	return check_launch("exchange_rho_u_flags");
+}
+
+int fx3d_codec_encode(int device, int storage, const float* in, uint16_t* out, size_t count, fx3d_stream stream) {
+	if(storage!=FX3D_FP16S&&storage!=FX3D_FP16C) { set_error("codec entry points are for FP16S / FP16C"); return FX3D_ERR_INVALID; }
+	if(int rc = use_device(device)) return rc;
+	const dim3 b(128u), g((uint32_t)((count+127u)/128u));
+	if(count==0u) return FX3D_OK;
+	if(storage==FX3D_FP16S) FX3D_LAUNCH((k_codec_encode<ST_FP16S>), g, b, stream, in, out, (uint64_t)count);
+	else FX3D_LAUNCH((k_codec_encode<ST_FP16C>), g, b, stream, in, out, (uint64_t)count);
+	return check_launch("codec_encode");
+}
+int fx3d_codec_decode(int device, int storage, const uint16_t* in, float* out, size_t count, fx3d_stream stream) {
+	if(storage!=FX3D_FP16S&&storage!=FX3D_FP16C) { set_error("codec entry points are for FP16S / FP16C"); return FX3D_ERR_INVALID; }
+	if(int rc = use_device(device)) return rc;
+	const dim3 b(128u), g((uint32_t)((count+127u)/128u));
+	if(count==0u) return FX3D_OK;
+	if(storage==FX3D_FP16S) FX3D_LAUNCH((k_codec_decode<ST_FP16S>), g, b, stream, in, out, (uint64_t)count);
+	else FX3D_LAUNCH((k_codec_decode<ST_FP16C>), g, b, stream, in, out, (uint64_t)count);
+	return check_launch("codec_decode");
+}
+
+} // extern "C"

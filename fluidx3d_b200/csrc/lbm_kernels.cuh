@@ -1,0 +1,446 @@
+// lbm_kernels.cuh -- device kernels of the LBM hot path for sm_100a.
+//
+// Replaces the reference's OpenCL kernels (FluidX3D v3.7 src/kernel.cpp): stream_collide :1454-1636 with
+// load_f/store_f :1326-1339, initialize :1358-1430, update_fields :1794-1870, transfer_extract_fi /
+// transfer__insert_fi :2049-2131, transfer_*_rho_u_flags :2133-2158 -- and adds the direct peer (NVLink) halo
+// exchange that replaces LBM::communicate_field (src/lbm.cpp:1355-1383).
+//
+// DDF memory layout (private to this library; DDFs never exist on the host, src/lbm.hpp:38): structure of arrays,
+// one array per slot i, element (x,y,z) of slot i at  i*slot + (x+xo) + px*(y + Ny*z)  where px is the row pitch
+// rounded up to 64 elements and xo shifts x so that the first non-halo cell of every row starts on a 16-byte
+// boundary. Esoteric-Pull slot semantics are exactly the reference's (which slot holds which population at which
+// step parity), so solid-cell bounce-back, TYPE_E behaviour and the halo exchange addresses are unchanged.
+// rho, u (SoA, 3 planes) and flags keep the reference's plain layout n = x+(y+z*Ny)*Nx: they are what the host API
+// reads and writes.
+#pragma once
+#include "lbm_core.cuh"
+
+namespace fx3d {
+
+struct Lattice { // one LBM_Domain as the device sees it (passed by value)
+	uint32_t Nx, Ny, Nz; // local size, halo layers included
+	uint32_t Hx, Hy, Hz; // 1 where the axis is decomposed (halo layer present), else 0
+	uint32_t px, xo;     // DDF row pitch and x offset, in elements
+	uint64_t slot;       // elements between consecutive DDF slots
+	void* fi;
+	float* rho;
+	float* u;
+	uint8_t* flags;
+	float w, fx, fy, fz;
+	uint32_t odd;        // t&1
+	uint32_t eb;         // EQUILIBRIUM_BOUNDARIES enabled
+	uint32_t upd;        // UPDATE_FIELDS enabled
+};
+struct Region { uint32_t g0, g1, y0, y1, z0, z1; }; // x-group range [g0,g1), cell ranges in y and z
+
+FX3D_HD uint64_t cells(const Lattice& L) { return (uint64_t)L.Nx*L.Ny*L.Nz; }
+FX3D_HD uint64_t lin(const Lattice& L, uint32_t x, uint32_t y, uint32_t z) { return (uint64_t)x+((uint64_t)y+(uint64_t)z*L.Ny)*L.Nx; }
+FX3D_HD uint64_t row(const Lattice& L, uint32_t y, uint32_t z) { return (uint64_t)L.px*((uint64_t)y+(uint64_t)z*L.Ny); }
+FX3D_HD uint64_t phys(const Lattice& L, uint32_t x, uint32_t y, uint32_t z) { return row(L, y, z)+(uint64_t)(x+L.xo); }
+FX3D_HD uint32_t inc(uint32_t v, uint32_t n) { return v+1u==n ? 0u : v+1u; }
+FX3D_HD uint32_t dec(uint32_t v, uint32_t n) { return v==0u ? n-1u : v-1u; }
+template<int E> FX3D_HD uint32_t step(uint32_t v, uint32_t n) { if constexpr(E>0) return inc(v, n); else if constexpr(E<0) return dec(v, n); else return v; }
+FX3D_HD uint32_t step_rt(int e, uint32_t v, uint32_t n) { return e>0 ? inc(v, n) : e<0 ? dec(v, n) : v; }
+
+// ---- K consecutive x-elements of one slot, as loaded ----
+template<int ST, int K> struct Pack;
+template<> struct Pack<ST_FP32, 4> {
+	float e[4];
+	FX3D_HD void load(const float* p) { const float4 t = *reinterpret_cast<const float4*>(p); e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w; }
+	FX3D_HD void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(e[0], e[1], e[2], e[3]); }
+	FX3D_HD void store_1_3(float* p) const { p[1] = e[1]; *reinterpret_cast<float2*>(p+2) = make_float2(e[2], e[3]); } // elements 1..3 only
+	FX3D_HD void store_0_2(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(e[0], e[1]); p[2] = e[2]; } // elements 0..2 only
+	template<int c> FX3D_HD float get() const { return e[c]; }
+	template<int c> FX3D_HD void set(float v) { e[c] = v; }
+	FX3D_HD uint32_t first_bits() const { return __float_as_uint(e[0]); }
+	FX3D_HD uint32_t last_bits() const { return __float_as_uint(e[3]); }
+	FX3D_HD void push_back(uint32_t b) { e[0] = e[1]; e[1] = e[2]; e[2] = e[3]; e[3] = __uint_as_float(b); }  // {e1,e2,e3,b}
+	FX3D_HD void push_front(uint32_t b) { e[3] = e[2]; e[2] = e[1]; e[1] = e[0]; e[0] = __uint_as_float(b); } // {b,e0,e1,e2}
+	static FX3D_HD uint32_t bits(float v) { return __float_as_uint(v); }
+	static FX3D_HD float from_bits(uint32_t b) { return __uint_as_float(b); }
+};
+template<int ST> struct Pack<ST, 4> { // 16-bit storage: 4 elements in two 32-bit registers
+	uint32_t r[2];
+	FX3D_HD void load(const uint16_t* p) { const uint2 t = *reinterpret_cast<const uint2*>(p); r[0] = t.x; r[1] = t.y; }
+	FX3D_HD void store(uint16_t* p) const { *reinterpret_cast<uint2*>(p) = make_uint2(r[0], r[1]); }
+	FX3D_HD void store_1_3(uint16_t* p) const { p[1] = (uint16_t)(r[0]>>16); *reinterpret_cast<uint32_t*>(p+2) = r[1]; }
+	FX3D_HD void store_0_2(uint16_t* p) const { *reinterpret_cast<uint32_t*>(p) = r[0]; p[2] = (uint16_t)(r[1]&0xFFFFu); }
+	template<int c> FX3D_HD uint16_t get() const { return (uint16_t)((c&1) ? r[c>>1]>>16 : r[c>>1]&0xFFFFu); }
+	template<int c> FX3D_HD void set(uint16_t v) { r[c>>1] = (c&1) ? (r[c>>1]&0x0000FFFFu)|((uint32_t)v<<16) : (r[c>>1]&0xFFFF0000u)|(uint32_t)v; }
+	FX3D_HD uint32_t first_bits() const { return r[0]&0xFFFFu; }
+	FX3D_HD uint32_t last_bits() const { return r[1]>>16; }
+	FX3D_HD void push_back(uint32_t b) { r[0] = (r[0]>>16)|(r[1]<<16); r[1] = (r[1]>>16)|(b<<16); }
+	FX3D_HD void push_front(uint32_t b) { r[1] = (r[1]<<16)|(r[0]>>16); r[0] = (r[0]<<16)|(b&0xFFFFu); }
+	static FX3D_HD uint32_t bits(uint16_t v) { return (uint32_t)v; }
+	static FX3D_HD uint16_t from_bits(uint32_t b) { return (uint16_t)b; }
+};
+
+// ================================================================================================================
+// stream_collide, vector form: one thread owns K=4 x-consecutive cells and moves every slot with one aligned
+// 16-byte (FP32) / 8-byte (FP16) access. Directions with an x component are misaligned by one element: the thread
+// loads the aligned vector and obtains / hands over the straddling element by a warp shuffle; only at warp, block,
+// row or region ends does a lane fall back to one scalar access. Every (cell,slot) is still read and written by
+// exactly one thread (the Esoteric-Pull invariant), solid cells' populations pass through unchanged.
+// ================================================================================================================
+template<int Q, int COLL, int ST, bool VF>
+__global__ void __launch_bounds__(128) k_stream_collide_v4(const Lattice L, const Region R) {
+	constexpr int K = 4;
+	constexpr unsigned FULL = 0xFFFFFFFFu;
+	typedef Codec<ST> C;
+	typedef typename C::elem_t E;
+	typedef Pack<ST, K> P;
+	const uint32_t g = R.g0+blockIdx.x*blockDim.x+threadIdx.x;
+	const uint32_t y = R.y0+blockIdx.y*blockDim.y+threadIdx.y;
+	const uint32_t z = R.z0+blockIdx.z;
+	const bool valid = g<R.g1 && y<R.y1;
+	if(!__any_sync(FULL, valid)) return; // warp-uniform
+	const uint32_t lane = (threadIdx.x+threadIdx.y*blockDim.x)&31u;
+	const bool has_right = valid && lane<31u && threadIdx.x+1u<blockDim.x && g+1u<R.g1; // lane+1 owns the next K cells of this row
+	const bool has_left = valid && lane>0u && threadIdx.x>0u;                           // lane-1 owns the previous K cells
+	const uint32_t x0 = L.Hx+(uint32_t)K*g;
+	const uint32_t yp = inc(y, L.Ny), ym = dec(y, L.Ny), zp = inc(z, L.Nz), zm = dec(z, L.Nz);
+	const uint32_t xr = x0+(uint32_t)K>=L.Nx ? 0u : x0+(uint32_t)K; // x of the element right of my vector (periodic)
+	const uint32_t xl = x0==0u ? L.Nx-1u : x0-1u;                    // x of the element left of my vector
+	const uint64_t col = (uint64_t)(x0+L.xo);
+	E* const fi = reinterpret_cast<E*>(L.fi);
+	const uint32_t odd = L.odd;
+
+	uint32_t fl[K];
+	bool any_active = false;
+	if(valid) {
+		const uint8_t* fp = L.flags+lin(L, x0, y, z);
+		if(((L.Nx|x0)&3u)==0u) { // rows are 4-byte aligned: one load for the 4 flags
+			const uint32_t f4 = *reinterpret_cast<const uint32_t*>(fp);
+			fl[0] = f4&0xFFu; fl[1] = (f4>>8)&0xFFu; fl[2] = (f4>>16)&0xFFu; fl[3] = f4>>24;
+		} else { fl[0] = fp[0]; fl[1] = fp[1]; fl[2] = fp[2]; fl[3] = fp[3]; }
+		any_active = (fl[0]&TYPE_BO)!=TYPE_S || (fl[1]&TYPE_BO)!=TYPE_S || (fl[2]&TYPE_BO)!=TYPE_S || (fl[3]&TYPE_BO)!=TYPE_S;
+	} else { fl[0] = fl[1] = fl[2] = fl[3] = TYPE_S; }
+
+	// ---- stream in: A[i] holds, per owned cell, the population that load_f() assigns to fhn[i] ----
+	P A[Q];
+	const uint64_t row0 = row(L, y, z);
+	if(valid) {
+		A[0].load(fi+row0+col);
+		static_for<1, Q, 2>([&](auto I) {
+			constexpr int i = I;
+			const uint64_t sl = (uint64_t)(odd ? i : i+1)*L.slot, sn = (uint64_t)(odd ? i+1 : i)*L.slot;
+			const uint64_t rown = row(L, dir_y(i)>0 ? yp : dir_y(i)<0 ? ym : y, dir_z(i)>0 ? zp : dir_z(i)<0 ? zm : z);
+			A[i  ].load(fi+sl+row0+col);
+			A[i+1].load(fi+sn+rown+col); // aligned vector of the neighbour row; x-shift fixed up below
+		});
+	} else {
+		static_for<0, Q, 1>([&](auto I) { A[I] = P{}; });
+	}
+	static_for<1, Q, 2>([&](auto I) {
+		constexpr int i = I;
+		if constexpr(dir_x(i)!=0) {
+			const uint64_t sn = (uint64_t)(odd ? i+1 : i)*L.slot;
+			const uint64_t rown = row(L, dir_y(i)>0 ? yp : dir_y(i)<0 ? ym : y, dir_z(i)>0 ? zp : dir_z(i)<0 ? zm : z);
+			if constexpr(dir_x(i)>0) { // need elements x0+1..x0+4: take the right lane's first element
+				uint32_t b = __shfl_down_sync(FULL, A[i+1].first_bits(), 1u);
+				if(valid && !has_right) b = P::bits(fi[sn+rown+(uint64_t)(xr+L.xo)]);
+				A[i+1].push_back(b);
+			} else { // need elements x0-1..x0+2: take the left lane's last element
+				uint32_t b = __shfl_up_sync(FULL, A[i+1].last_bits(), 1u);
+				if(valid && !has_left) b = P::bits(fi[sn+rown+(uint64_t)(xl+L.xo)]);
+				A[i+1].push_front(b);
+			}
+		}
+	});
+
+	// ---- collide the owned cells one after the other ----
+	static_for<0, K, 1>([&](auto Cc) {
+		constexpr int c = Cc;
+		const uint32_t fb = fl[c]&TYPE_BO;
+		if(valid && fb!=TYPE_S) {
+			float f[Q];
+			static_for<0, Q, 1>([&](auto I) { f[I] = C::decode(A[I].template get<c>()); });
+			const bool is_e = L.eb!=0u && fb==TYPE_E;
+			float rho_e = 1.0f, ux_e = 0.0f, uy_e = 0.0f, uz_e = 0.0f;
+			const uint64_t n = lin(L, x0+(uint32_t)c, y, z), N = cells(L);
+			if(is_e) { rho_e = L.rho[n]; ux_e = L.u[n]; uy_e = L.u[N+n]; uz_e = L.u[2ull*N+n]; }
+			float rhon, uxn, uyn, uzn;
+			collide_cell<Q, COLL, VF>(f, is_e, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+			if(L.upd!=0u && !is_e) { L.rho[n] = rhon; L.u[n] = uxn; L.u[N+n] = uyn; L.u[2ull*N+n] = uzn; }
+			// store_f(): fhn[i] goes to the neighbour-side slot, fhn[i+1] to the local slot
+			A[0].template set<c>(C::encode(f[0]));
+			static_for<1, Q, 2>([&](auto I) {
+				constexpr int i = I;
+				A[i+1].template set<c>(C::encode(f[i]));
+				A[i  ].template set<c>(C::encode(f[i+1]));
+			});
+		}
+	});
+
+	// ---- stream out (same addresses as stream in) ----
+	if(!__any_sync(FULL, any_active)) return; // nothing but solid cells in this warp: nothing changed
+	if(valid) A[0].store(fi+row0+col);
+	static_for<1, Q, 2>([&](auto I) {
+		constexpr int i = I;
+		const uint64_t sl = (uint64_t)(odd ? i : i+1)*L.slot, sn = (uint64_t)(odd ? i+1 : i)*L.slot;
+		const uint64_t rown = row(L, dir_y(i)>0 ? yp : dir_y(i)<0 ? ym : y, dir_z(i)>0 ? zp : dir_z(i)<0 ? zm : z);
+		if(valid) A[i].store(fi+sl+row0+col);
+		if constexpr(dir_x(i)==0) {
+			if(valid) A[i+1].store(fi+sn+rown+col);
+		} else if constexpr(dir_x(i)>0) { // my values belong to x0+1..x0+4
+			const uint32_t last = A[i+1].last_bits();
+			const uint32_t up = __shfl_up_sync(FULL, last, 1u);
+			if(valid) {
+				if(!has_right) fi[sn+rown+(uint64_t)(xr+L.xo)] = P::from_bits(last);
+				A[i+1].push_front(up); // {left lane's x0, mine x0+1..x0+3}
+				if(has_left) A[i+1].store(fi+sn+rown+col); else A[i+1].store_1_3(fi+sn+rown+col);
+			}
+		} else { // my values belong to x0-1..x0+2
+			const uint32_t first = A[i+1].first_bits();
+			const uint32_t dn = __shfl_down_sync(FULL, first, 1u);
+			if(valid) {
+				if(!has_left) fi[sn+rown+(uint64_t)(xl+L.xo)] = P::from_bits(first);
+				A[i+1].push_back(dn); // {mine x0..x0+2, right lane's x0+3}
+				if(has_right) A[i+1].store(fi+sn+rown+col); else A[i+1].store_0_2(fi+sn+rown+col);
+			}
+		}
+	});
+}
+
+// ================================================================================================================
+// scalar cell access shared by the general kernels (any Nx): one thread per cell, addresses as load_f/store_f
+// ================================================================================================================
+template<int Q, int ST> struct CellIO {
+	typedef Codec<ST> C;
+	typedef typename C::elem_t E;
+	uint64_t here, nb[Q]; // physical offsets (without slot) of the cell and of its "+" neighbours (odd i)
+	FX3D_HD void locate(const Lattice& L, uint32_t x, uint32_t y, uint32_t z) {
+		here = phys(L, x, y, z);
+		static_for<1, Q, 2>([&](auto I) {
+			constexpr int i = I;
+			nb[i] = phys(L, step<dir_x(i)>(x, L.Nx), step<dir_y(i)>(y, L.Ny), step<dir_z(i)>(z, L.Nz));
+		});
+	}
+	FX3D_HD void pull(const Lattice& L, uint32_t odd, float (&f)[Q]) const { // load_f, src/kernel.cpp:1326-1332
+		const E* fi = reinterpret_cast<const E*>(L.fi);
+		f[0] = C::decode(fi[here]);
+		static_for<1, Q, 2>([&](auto I) {
+			constexpr int i = I;
+			f[i  ] = C::decode(fi[(uint64_t)(odd ? i : i+1)*L.slot+here]);
+			f[i+1] = C::decode(fi[(uint64_t)(odd ? i+1 : i)*L.slot+nb[i]]);
+		});
+	}
+	FX3D_HD void push(const Lattice& L, uint32_t odd, const float (&f)[Q]) const { // store_f, src/kernel.cpp:1333-1339
+		E* fi = reinterpret_cast<E*>(L.fi);
+		fi[here] = C::encode(f[0]);
+		static_for<1, Q, 2>([&](auto I) {
+			constexpr int i = I;
+			fi[(uint64_t)(odd ? i+1 : i)*L.slot+nb[i]] = C::encode(f[i]);
+			fi[(uint64_t)(odd ? i : i+1)*L.slot+here] = C::encode(f[i+1]);
+		});
+	}
+};
+
+FX3D_HD bool region_cell(const Region& R, uint32_t& x, uint32_t& y, uint32_t& z) { // g0/g1 are plain x bounds here
+	x = R.g0+blockIdx.x*blockDim.x+threadIdx.x; y = R.y0+blockIdx.y*blockDim.y+threadIdx.y; z = R.z0+blockIdx.z;
+	return x<R.g1 && y<R.y1;
+}
+
+// general stream_collide (any grid size): one thread per cell, scalar accesses -- the reference's own access pattern
+template<int Q, int COLL, int ST, bool VF>
+__global__ void __launch_bounds__(128) k_stream_collide_v1(const Lattice L, const Region R) {
+	uint32_t x, y, z;
+	if(!region_cell(R, x, y, z)) return;
+	const uint64_t n = lin(L, x, y, z), N = cells(L);
+	const uint32_t fb = L.flags[n]&TYPE_BO;
+	if(fb==TYPE_S) return;
+	CellIO<Q, ST> io; io.locate(L, x, y, z);
+	float f[Q];
+	io.pull(L, L.odd, f);
+	const bool is_e = L.eb!=0u && fb==TYPE_E;
+	float rho_e = 1.0f, ux_e = 0.0f, uy_e = 0.0f, uz_e = 0.0f;
+	if(is_e) { rho_e = L.rho[n]; ux_e = L.u[n]; uy_e = L.u[N+n]; uz_e = L.u[2ull*N+n]; }
+	float rhon, uxn, uyn, uzn;
+	collide_cell<Q, COLL, VF>(f, is_e, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+	if(L.upd!=0u && !is_e) { L.rho[n] = rhon; L.u[n] = uxn; L.u[N+n] = uyn; L.u[2ull*N+n] = uzn; }
+	io.push(L, L.odd, f);
+}
+
+// initialize, src/kernel.cpp:1358-1430 (build without MOVING_BOUNDARIES / SURFACE / TEMPERATURE)
+template<int Q, int ST>
+__global__ void __launch_bounds__(128) k_initialize(const Lattice L, const Region R) {
+	uint32_t x, y, z;
+	if(!region_cell(R, x, y, z)) return;
+	const uint64_t n = lin(L, x, y, z), N = cells(L);
+	if((L.flags[n]&TYPE_BO)==TYPE_S) { L.u[n] = 0.0f; L.u[N+n] = 0.0f; L.u[2ull*N+n] = 0.0f; }
+	float feq[Q];
+	equilibrium<Q>(L.rho[n], L.u[n], L.u[N+n], L.u[2ull*N+n], feq);
+	CellIO<Q, ST> io; io.locate(L, x, y, z);
+	io.push(L, 1u, feq); // odd-step layout is baked in (:1429)
+}
+
+// update_fields, src/kernel.cpp:1794-1870
+template<int Q, int ST, bool VF>
+__global__ void __launch_bounds__(128) k_update_fields(const Lattice L, const Region R) {
+	uint32_t x, y, z;
+	if(!region_cell(R, x, y, z)) return;
+	const uint64_t n = lin(L, x, y, z), N = cells(L);
+	const uint32_t fb = L.flags[n]&TYPE_BO;
+	if(fb==TYPE_S) return;
+	CellIO<Q, ST> io; io.locate(L, x, y, z);
+	float f[Q];
+	io.pull(L, L.odd, f);
+	float rhon, uxn, uyn, uzn;
+	fields_of_cell<Q, VF>(f, L.fx, L.fy, L.fz, rhon, uxn, uyn, uzn);
+	if(L.eb!=0u && fb==TYPE_E) return;
+	L.rho[n] = rhon; L.u[n] = uxn; L.u[N+n] = uyn; L.u[2ull*N+n] = uzn;
+}
+
+// ================================================================================================================
+// halo transfer. Direction lists per face side (position b pairs opposite directions on the two sides),
+// src/kernel.cpp:2069-2101; face-cell decomposition of a per axis :2053-2068.
+// ================================================================================================================
+template<int Q> FX3D_HDC constexpr int transfers() { return Q==19 ? 5 : 9; }
+template<int Q> FX3D_HDC constexpr int xfer_dir(int side, int b) {
+	if constexpr(Q==19) {
+		constexpr uint8_t t[6][5] = { { 1, 7,13, 9,15 }, { 2, 8,14,10,16 }, { 3, 7,14,11,17 }, { 4, 8,13,12,18 }, { 5, 9,16,11,18 }, { 6,10,15,12,17 } };
+		return t[side][b];
+	} else {
+		constexpr uint8_t t[6][9] = { { 1, 7,13, 9,15,19,26,21,23 }, { 2, 8,14,10,16,20,25,22,24 }, { 3, 7,14,11,17,19,24,21,25 },
+			{ 4, 8,13,12,18,20,23,22,26 }, { 5, 9,16,11,18,19,22,23,25 }, { 6,10,15,12,17,20,21,24,26 } };
+		return t[side][b];
+	}
+}
+FX3D_HD uint32_t face_area(const Lattice& L, uint32_t axis) { return axis==0u ? L.Ny*L.Nz : axis==1u ? L.Nz*L.Nx : L.Nx*L.Ny; }
+FX3D_HD uint32_t axis_len(const Lattice& L, uint32_t axis) { return axis==0u ? L.Nx : axis==1u ? L.Ny : L.Nz; }
+FX3D_HD void face_coords(const Lattice& L, uint32_t axis, uint32_t a, uint32_t layer, uint32_t& x, uint32_t& y, uint32_t& z) {
+	if(axis==0u) { x = layer; y = a%L.Ny; z = a/L.Ny; }
+	else if(axis==1u) { x = a/L.Nz; y = layer; z = a%L.Nz; }
+	else { x = a%L.Nx; y = a/L.Nx; z = layer; }
+}
+// physical offset (slot included) that extract_fi() reads for direction i at face cell (x,y,z), src/kernel.cpp:2102-2110
+FX3D_HD uint64_t extract_addr(const Lattice& L, uint32_t odd, int i, uint32_t x, uint32_t y, uint32_t z) {
+	const uint32_t slot = odd ? ((i&1) ? i+1 : i-1) : i;
+	if(i&1) { x = step_rt(dir_x(i), x, L.Nx); y = step_rt(dir_y(i), y, L.Ny); z = step_rt(dir_z(i), z, L.Nz); } // cell j[i]
+	return (uint64_t)slot*L.slot+phys(L, x, y, z);
+}
+// physical offset that insert_fi() writes for direction i at face cell (x,y,z), src/kernel.cpp:2111-2119
+FX3D_HD uint64_t insert_addr(const Lattice& L, uint32_t odd, int i, uint32_t x, uint32_t y, uint32_t z) {
+	const uint32_t slot = odd ? i : ((i&1) ? i+1 : i-1);
+	if(!(i&1)) { x = step_rt(dir_x(i-1), x, L.Nx); y = step_rt(dir_y(i-1), y, L.Ny); z = step_rt(dir_z(i-1), z, L.Nz); } // cell j[i-1]
+	return (uint64_t)slot*L.slot+phys(L, x, y, z);
+}
+
+// staged transfer through linear buffers laid out buf[b*A+a] like the reference's (kept for interface parity and as
+// the building block of host-staged exchange): EXTRACT=true transfer_extract_fi, false transfer__insert_fi
+template<int Q, int ST, bool EXTRACT>
+__global__ void __launch_bounds__(128) k_transfer_fi(const Lattice L, const uint32_t axis, void* buf_p, void* buf_m) {
+	typedef typename Codec<ST>::elem_t E;
+	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x, A = face_area(L, axis), len = axis_len(L, axis);
+	if(a>=A) return;
+	E* fi = reinterpret_cast<E*>(L.fi);
+	E* bp = reinterpret_cast<E*>(buf_p); E* bm = reinterpret_cast<E*>(buf_m);
+	uint32_t x, y, z;
+	face_coords(L, axis, a, EXTRACT ? len-2u : len-1u, x, y, z);
+	for(int b=0; b<transfers<Q>(); b++) {
+		const int i = xfer_dir<Q>(2*(int)axis, b);
+		if(EXTRACT) bp[(uint64_t)b*A+a] = fi[extract_addr(L, L.odd, i, x, y, z)]; else fi[insert_addr(L, L.odd, i, x, y, z)] = bp[(uint64_t)b*A+a];
+	}
+	face_coords(L, axis, a, EXTRACT ? 1u : 0u, x, y, z);
+	for(int b=0; b<transfers<Q>(); b++) {
+		const int i = xfer_dir<Q>(2*(int)axis+1, b);
+		if(EXTRACT) bm[(uint64_t)b*A+a] = fi[extract_addr(L, L.odd, i, x, y, z)]; else fi[insert_addr(L, L.odd, i, x, y, z)] = bm[(uint64_t)b*A+a];
+	}
+}
+// rho/u/flags halo: 4 float planes then one byte plane at byte 16*A, src/kernel.cpp:2133-2158
+template<bool EXTRACT>
+__global__ void __launch_bounds__(128) k_transfer_rho_u_flags(const Lattice L, const uint32_t axis, void* buf_p, void* buf_m) {
+	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x, A = face_area(L, axis), len = axis_len(L, axis);
+	if(a>=A) return;
+	const uint64_t N = cells(L);
+	uint32_t x, y, z;
+	for(int side=0; side<2; side++) {
+		face_coords(L, axis, a, side==0 ? (EXTRACT ? len-2u : len-1u) : (EXTRACT ? 1u : 0u), x, y, z);
+		const uint64_t n = lin(L, x, y, z);
+		float* fb = reinterpret_cast<float*>(side==0 ? buf_p : buf_m);
+		uint8_t* cb = reinterpret_cast<uint8_t*>(side==0 ? buf_p : buf_m);
+		if(EXTRACT) {
+			fb[a] = L.rho[n]; fb[A+a] = L.u[n]; fb[2ull*A+a] = L.u[N+n]; fb[3ull*A+a] = L.u[2ull*N+n]; cb[16ull*A+a] = L.flags[n];
+		} else {
+			L.rho[n] = fb[a]; L.u[n] = fb[A+a]; L.u[N+n] = fb[2ull*A+a]; L.u[2ull*N+n] = fb[3ull*A+a]; L.flags[n] = cb[16ull*A+a];
+		}
+	}
+}
+
+// Direct peer exchange of one axis: every face cell pulls, over NVLink peer loads (or the same GPU), exactly the
+// raw DDF bits that the reference's extract -> host swap -> insert sequence would have delivered
+// (src/lbm.cpp:1355-1383: domain d's "+" buffer goes to its +axis neighbour's "-" side and vice versa).
+//   my layer len-1 ("+" insert, list p)  <-  +axis neighbour's "-" extract at its layer 1   (list m)
+//   my layer 0     ("-" insert, list m)  <-  -axis neighbour's "+" extract at its layer len-2 (list p)
+// All domains have identical local geometry, so the neighbour's addresses follow from my Lattice.
+template<int Q, int ST>
+__global__ void __launch_bounds__(128) k_exchange_fi(const Lattice L, const uint32_t axis, const void* fi_plus, const void* fi_minus) {
+	typedef typename Codec<ST>::elem_t E;
+	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x, A = face_area(L, axis), len = axis_len(L, axis);
+	if(a>=A) return;
+	E* fi = reinterpret_cast<E*>(L.fi);
+	const E* fp = reinterpret_cast<const E*>(fi_plus); const E* fm = reinterpret_cast<const E*>(fi_minus);
+	uint32_t xi, yi, zi, xe, ye, ze;
+	face_coords(L, axis, a, len-1u, xi, yi, zi); face_coords(L, axis, a, 1u, xe, ye, ze);
+	for(int b=0; b<transfers<Q>(); b++)
+		fi[insert_addr(L, L.odd, xfer_dir<Q>(2*(int)axis, b), xi, yi, zi)] = fp[extract_addr(L, L.odd, xfer_dir<Q>(2*(int)axis+1, b), xe, ye, ze)];
+	face_coords(L, axis, a, 0u, xi, yi, zi); face_coords(L, axis, a, len-2u, xe, ye, ze);
+	for(int b=0; b<transfers<Q>(); b++)
+		fi[insert_addr(L, L.odd, xfer_dir<Q>(2*(int)axis+1, b), xi, yi, zi)] = fm[extract_addr(L, L.odd, xfer_dir<Q>(2*(int)axis, b), xe, ye, ze)];
+}
+struct PeerFields { const float* rho; const float* u; const uint8_t* flags; };
+#if defined(FX3D_TU_LBM) // non-template kernels are defined in exactly one translation unit
+__global__ void __launch_bounds__(128) k_exchange_rho_u_flags(const Lattice L, const uint32_t axis, const PeerFields plus, const PeerFields minus) {
+	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x, A = face_area(L, axis), len = axis_len(L, axis);
+	if(a>=A) return;
+	const uint64_t N = cells(L);
+	uint32_t x, y, z;
+	for(int side=0; side<2; side++) {
+		const PeerFields& src = side==0 ? plus : minus;
+		face_coords(L, axis, a, side==0 ? 1u : len-2u, x, y, z);
+		const uint64_t ns = lin(L, x, y, z);
+		face_coords(L, axis, a, side==0 ? len-1u : 0u, x, y, z);
+		const uint64_t nd = lin(L, x, y, z);
+		L.rho[nd] = src.rho[ns]; L.u[nd] = src.u[ns]; L.u[N+nd] = src.u[N+ns]; L.u[2ull*N+nd] = src.u[2ull*N+ns]; L.flags[nd] = src.flags[ns];
+	}
+}
+
+#endif // FX3D_TU_LBM
+
+// storage codec self-test: out[k] = encode(in[k]) with the fast and with the literal formula, dec[h] likewise
+template<int ST>
+__global__ void k_codec_encode(const float* in, uint16_t* out, uint64_t n) {
+	const uint64_t k = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x;
+	if(k<n) out[k] = Codec<ST>::encode(in[k]);
+}
+template<int ST>
+__global__ void k_codec_decode(const uint16_t* in, float* out, uint64_t n) {
+	const uint64_t k = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x;
+	if(k<n) out[k] = Codec<ST>::decode(in[k]);
+}
+#if defined(FX3D_TU_RUNTIME)
+// exhaustive check over all 2^32 binary32 inputs: counts inputs where the one-multiply FP16C encode differs from
+// the reference's literal formula (and all 2^16 codes for decode); NaN payloads excluded for decode comparisons
+__global__ void k_fp16c_exhaustive(unsigned long long* mismatches, uint32_t* first_bad) {
+	const uint64_t stride = (uint64_t)gridDim.x*blockDim.x;
+	unsigned long long bad = 0ull;
+	for(uint64_t k = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x; k<(1ull<<32); k += stride) {
+		const float x = __uint_as_float((uint32_t)k);
+		if(x!=x) continue; // NaN inputs are outside the contract
+		if(fp16c_encode(x)!=fp16c_encode_literal(x)) { if(bad==0ull) first_bad[0] = (uint32_t)k; bad++; }
+		if(k<65536ull) {
+			const float a = fp16c_decode((uint16_t)k), b = fp16c_decode_literal((uint16_t)k);
+			if(__float_as_uint(a)!=__float_as_uint(b)) { if(bad==0ull) first_bad[0] = (uint32_t)k; bad++; }
+		}
+	}
+	if(bad) {
+#if defined(FX3D_HOST_EMULATION)
+		*mismatches += bad;
+#else
+		atomicAdd(mismatches, bad);
+#endif
+	}
+}
+#endif // FX3D_TU_RUNTIME
+
+} // namespace fx3d

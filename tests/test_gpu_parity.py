@@ -1,0 +1,262 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI by the product's host
+classes, against the CPU oracle on identical seeded inputs -- bit-exact fields (both follow the reference's operation
+order), bit-exact flags and FP16 pack/unpack -- plus the committed golden vectors (made from the reference's own device
+code) and size-independent properties at the BASELINE sizes."""
+import ctypes as C
+import glob
+import os
+import numpy as np
+import pytest
+from helpers import (ROOT, OracleBackend, HostSim, scenario, load_scenario, FP32, FP16S, FP16C, SRT, TRT, VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, TYPE_S, TYPE_E)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fx():
+    import fluidx3d_b200 as fx
+    from fluidx3d_b200 import lbm as lbm_mod, capi
+    lbm_mod.VERBOSE = False
+    lib = capi.lib()
+    assert lib.num_devices() >= 1
+    return fx
+
+
+def bits(a):
+    return a.view(np.uint32) if a.dtype == np.float32 else a
+
+
+def product(fx, v, dims, D, steps, f, variant=0, nu=0.05, seed=3, scen=None, w=None):
+    from fluidx3d_b200 import capi
+    Q, coll, st, feat = v
+    capi.lib().set_kernel_variant(variant)
+    sim = fx.LBM(*dims, nu, *f, Dx=D[0], Dy=D[1], Dz=D[2], velocity_set=Q, collision=coll, storage=st, features=feat, devices=[0] * (D[0] * D[1] * D[2]))
+    if w is not None:
+        for _, dom in sim.local_domains(): dom.lat.w = w
+    rho, u, flags = scen if scen is not None else scenario(sim.Nx, sim.Ny, sim.Nz, seed=seed, eq_frac=0.03 if feat & 2 else 0.0)
+    sim.rho.set_global(rho); [sim.u.set_global(u[a], a) for a in range(3)]; sim.flags.set_global(flags)
+    sim.run(steps)
+    for m in (sim.rho, sim.u, sim.flags): m.read_from_device()
+    out = (sim.rho.get_global(), sim.u.get_global(0), sim.u.get_global(1), sim.u.get_global(2), sim.flags.get_global())
+    sim.close()
+    capi.lib().set_kernel_variant(0)
+    return out
+
+
+def oracle(v, dims, D, steps, f, nu=0.05, seed=3, scen=None, w=None):
+    Q, coll, st, feat = v
+    sim = HostSim(OracleBackend(Q, coll, st, feat), *dims, *D, nu=nu, w=w, fx=f[0], fy=f[1], fz=f[2])
+    load_scenario(sim, *(scen if scen is not None else scenario(sim.Nx, sim.Ny, sim.Nz, seed=seed, eq_frac=0.03 if feat & 2 else 0.0)))
+    sim.run(steps)
+    return sim.fields()
+
+
+VARIANTS = [(19, SRT, FP32, 0), (19, SRT, FP16S, 0), (19, SRT, FP16C, 0), (19, TRT, FP32, 0), (19, SRT, FP32, 1), (19, SRT, FP32, 2), (19, TRT, FP16S, 3),
+            (19, SRT, FP32, 4), (27, SRT, FP32, 0), (27, TRT, FP32, 3), (27, SRT, FP16S, 0), (27, TRT, FP16C, 3), (27, SRT, FP16C, 1), (19, TRT, FP16C, 2)]
+VID = [f"q{v[0]}c{v[1]}s{v[2]}f{v[3]}" for v in VARIANTS]
+
+
+@pytest.mark.parametrize("v", VARIANTS, ids=VID)
+@pytest.mark.parametrize("variant", [0, 1], ids=["vector4", "general"])
+def test_fields_bit_exact_small(fx, v, variant):
+    f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
+    for dims, steps in [((32, 12, 10), 1), ((32, 12, 10), 2), ((32, 12, 10), 3), ((64, 9, 7), 10), ((20, 6, 5), 5), ((7, 5, 3), 4), ((132, 4, 3), 3)]:
+        got, want = product(fx, v, dims, (1, 1, 1), steps, f, variant), oracle(v, dims, (1, 1, 1), steps, f)
+        for a, b in zip(got, want):
+            assert np.array_equal(bits(a), bits(b)), (dims, steps)
+
+
+@pytest.mark.parametrize("v", [(19, SRT, FP32, 0), (19, SRT, FP16S, 0), (19, SRT, FP16C, 0), (27, TRT, FP32, 3)], ids=["fp32", "fp16s", "fp16c", "q27trt"])
+def test_fields_bit_exact_medium_100_steps(fx, v):
+    # SURVEY 8d parity fixtures: 64^3 and the non-cubic 96x64x48, perturbed IC, 100 steps
+    f = (0.0, 1e-6, 0.0) if v[3] & 1 else (0.0, 0.0, 0.0)
+    for dims in [(64, 64, 64), (96, 64, 48)]:
+        got, want = product(fx, v, dims, (1, 1, 1), 100, f), oracle(v, dims, (1, 1, 1), 100, f)
+        for a, b in zip(got, want):
+            assert np.array_equal(bits(a), bits(b)), dims
+
+
+@pytest.mark.parametrize("D", [(2, 1, 1), (1, 2, 1), (1, 1, 2), (2, 2, 1), (2, 2, 2), (4, 1, 2)], ids=lambda d: "d" + "".join(map(str, d)))
+@pytest.mark.parametrize("v", [(19, SRT, FP32, 0), (19, SRT, FP16C, 0), (27, TRT, FP16S, 3)], ids=["fp32", "fp16c", "q27trt16s"])
+def test_decomposed_domains_bit_identical_to_single(fx, v, D):
+    # D domains time-sharing one GPU, direct exchange kernels + rendezvous; result must equal the unsplit run (and the oracle)
+    f = (1e-4, 0.0, -1e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
+    dims = (32, 16, 8)
+    for steps in (1, 6):
+        single, split, want = product(fx, v, dims, (1, 1, 1), steps, f), product(fx, v, dims, D, steps, f), oracle(v, dims, D, steps, f)
+        for a, b, c in zip(single, split, want):
+            assert np.array_equal(bits(a), bits(b)) and np.array_equal(bits(b), bits(c))
+
+
+def test_c4_fixture_64cube_split_2x2x2_bit_identical(fx):
+    v = (19, SRT, FP16C, 0)
+    single, split = product(fx, v, (64, 64, 64), (1, 1, 1), 20, (0, 0, 0)), product(fx, v, (64, 64, 64), (2, 2, 2), 20, (0, 0, 0))
+    for a, b in zip(single, split):
+        assert np.array_equal(bits(a), bits(b))
+
+
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "q*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_vectors_from_reference_device_code(fx, path):
+    g = np.load(path)
+    Q, coll, st, feat, Nx, Ny, Nz, Dx, Dy, Dz, steps = (int(x) for x in g["meta"])
+    f = tuple(float(x) for x in g["force"])
+    for variant in (0, 1):
+        rho, ux, uy, uz, flags = product(fx, (Q, coll, st, feat), (Nx, Ny, Nz), (Dx, Dy, Dz), steps, f, variant, nu=float(g["nu"]), scen=(g["in_rho"], list(g["in_u"]), g["in_flags"]))
+        assert np.array_equal(flags, g["out_flags"])
+        assert np.array_equal(bits(rho), bits(g["out_rho"]))
+        assert np.array_equal(bits(np.stack([ux, uy, uz])), bits(g["out_u"]))
+
+
+def test_fp16c_fast_codec_exhaustive_all_2_32_inputs(fx):
+    from fluidx3d_b200 import capi
+    bad, first = C.c_uint64(0), C.c_uint32(0)
+    capi.lib().codec_fp16c_exhaustive(0, C.byref(bad), C.byref(first))
+    assert bad.value == 0, f"first mismatch at bits 0x{first.value:08x}"
+
+
+@pytest.mark.parametrize("storage", [FP16S, FP16C], ids=["fp16s", "fp16c"])
+def test_codec_bit_exact_against_oracle_and_golden(fx, storage):
+    from fluidx3d_b200 import capi
+    lib = capi.lib()
+    orc = OracleBackend()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "fp16c_codec.npz"))
+    xs = g["encode_in"].view(np.float32)
+    n = xs.size
+    d_in, d_out = C.c_void_p(), C.c_void_p()
+    lib.malloc(0, n * 4, C.byref(d_in)); lib.malloc(0, n * 2, C.byref(d_out))
+    lib.memcpy_h2d(0, d_in, xs.ctypes.data, n * 4, None, 1)
+    lib.codec_encode(0, storage, d_in, d_out, n, None)
+    got = np.zeros(n, np.uint16)
+    lib.memcpy_d2h(0, got.ctypes.data, d_out, n * 2, None, 1)
+    enc = orc.lib.orc_fp16c_encode if storage == FP16C else orc.lib.orc_fp16s_encode
+    want = np.array([enc(float(x)) for x in xs], dtype=np.uint16)
+    assert np.array_equal(got, want)
+    if storage == FP16C:
+        assert np.array_equal(got, g["encode_out"])
+    codes = np.arange(65536, dtype=np.uint16)
+    lib.memcpy_h2d(0, d_out, codes.ctypes.data, 65536 * 2, None, 1)
+    lib.codec_decode(0, storage, d_out, d_in, 65536, None)
+    dec = np.zeros(65536, np.float32)
+    lib.memcpy_d2h(0, dec.ctypes.data, d_in, 65536 * 4, None, 1)
+    fdec = orc.lib.orc_fp16c_decode if storage == FP16C else orc.lib.orc_fp16s_decode
+    want_d = np.array([fdec(int(c)) for c in codes], dtype=np.float32)
+    finite = np.isfinite(want_d)
+    assert np.array_equal(dec[finite].view(np.uint32), want_d[finite].view(np.uint32))
+    if storage == FP16C:
+        assert np.array_equal(dec.view(np.uint32), g["decode_all_codes"])
+    lib.free(0, d_in); lib.free(0, d_out)
+
+
+def test_transfer_kernels_match_oracle_buffers(fx):
+    # the staged transfer_extract_fi / transfer__insert_fi pair: same linear buffer contents as the reference layout buf[b*A+a]
+    from fluidx3d_b200 import capi
+    lib = capi.lib()
+    for (Q, st) in [(19, FP32), (27, FP16S)]:
+        dims, D = (16, 8, 6), (2, 2, 2)
+        sim = fx.LBM(*dims, 0.05, Dx=2, Dy=2, Dz=2, velocity_set=Q, storage=st, devices=[0] * 8)
+        ref = HostSim(OracleBackend(Q, SRT, st, 0), *dims, *D, nu=0.05)
+        scen = scenario(*dims, seed=8)
+        sim.rho.set_global(scen[0]); [sim.u.set_global(scen[1][a], a) for a in range(3)]; sim.flags.set_global(scen[2])
+        load_scenario(ref, *scen)
+        sim.run(3); ref.run(3)
+        dom, rdom = sim.lbm_domain[0], ref.dom[0]
+        nbytes = lib.transfer_bytes(C.byref(dom.lat))
+        bp, bm = C.c_void_p(), C.c_void_p()
+        lib.malloc(0, nbytes, C.byref(bp)); lib.malloc(0, nbytes, C.byref(bm))
+        esz = 4 if st == FP32 else 2
+        T = 5 if Q == 19 else 9
+        for axis in range(3):
+            lib.transfer_extract_fi(C.byref(dom.lat), axis, dom.t, bp, bm, dom.stream)
+            hp, hm = np.zeros(nbytes, np.uint8), np.zeros(nbytes, np.uint8)
+            lib.memcpy_d2h(0, hp.ctypes.data, bp, nbytes, dom.stream, 1); lib.memcpy_d2h(0, hm.ctypes.data, bm, nbytes, dom.stream, 1)
+            ref.b.extract_fi(axis, ref.t, rdom.buf_p, rdom.buf_m, rdom.fi)
+            A = [dom.Ny * dom.Nz, dom.Nz * dom.Nx, dom.Nx * dom.Ny][axis]
+            assert np.array_equal(hp[:A * T * esz], rdom.buf_p[:A * T * esz]) and np.array_equal(hm[:A * T * esz], rdom.buf_m[:A * T * esz])
+        lib.free(0, bp); lib.free(0, bm)
+        sim.close()
+
+
+def test_mass_conservation_and_finite_at_baseline_size(fx):
+    # C1 size (256^3 FP32) with the perturbed IC: total mass conserved, fields finite, after an even number of steps
+    N = 256
+    sim = fx.LBM(N, N, N, 1.0, velocity_set=19, collision=SRT, storage=FP32)
+    rho, u, flags = scenario(N, N, N, seed=1, solid_frac=0.0)
+    sim.rho.set_global(rho); [sim.u.set_global(u[a], a) for a in range(3)]; sim.flags.set_global(flags)
+    sim.run(0); sim.rho.read_from_device()
+    m0 = float(np.sum(sim.rho.get_global().astype(np.float64) - 1.0))
+    sim.run(50); sim.rho.read_from_device(); sim.u.read_from_device()
+    r = sim.rho.get_global()
+    m1 = float(np.sum(r.astype(np.float64) - 1.0))
+    assert np.isfinite(r).all() and np.isfinite(sim.u.get_global(0)).all()
+    assert abs(m1 - m0) < 1e-6 * N ** 3
+    sim.close()
+
+
+def test_fluid_at_rest_stays_at_rest_fp16s_512(fx):
+    # C2 (512^3 FP16S periodic, default fields): rho=1, u=0 is a fixed point of the scheme, bit for bit
+    sim = fx.LBM(512, 512, 512, 1.0, velocity_set=19, collision=SRT, storage=FP16S)
+    sim.run(10); sim.rho.read_from_device(); sim.u.read_from_device()
+    assert np.all(sim.rho.get_global() == 1.0) and np.all(sim.u.get_global(0) == 0.0) and np.all(sim.u.get_global(2) == 0.0)
+    sim.close()
+
+
+def test_poiseuille_flow(fx):
+    # src/setup.cpp:84-144 with R=31: L2 error of the parabolic profile within the reference's quoted 2-5 % (FP32 and FP16S)
+    R, umax, tau = 31, 0.1, 1.0
+    nu = (tau - 0.5) / 3.0
+    H = 2 * (R + 1)
+    f = 4.0 * umax * nu / R ** 2
+    zz, yy, xx = np.meshgrid(np.arange(H), np.arange(4), np.arange(H), indexing="ij")
+    rr = np.sqrt((xx - (0.5 * H - 0.5)) ** 2 + (zz - (0.5 * H - 0.5)) ** 2)
+    flags = np.where(rr ** 2 <= (0.5 * H - 1.0) ** 2, 0, TYPE_S).astype(np.uint8)
+    for st, tol in [(FP32, 0.05), (FP16S, 0.05), (FP16C, 0.05)]:
+        sim = fx.LBM(H, 4, H, nu, 0.0, f, 0.0, velocity_set=19, collision=SRT, storage=st, features=VOLUME_FORCE)
+        sim.flags.set_global(flags)
+        sim.run(12000); sim.u.read_from_device()
+        unum = np.sqrt(sum(sim.u.get_global(a).astype(np.float64) ** 2 for a in range(3)))[:, 2, :]
+        r = np.sqrt((xx + 0.5 - 0.5 * H) ** 2 + (zz + 0.5 - 0.5 * H) ** 2)[:, 2, :]
+        uref = umax * (R ** 2 - r ** 2) / R ** 2
+        m = r < R
+        err = np.sqrt(np.sum((unum[m] - uref[m]) ** 2) / np.sum(uref[m] ** 2))
+        assert err < tol, (st, err)
+        sim.close()
+
+
+def test_taylor_green_decay(fx):
+    N, nu, A = 128, 0.02, 0.05
+    zz, yy, xx = np.meshgrid(np.arange(4), np.arange(N), np.arange(N), indexing="ij")
+    k = 2 * np.pi / N
+    px, py = xx + 0.5 - 0.5 * N, yy + 0.5 - 0.5 * N
+    ux = (A * np.cos(k * px) * np.sin(k * py)).astype(np.float32)
+    uy = (-A * np.sin(k * px) * np.cos(k * py)).astype(np.float32)
+    rho = (1.0 - A * A * 3.0 / 4.0 * (np.cos(2 * k * px) + np.cos(2 * k * py))).astype(np.float32)
+    for st in (FP32, FP16S):
+        sim = fx.LBM(N, N, 4, nu, velocity_set=19, collision=SRT, storage=st)
+        sim.rho.set_global(rho); sim.u.set_global(ux, 0); sim.u.set_global(uy, 1)
+        sim.run(0); sim.u.read_from_device()
+        e0 = float(np.sum(sim.u.get_global(0).astype(np.float64) ** 2))
+        T = 2000
+        sim.run(T); sim.u.read_from_device()
+        e1 = float(np.sum(sim.u.get_global(0).astype(np.float64) ** 2))
+        rate = -np.log(e1 / e0) / (2 * T)
+        assert rate == pytest.approx(nu * 2 * k * k, rel=0.02), st
+        sim.close()
+
+
+def test_error_behaviour(fx):
+    from fluidx3d_b200 import capi
+    lib = capi.lib()
+    lat = capi.Lattice(0, 8, 8, 8, 1, 1, 1, 15, 0, 0, 0, 1.0, None, None, None, None)  # D3Q15 is not on the path
+    with pytest.raises(capi.Fx3dError) as e:
+        lib.stream_collide(C.byref(lat), 0, 0.0, 0.0, 0.0, 0, None)
+    assert e.value.code == capi.ERR_INVALID and "velocity_set" in str(e.value)
+    with pytest.raises(capi.Fx3dError):
+        p = C.c_void_p(); lib.malloc(0, 1 << 60, C.byref(p))
+    sim = fx.LBM(8, 8, 8, 0.1)
+    sim.flags.set_global(np.full((8, 8, 8), TYPE_E, np.uint8))
+    with pytest.raises(ValueError):  # TYPE_E without EQUILIBRIUM_BOUNDARIES is fatal in the reference (src/lbm.cpp:866)
+        sim.run(1)
+    sim.close()

@@ -1,0 +1,90 @@
+"""Product host logic (fluidx3d_b200/lbm.py) + product kernel sources, compiled against tests/emul/cuda_emul.hpp and run
+as OS threads on the CPU, against the oracle. This is a development aid for a GPU-less container: it checks addressing,
+warp-shuffle hand-over, pack/unpack and operation order of the kernels; the GPU parity tests (-m gpu) are the gate."""
+import os
+import subprocess
+import numpy as np
+import pytest
+from helpers import (ROOT, OracleBackend, HostSim, scenario, load_scenario, FP32, FP16S, FP16C, SRT, TRT)
+from fluidx3d_b200 import capi
+from fluidx3d_b200 import lbm as lbm_mod
+from fluidx3d_b200.lbm import LBM
+
+lbm_mod.VERBOSE = False
+EMUL_SO = os.path.join(ROOT, "tests", "_build", "libfx3d_emul.so")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    subprocess.run(["make", "-j8", "-C", os.path.join(ROOT, "tests", "emul")], check=True, capture_output=True)
+    return capi.Lib(EMUL_SO)
+
+
+def bits(a):
+    return a.view(np.uint32) if a.dtype == np.float32 else a
+
+
+def product(lib, v, dims, D, steps, f, variant, nu=0.05, seed=3):
+    Q, coll, st, feat = v
+    lib.set_kernel_variant(variant)
+    sim = LBM(*dims, nu, *f, Dx=D[0], Dy=D[1], Dz=D[2], velocity_set=Q, collision=coll, storage=st, features=feat, lib=lib)
+    rho, u, flags = scenario(sim.Nx, sim.Ny, sim.Nz, seed=seed, eq_frac=0.03 if feat & 2 else 0.0)
+    sim.rho.set_global(rho); [sim.u.set_global(u[a], a) for a in range(3)]; sim.flags.set_global(flags)
+    sim.run(steps)
+    for m in (sim.rho, sim.u, sim.flags): m.read_from_device()
+    out = (sim.rho.get_global(), sim.u.get_global(0), sim.u.get_global(1), sim.u.get_global(2), sim.flags.get_global())
+    sim.close()
+    lib.set_kernel_variant(0)
+    return out
+
+
+def oracle(v, dims, D, steps, f, nu=0.05, seed=3):
+    Q, coll, st, feat = v
+    sim = HostSim(OracleBackend(Q, coll, st, feat), *dims, *D, nu=nu, fx=f[0], fy=f[1], fz=f[2])
+    load_scenario(sim, *scenario(sim.Nx, sim.Ny, sim.Nz, seed=seed, eq_frac=0.03 if feat & 2 else 0.0))
+    sim.run(steps)
+    return sim.fields()
+
+
+CASES = [((19, SRT, FP32, 0), (16, 6, 4), (1, 1, 1)), ((19, SRT, FP16S, 0), (16, 6, 4), (1, 1, 1)), ((19, SRT, FP16C, 0), (8, 6, 5), (1, 1, 1)),
+         ((19, TRT, FP32, 3), (16, 6, 6), (2, 1, 2)), ((27, TRT, FP32, 3), (8, 6, 5), (1, 1, 1)), ((27, SRT, FP16S, 0), (16, 6, 6), (2, 1, 2)),
+         ((19, SRT, FP16S, 0), (12, 6, 6), (2, 2, 1)), ((19, SRT, FP32, 0), (7, 6, 5), (1, 1, 1))]
+
+
+@pytest.mark.parametrize("v,dims,D", CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in CASES])
+@pytest.mark.parametrize("variant", [0, 1], ids=["vector4", "general"])
+def test_emulated_kernels_match_oracle(emul, v, dims, D, variant):
+    f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
+    for steps in (1, 4):
+        got, want = product(emul, v, dims, D, steps, f, variant), oracle(v, dims, D, steps, f)
+        for a, b in zip(got, want):
+            assert np.array_equal(bits(a), bits(b))
+
+
+def test_library_exports_every_declared_symbol():
+    # the product library itself (built by nvcc) must load without a GPU and export everything include/fx3d.h declares
+    import re
+    hdr = open(os.path.join(ROOT, "include", "fx3d.h")).read()
+    declared = set(re.findall(r"\b(fx3d_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(capi.EXPORTED_SYMBOLS), declared ^ set(capi.EXPORTED_SYMBOLS)
+    if not os.path.exists(capi.DEFAULT_LIB):
+        subprocess.run(["make", "-j8", "-C", os.path.join(ROOT, "fluidx3d_b200", "csrc")], check=True, capture_output=True)
+    capi.Lib()  # raises if a symbol is missing
+
+
+def test_relaxation_rate_matches_oracle_round_trip():
+    lib = capi.Lib()
+    orc = OracleBackend()
+    for nu in (1.0, 1.0 / 6.0, 0.01, 0.02, 0.05, 1e-3, 3.3e-5, 0.0062, 7.5e-4, 12.5):
+        assert np.float32(lib.relaxation_rate(nu)) == np.float32(orc.w_from_nu(nu))
+
+
+def test_constructor_checks():
+    lib = capi.Lib(EMUL_SO) if os.path.exists(EMUL_SO) else None
+    if lib is None:
+        pytest.skip("emulation library not built")
+    with pytest.raises(ValueError): LBM(0, 4, 4, 0.1, lib=lib)
+    with pytest.raises(ValueError): LBM(4, 4, 4, 0.0, lib=lib)
+    with pytest.raises(ValueError): LBM(4, 4, 4, -1.0, lib=lib)
+    with pytest.raises(ValueError): LBM(4, 4, 4, 0.1, 1e-3, 0.0, 0.0, lib=lib)  # force without VOLUME_FORCE
+    with pytest.raises(ValueError): LBM(4, 4, 4, 0.1, Dx=0, lib=lib)
