@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-DEFAULT_LIB = os.path.join(HERE, "libfx3d_cuda.so")
+DEFAULT_LIB = os.environ.get("FX3D_LIB", os.path.join(HERE, "libfx3d_cuda.so"))  # FX3D_LIB: alternative build of the same CUDA library (tuning experiments)
 
 FP32, FP16S, FP16C = 0, 1, 2
 SRT, TRT = 0, 1
@@ -83,6 +83,8 @@ _SIGS = {
     "fx3d_codec_encode": (_I, [_I, _I, _VP, _VP, _SZ, _VP], True),
     "fx3d_codec_decode": (_I, [_I, _I, _VP, _VP, _SZ, _VP], True),
     "fx3d_codec_fp16c_exhaustive": (_I, [_I, C.POINTER(_U64), C.POINTER(_U32)], True),
+    "fx3d_selftest_division": (_I, [_I, _U64, C.POINTER(_U64)], True),
+    "fx3d_selftest_packed_math": (_I, [_I, _U64, C.POINTER(_U64)], True),
 }
 EXPORTED_SYMBOLS = tuple(_SIGS)
 

@@ -38,6 +38,8 @@ inline bool make_lattice(const fx3d_lattice* in, uint64_t t, float fx, float fy,
 	L.xo = L.Hx ? 7u : 0u;
 	L.px = ((in->Nx+L.xo+63u)/64u)*64u;
 	L.slot = (uint64_t)L.px*in->Ny*in->Nz;
+	if(L.slot>0xFFFFFFFFull) { set_error("a domain may hold at most 2^32-1 (padded) cells"); return false; }
+	L.slot32 = (uint32_t)L.slot;
 	L.fi = in->fi; L.rho = in->rho; L.u = in->u; L.flags = in->flags;
 	L.w = in->w; L.fx = fx; L.fy = fy; L.fz = fz;
 	L.odd = (uint32_t)(t&1ull);

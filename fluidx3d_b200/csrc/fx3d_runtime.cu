@@ -275,4 +275,42 @@ int fx3d_codec_fp16c_exhaustive(int device, uint64_t* mismatches, uint32_t* firs
 	return FX3D_OK;
 }
 
+int fx3d_selftest_packed_math(int device, uint64_t samples, uint64_t* mismatches) {
+	if(!mismatches) return FX3D_ERR_INVALID;
+	if(int rc = use_device(device)) return rc;
+	unsigned long long* d_bad = nullptr;
+	FX3D_CUDA(cudaMalloc(&d_bad, sizeof(unsigned long long)), "cudaMalloc");
+	cudaMemset(d_bad, 0, sizeof(unsigned long long));
+	const dim3 g(148u), b(128u);
+	const unsigned long long per = (unsigned long long)(samples/(148u*128u)+1u);
+	FX3D_LAUNCH((k_selftest_lanes<19, COLL_SRT, false>), g, b, nullptr, per, 1.0f, d_bad);
+	FX3D_LAUNCH((k_selftest_lanes<19, COLL_SRT, false>), g, b, nullptr, per, 32768.0f, d_bad);
+	FX3D_LAUNCH((k_selftest_lanes<19, COLL_TRT, true>), g, b, nullptr, per, 1.0f, d_bad);
+	FX3D_LAUNCH((k_selftest_lanes<19, COLL_SRT, true>), g, b, nullptr, per, 32768.0f, d_bad);
+	FX3D_LAUNCH((k_selftest_lanes<27, COLL_TRT, true>), g, b, nullptr, per, 32768.0f, d_bad);
+	FX3D_LAUNCH((k_selftest_lanes<27, COLL_SRT, false>), g, b, nullptr, per, 1.0f, d_bad);
+	FX3D_LAUNCH((k_selftest_lanes<27, COLL_TRT, false>), g, b, nullptr, per, 1.0f, d_bad);
+	unsigned long long bad = 0ull;
+	const cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+	cudaFree(d_bad);
+	if(e!=cudaSuccess) return cuda_fail(e, "packed-math self-test");
+	*mismatches = (uint64_t)bad;
+	return FX3D_OK;
+}
+int fx3d_selftest_division(int device, uint64_t samples, uint64_t* mismatches) {
+	if(!mismatches) return FX3D_ERR_INVALID;
+	if(int rc = use_device(device)) return rc;
+	unsigned long long* d_bad = nullptr;
+	FX3D_CUDA(cudaMalloc(&d_bad, sizeof(unsigned long long)), "cudaMalloc");
+	cudaMemset(d_bad, 0, sizeof(unsigned long long));
+	const unsigned threads = 148u*8u*256u;
+	FX3D_LAUNCH(k_selftest_division, dim3(148u*8u), dim3(256u), nullptr, (unsigned long long)((samples+threads-1u)/threads), d_bad);
+	unsigned long long bad = 0ull;
+	const cudaError_t e = cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost);
+	cudaFree(d_bad);
+	if(e!=cudaSuccess) return cuda_fail(e, "division self-test");
+	*mismatches = (uint64_t)bad;
+	return FX3D_OK;
+}
+
 } // extern "C"

@@ -15,6 +15,10 @@
 #pragma once
 #include "lbm_core.cuh"
 
+#ifndef FX3D_V4_MINBLOCKS
+#define FX3D_V4_MINBLOCKS 3 // resident 128-thread blocks per SM the vector kernel is compiled for (register cap 65536/(128*n))
+#endif
+
 namespace fx3d {
 
 struct Lattice { // one LBM_Domain as the device sees it (passed by value)
@@ -22,6 +26,7 @@ struct Lattice { // one LBM_Domain as the device sees it (passed by value)
 	uint32_t Hx, Hy, Hz; // 1 where the axis is decomposed (halo layer present), else 0
 	uint32_t px, xo;     // DDF row pitch and x offset, in elements
 	uint64_t slot;       // elements between consecutive DDF slots
+	uint32_t slot32;     // the same, known to fit 32 bits (checked on the host)
 	void* fi;
 	float* rho;
 	float* u;
@@ -42,164 +47,204 @@ FX3D_HD uint32_t dec(uint32_t v, uint32_t n) { return v==0u ? n-1u : v-1u; }
 template<int E> FX3D_HD uint32_t step(uint32_t v, uint32_t n) { if constexpr(E>0) return inc(v, n); else if constexpr(E<0) return dec(v, n); else return v; }
 FX3D_HD uint32_t step_rt(int e, uint32_t v, uint32_t n) { return e>0 ? inc(v, n) : e<0 ? dec(v, n) : v; }
 
-// ---- K consecutive x-elements of one slot, as loaded ----
-template<int ST, int K> struct Pack;
-template<> struct Pack<ST_FP32, 4> {
-	float e[4];
-	FX3D_HD void load(const float* p) { const float4 t = *reinterpret_cast<const float4*>(p); e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w; }
-	FX3D_HD void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(e[0], e[1], e[2], e[3]); }
-	FX3D_HD void store_1_3(float* p) const { p[1] = e[1]; *reinterpret_cast<float2*>(p+2) = make_float2(e[2], e[3]); } // elements 1..3 only
-	FX3D_HD void store_0_2(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(e[0], e[1]); p[2] = e[2]; } // elements 0..2 only
-	template<int c> FX3D_HD float get() const { return e[c]; }
-	template<int c> FX3D_HD void set(float v) { e[c] = v; }
-	FX3D_HD uint32_t first_bits() const { return __float_as_uint(e[0]); }
-	FX3D_HD uint32_t last_bits() const { return __float_as_uint(e[3]); }
-	FX3D_HD void push_back(uint32_t b) { e[0] = e[1]; e[1] = e[2]; e[2] = e[3]; e[3] = __uint_as_float(b); }  // {e1,e2,e3,b}
-	FX3D_HD void push_front(uint32_t b) { e[3] = e[2]; e[2] = e[1]; e[1] = e[0]; e[0] = __uint_as_float(b); } // {b,e0,e1,e2}
+FX3D_HD char* mad_wide(uint32_t a, uint32_t b, char* c) { // c + a*b with the product taken in 64 bits: one IMAD.WIDE.U32
+#if defined(FX3D_HOST_EMULATION)
+	return c+(uint64_t)a*(uint64_t)b;
+#else
+	unsigned long long r; asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"((unsigned long long)c)); return reinterpret_cast<char*>(r);
+#endif
+}
+
+// ---- 4 consecutive x-elements of one slot, as loaded; cells (0,1) and (2,3) form the two F2 lane pairs ----
+struct alignas(16) Raw16 { unsigned long long x, y; };
+struct alignas(8) Raw8 { uint32_t x, y; };
+template<int ST> struct Pack4;
+template<> struct Pack4<ST_FP32> {
+	F2 p[2];
+	FX3D_HD void load(const float* q) { const Raw16 t = *reinterpret_cast<const Raw16*>(q); memcpy_bits(p[0], t.x); memcpy_bits(p[1], t.y); }
+	FX3D_HD void store(float* q) const { Raw16 t; t.x = bits64(p[0]); t.y = bits64(p[1]); *reinterpret_cast<Raw16*>(q) = t; }
+	FX3D_HD void store_1_3(float* q) const { q[1] = f2_hi(p[0]); *reinterpret_cast<unsigned long long*>(q+2) = bits64(p[1]); } // elements 1..3 only
+	FX3D_HD void store_0_2(float* q) const { *reinterpret_cast<unsigned long long*>(q) = bits64(p[0]); q[2] = f2_lo(p[1]); } // elements 0..2 only
+	FX3D_HD uint32_t first_bits() const { return __float_as_uint(f2_lo(p[0])); }
+	FX3D_HD uint32_t last_bits() const { return __float_as_uint(f2_hi(p[1])); }
+	FX3D_HD void push_back(uint32_t b) { p[0] = make_f2(f2_hi(p[0]), f2_lo(p[1])); p[1] = make_f2(f2_hi(p[1]), __uint_as_float(b)); }  // {e1,e2,e3,b}
+	FX3D_HD void push_front(uint32_t b) { p[1] = make_f2(f2_hi(p[0]), f2_lo(p[1])); p[0] = make_f2(__uint_as_float(b), f2_lo(p[0])); } // {b,e0,e1,e2}
+	template<int k> FX3D_HD F2 get_pair() const { return p[k]; }
+	template<int k> FX3D_HD void set_pair(F2 v) { p[k] = v; }
+	template<int k> FX3D_HD void set_lanes(F2 v, bool lo, bool hi) { p[k] = make_f2(lo ? f2_lo(v) : f2_lo(p[k]), hi ? f2_hi(v) : f2_hi(p[k])); }
 	static FX3D_HD uint32_t bits(float v) { return __float_as_uint(v); }
 	static FX3D_HD float from_bits(uint32_t b) { return __uint_as_float(b); }
+#if defined(FX3D_HOST_EMULATION)
+	static FX3D_HD void memcpy_bits(F2& d, unsigned long long v) { std::memcpy(&d, &v, 8); }
+	static FX3D_HD unsigned long long bits64(const F2& s) { unsigned long long v; std::memcpy(&v, &s, 8); return v; }
+#else
+	static FX3D_HD void memcpy_bits(F2& d, unsigned long long v) { d.v = v; }
+	static FX3D_HD unsigned long long bits64(const F2& s) { return s.v; }
+#endif
 };
-template<int ST> struct Pack<ST, 4> { // 16-bit storage: 4 elements in two 32-bit registers
+// 16-bit storage: 4 elements in two 32-bit registers; a register is one lane pair
+FX3D_HD F2 unpack_half2_raw(uint32_t r) { return make_f2(__half2float(__ushort_as_half((uint16_t)(r&0xFFFFu))), __half2float(__ushort_as_half((uint16_t)(r>>16)))); }
+FX3D_HD uint32_t pack_half2_raw(F2 v) {
+#if defined(FX3D_HOST_EMULATION)
+	return (uint32_t)__half_as_ushort(__float2half_rn(f2_lo(v)))|((uint32_t)__half_as_ushort(__float2half_rn(f2_hi(v)))<<16);
+#else
+	uint32_t r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(f2_hi(v)), "f"(f2_lo(v))); return r; // one instruction converts and packs both lanes
+#endif
+}
+template<int ST> struct Pack4 {
 	uint32_t r[2];
-	FX3D_HD void load(const uint16_t* p) { const uint2 t = *reinterpret_cast<const uint2*>(p); r[0] = t.x; r[1] = t.y; }
-	FX3D_HD void store(uint16_t* p) const { *reinterpret_cast<uint2*>(p) = make_uint2(r[0], r[1]); }
-	FX3D_HD void store_1_3(uint16_t* p) const { p[1] = (uint16_t)(r[0]>>16); *reinterpret_cast<uint32_t*>(p+2) = r[1]; }
-	FX3D_HD void store_0_2(uint16_t* p) const { *reinterpret_cast<uint32_t*>(p) = r[0]; p[2] = (uint16_t)(r[1]&0xFFFFu); }
-	template<int c> FX3D_HD uint16_t get() const { return (uint16_t)((c&1) ? r[c>>1]>>16 : r[c>>1]&0xFFFFu); }
-	template<int c> FX3D_HD void set(uint16_t v) { r[c>>1] = (c&1) ? (r[c>>1]&0x0000FFFFu)|((uint32_t)v<<16) : (r[c>>1]&0xFFFF0000u)|(uint32_t)v; }
+	FX3D_HD void load(const uint16_t* q) { const Raw8 t = *reinterpret_cast<const Raw8*>(q); r[0] = t.x; r[1] = t.y; }
+	FX3D_HD void store(uint16_t* q) const { Raw8 t; t.x = r[0]; t.y = r[1]; *reinterpret_cast<Raw8*>(q) = t; }
+	FX3D_HD void store_1_3(uint16_t* q) const { q[1] = (uint16_t)(r[0]>>16); *reinterpret_cast<uint32_t*>(q+2) = r[1]; }
+	FX3D_HD void store_0_2(uint16_t* q) const { *reinterpret_cast<uint32_t*>(q) = r[0]; q[2] = (uint16_t)(r[1]&0xFFFFu); }
 	FX3D_HD uint32_t first_bits() const { return r[0]&0xFFFFu; }
 	FX3D_HD uint32_t last_bits() const { return r[1]>>16; }
 	FX3D_HD void push_back(uint32_t b) { r[0] = (r[0]>>16)|(r[1]<<16); r[1] = (r[1]>>16)|(b<<16); }
 	FX3D_HD void push_front(uint32_t b) { r[1] = (r[1]<<16)|(r[0]>>16); r[0] = (r[0]<<16)|(b&0xFFFFu); }
+	template<int k> FX3D_HD F2 get_pair() const { // to the working scale of Codec<ST>
+		if constexpr(ST==ST_FP16S) return unpack_half2_raw(r[k]);
+		else return vmul(make_f2(__uint_as_float(fp16c_decode_bits(r[k]&0xFFFFu)), __uint_as_float(fp16c_decode_bits(r[k]>>16))), vsplat<F2>(0x1p112f));
+	}
+	static FX3D_HD uint32_t encode_pair(F2 v) {
+		if constexpr(ST==ST_FP16S) return pack_half2_raw(v);
+		else { const F2 s = vmul_rz(v, vsplat<F2>(0x1p-112f)); return fp16c_encode_bits(f2_lo(s))|(fp16c_encode_bits(f2_hi(s))<<16); }
+	}
+	template<int k> FX3D_HD void set_pair(F2 v) { r[k] = encode_pair(v); }
+	template<int k> FX3D_HD void set_lanes(F2 v, bool lo, bool hi) { const uint32_t m = (lo ? 0x0000FFFFu : 0u)|(hi ? 0xFFFF0000u : 0u); r[k] = (encode_pair(v)&m)|(r[k]&~m); }
 	static FX3D_HD uint32_t bits(uint16_t v) { return (uint32_t)v; }
 	static FX3D_HD uint16_t from_bits(uint32_t b) { return (uint16_t)b; }
 };
 
 // ================================================================================================================
-// stream_collide, vector form: one thread owns K=4 x-consecutive cells and moves every slot with one aligned
+// stream_collide, vector form: one thread owns 4 x-consecutive cells and moves every slot with one aligned
 // 16-byte (FP32) / 8-byte (FP16) access. Directions with an x component are misaligned by one element: the thread
 // loads the aligned vector and obtains / hands over the straddling element by a warp shuffle; only at warp, block,
-// row or region ends does a lane fall back to one scalar access. Every (cell,slot) is still read and written by
-// exactly one thread (the Esoteric-Pull invariant), solid cells' populations pass through unchanged.
+// row or region ends does a lane fall back to one scalar access. The two cell pairs are collided in packed
+// binary32x2 arithmetic (F2). Every (cell,slot) is still read and written by exactly one thread (the Esoteric-Pull
+// invariant); solid cells' populations pass through unchanged.
 // ================================================================================================================
 template<int Q, int COLL, int ST, bool VF>
-__global__ void __launch_bounds__(128) k_stream_collide_v4(const Lattice L, const Region R) {
+__global__ void __launch_bounds__(128, FX3D_V4_MINBLOCKS) k_stream_collide_v4(const Lattice L, const Region R) {
 	constexpr int K = 4;
 	constexpr unsigned FULL = 0xFFFFFFFFu;
 	typedef Codec<ST> C;
 	typedef typename C::elem_t E;
-	typedef Pack<ST, K> P;
+	typedef Pack4<ST> P;
 	const uint32_t g = R.g0+blockIdx.x*blockDim.x+threadIdx.x;
 	const uint32_t y = R.y0+blockIdx.y*blockDim.y+threadIdx.y;
 	const uint32_t z = R.z0+blockIdx.z;
 	const bool valid = g<R.g1 && y<R.y1;
 	if(!__any_sync(FULL, valid)) return; // warp-uniform
 	const uint32_t lane = (threadIdx.x+threadIdx.y*blockDim.x)&31u;
-	const bool has_right = valid && lane<31u && threadIdx.x+1u<blockDim.x && g+1u<R.g1; // lane+1 owns the next K cells of this row
-	const bool has_left = valid && lane>0u && threadIdx.x>0u;                           // lane-1 owns the previous K cells
-	const uint32_t x0 = L.Hx+(uint32_t)K*g;
-	const uint32_t yp = inc(y, L.Ny), ym = dec(y, L.Ny), zp = inc(z, L.Nz), zm = dec(z, L.Nz);
-	const uint32_t xr = x0+(uint32_t)K>=L.Nx ? 0u : x0+(uint32_t)K; // x of the element right of my vector (periodic)
-	const uint32_t xl = x0==0u ? L.Nx-1u : x0-1u;                    // x of the element left of my vector
-	const uint64_t col = (uint64_t)(x0+L.xo);
-	E* const fi = reinterpret_cast<E*>(L.fi);
+	const bool has_right = valid && lane<31u && threadIdx.x+1u<blockDim.x && g+1u<R.g1; // lane+1 owns the next 4 cells of this row
+	const bool has_left = valid && lane>0u && threadIdx.x>0u;                           // lane-1 owns the previous 4 cells
+	// Address of my vector in row (y+ey, z+ez) of slot s: one 64-bit pointer per distinct neighbour row, computed once,
+	// plus s*slot as a single 32x32+64 multiply-add (IMAD.WIDE.U32) on uniform operands. Lanes outside the region
+	// alias the last valid cell group for loads (clamped coordinates) and never store.
+	const uint32_t gc = g<R.g1 ? g : R.g1-1u, yc = y<R.y1 ? y : R.y1-1u;
+	const uint32_t x0 = L.Hx+(uint32_t)K*gc;
+	const uint32_t yy[3] = { dec(yc, L.Ny), yc, inc(yc, L.Ny) }, zz[3] = { dec(z, L.Nz), z, inc(z, L.Nz) };
+	const int dxr = (x0+(uint32_t)K>=L.Nx ? 0 : (int)x0+K)-(int)x0; // element offset of the cell right of my vector (periodic wrap)
+	const int dxl = (x0==0u ? (int)L.Nx-1 : (int)x0-1)-(int)x0;     // element offset of the cell left of my vector
 	const uint32_t odd = L.odd;
+	char* rowp[3][3];
+	static_for<0, 9, 1>([&](auto J) { constexpr int j = J; rowp[j/3][j%3] = reinterpret_cast<char*>(L.fi)+(row(L, yy[j/3], zz[j%3])+(uint64_t)(x0+L.xo))*sizeof(E); });
+	auto at = [&](auto EY, auto EZ, uint32_t s) -> E* { return reinterpret_cast<E*>(mad_wide(L.slot32, s*(uint32_t)sizeof(E), rowp[EY.value+1][EZ.value+1])); };
+#define FX3D_AT(ey, ez, s) at(std::integral_constant<int, (ey)>{}, std::integral_constant<int, (ez)>{}, (s))
 
 	uint32_t fl[K];
 	bool any_active = false;
 	if(valid) {
-		const uint8_t* fp = L.flags+lin(L, x0, y, z);
+		const uint8_t* fp = L.flags+lin(L, x0, yc, z);
 		if(((L.Nx|x0)&3u)==0u) { // rows are 4-byte aligned: one load for the 4 flags
 			const uint32_t f4 = *reinterpret_cast<const uint32_t*>(fp);
 			fl[0] = f4&0xFFu; fl[1] = (f4>>8)&0xFFu; fl[2] = (f4>>16)&0xFFu; fl[3] = f4>>24;
 		} else { fl[0] = fp[0]; fl[1] = fp[1]; fl[2] = fp[2]; fl[3] = fp[3]; }
 		any_active = (fl[0]&TYPE_BO)!=TYPE_S || (fl[1]&TYPE_BO)!=TYPE_S || (fl[2]&TYPE_BO)!=TYPE_S || (fl[3]&TYPE_BO)!=TYPE_S;
 	} else { fl[0] = fl[1] = fl[2] = fl[3] = TYPE_S; }
-
 	// ---- stream in: A[i] holds, per owned cell, the population that load_f() assigns to fhn[i] ----
 	P A[Q];
-	const uint64_t row0 = row(L, y, z);
-	if(valid) {
-		A[0].load(fi+row0+col);
-		static_for<1, Q, 2>([&](auto I) {
-			constexpr int i = I;
-			const uint64_t sl = (uint64_t)(odd ? i : i+1)*L.slot, sn = (uint64_t)(odd ? i+1 : i)*L.slot;
-			const uint64_t rown = row(L, dir_y(i)>0 ? yp : dir_y(i)<0 ? ym : y, dir_z(i)>0 ? zp : dir_z(i)<0 ? zm : z);
-			A[i  ].load(fi+sl+row0+col);
-			A[i+1].load(fi+sn+rown+col); // aligned vector of the neighbour row; x-shift fixed up below
-		});
-	} else {
-		static_for<0, Q, 1>([&](auto I) { A[I] = P{}; });
-	}
+	A[0].load(FX3D_AT(0, 0, 0u));
 	static_for<1, Q, 2>([&](auto I) {
 		constexpr int i = I;
-		if constexpr(dir_x(i)!=0) {
-			const uint64_t sn = (uint64_t)(odd ? i+1 : i)*L.slot;
-			const uint64_t rown = row(L, dir_y(i)>0 ? yp : dir_y(i)<0 ? ym : y, dir_z(i)>0 ? zp : dir_z(i)<0 ? zm : z);
-			if constexpr(dir_x(i)>0) { // need elements x0+1..x0+4: take the right lane's first element
-				uint32_t b = __shfl_down_sync(FULL, A[i+1].first_bits(), 1u);
-				if(valid && !has_right) b = P::bits(fi[sn+rown+(uint64_t)(xr+L.xo)]);
-				A[i+1].push_back(b);
-			} else { // need elements x0-1..x0+2: take the left lane's last element
-				uint32_t b = __shfl_up_sync(FULL, A[i+1].last_bits(), 1u);
-				if(valid && !has_left) b = P::bits(fi[sn+rown+(uint64_t)(xl+L.xo)]);
-				A[i+1].push_front(b);
-			}
+		A[i  ].load(FX3D_AT(0, 0, odd ? (uint32_t)i : (uint32_t)i+1u));
+		A[i+1].load(FX3D_AT(dir_y(i), dir_z(i), odd ? (uint32_t)i+1u : (uint32_t)i)); // aligned vector of the neighbour row; x-shift fixed up below
+	});
+	static_for<1, Q, 2>([&](auto I) {
+		constexpr int i = I;
+		if constexpr(dir_x(i)>0) { // need elements x0+1..x0+4: take the right lane's first element
+			uint32_t b = __shfl_down_sync(FULL, A[i+1].first_bits(), 1u);
+			if(valid && !has_right) b = P::bits(FX3D_AT(dir_y(i), dir_z(i), odd ? (uint32_t)i+1u : (uint32_t)i)[dxr]);
+			A[i+1].push_back(b);
+		} else if constexpr(dir_x(i)<0) { // need elements x0-1..x0+2: take the left lane's last element
+			uint32_t b = __shfl_up_sync(FULL, A[i+1].last_bits(), 1u);
+			if(valid && !has_left) b = P::bits(FX3D_AT(dir_y(i), dir_z(i), odd ? (uint32_t)i+1u : (uint32_t)i)[dxl]);
+			A[i+1].push_front(b);
 		}
 	});
 
-	// ---- collide the owned cells one after the other ----
-	static_for<0, K, 1>([&](auto Cc) {
-		constexpr int c = Cc;
-		const uint32_t fb = fl[c]&TYPE_BO;
-		if(valid && fb!=TYPE_S) {
-			float f[Q];
-			static_for<0, Q, 1>([&](auto I) { f[I] = C::decode(A[I].template get<c>()); });
-			const bool is_e = L.eb!=0u && fb==TYPE_E;
-			float rho_e = 1.0f, ux_e = 0.0f, uy_e = 0.0f, uz_e = 0.0f;
-			const uint64_t n = lin(L, x0+(uint32_t)c, y, z), N = cells(L);
-			if(is_e) { rho_e = L.rho[n]; ux_e = L.u[n]; uy_e = L.u[N+n]; uz_e = L.u[2ull*N+n]; }
-			float rhon, uxn, uyn, uzn;
-			collide_cell<Q, COLL, VF>(f, is_e, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
-			if(L.upd!=0u && !is_e) { L.rho[n] = rhon; L.u[n] = uxn; L.u[N+n] = uyn; L.u[2ull*N+n] = uzn; }
+	// ---- collide the two cell pairs in packed arithmetic ----
+	static_for<0, 2, 1>([&](auto Pp) {
+		constexpr int p = Pp;
+		const uint32_t fb_lo = fl[2*p]&TYPE_BO, fb_hi = fl[2*p+1]&TYPE_BO;
+		const bool act_lo = valid && fb_lo!=TYPE_S, act_hi = valid && fb_hi!=TYPE_S;
+		if(act_lo || act_hi) {
+			F2 f[Q];
+			static_for<0, Q, 1>([&](auto I) { f[I] = A[I].template get_pair<p>(); });
+			const bool e_lo = L.eb!=0u && act_lo && fb_lo==TYPE_E, e_hi = L.eb!=0u && act_hi && fb_hi==TYPE_E;
+			const uint64_t n = lin(L, x0+2u*(uint32_t)p, yc, z), N = cells(L);
+			F2 rho_e = vsplat<F2>(1.0f), ux_e = vsplat<F2>(0.0f), uy_e = ux_e, uz_e = ux_e;
+			if(e_lo || e_hi) {
+				const uint64_t nl = e_lo ? n : n+1ull, nh = e_hi ? n+1ull : n; // only TYPE_E lanes are used
+				rho_e = make_f2(L.rho[nl], L.rho[nh]); ux_e = make_f2(L.u[nl], L.u[nh]); uy_e = make_f2(L.u[N+nl], L.u[N+nh]); uz_e = make_f2(L.u[2ull*N+nl], L.u[2ull*N+nh]);
+			}
+			F2 rhon, uxn, uyn, uzn;
+			collide_cell<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+			if(L.upd!=0u) {
+				if(act_lo && !e_lo) { L.rho[n] = f2_lo(rhon); L.u[n] = f2_lo(uxn); L.u[N+n] = f2_lo(uyn); L.u[2ull*N+n] = f2_lo(uzn); }
+				if(act_hi && !e_hi) { L.rho[n+1ull] = f2_hi(rhon); L.u[n+1ull] = f2_hi(uxn); L.u[N+n+1ull] = f2_hi(uyn); L.u[2ull*N+n+1ull] = f2_hi(uzn); }
+			}
 			// store_f(): fhn[i] goes to the neighbour-side slot, fhn[i+1] to the local slot
-			A[0].template set<c>(C::encode(f[0]));
-			static_for<1, Q, 2>([&](auto I) {
-				constexpr int i = I;
-				A[i+1].template set<c>(C::encode(f[i]));
-				A[i  ].template set<c>(C::encode(f[i+1]));
-			});
+			if(act_lo && act_hi) {
+				A[0].template set_pair<p>(f[0]);
+				static_for<1, Q, 2>([&](auto I) { constexpr int i = I; A[i+1].template set_pair<p>(f[i]); A[i].template set_pair<p>(f[i+1]); });
+			} else { // one of the two cells is solid: its populations keep their bits
+				A[0].template set_lanes<p>(f[0], act_lo, act_hi);
+				static_for<1, Q, 2>([&](auto I) { constexpr int i = I; A[i+1].template set_lanes<p>(f[i], act_lo, act_hi); A[i].template set_lanes<p>(f[i+1], act_lo, act_hi); });
+			}
 		}
 	});
 
 	// ---- stream out (same addresses as stream in) ----
 	if(!__any_sync(FULL, any_active)) return; // nothing but solid cells in this warp: nothing changed
-	if(valid) A[0].store(fi+row0+col);
+	if(valid) A[0].store(FX3D_AT(0, 0, 0u));
 	static_for<1, Q, 2>([&](auto I) {
 		constexpr int i = I;
-		const uint64_t sl = (uint64_t)(odd ? i : i+1)*L.slot, sn = (uint64_t)(odd ? i+1 : i)*L.slot;
-		const uint64_t rown = row(L, dir_y(i)>0 ? yp : dir_y(i)<0 ? ym : y, dir_z(i)>0 ? zp : dir_z(i)<0 ? zm : z);
-		if(valid) A[i].store(fi+sl+row0+col);
+		const uint32_t sl = odd ? (uint32_t)i : (uint32_t)i+1u, sn = odd ? (uint32_t)i+1u : (uint32_t)i;
+		if(valid) A[i].store(FX3D_AT(0, 0, sl));
 		if constexpr(dir_x(i)==0) {
-			if(valid) A[i+1].store(fi+sn+rown+col);
+			if(valid) A[i+1].store(FX3D_AT(dir_y(i), dir_z(i), sn));
 		} else if constexpr(dir_x(i)>0) { // my values belong to x0+1..x0+4
 			const uint32_t last = A[i+1].last_bits();
 			const uint32_t up = __shfl_up_sync(FULL, last, 1u);
 			if(valid) {
-				if(!has_right) fi[sn+rown+(uint64_t)(xr+L.xo)] = P::from_bits(last);
+				E* q = FX3D_AT(dir_y(i), dir_z(i), sn);
+				if(!has_right) q[dxr] = P::from_bits(last);
 				A[i+1].push_front(up); // {left lane's x0, mine x0+1..x0+3}
-				if(has_left) A[i+1].store(fi+sn+rown+col); else A[i+1].store_1_3(fi+sn+rown+col);
+				if(has_left) A[i+1].store(q); else A[i+1].store_1_3(q);
 			}
 		} else { // my values belong to x0-1..x0+2
 			const uint32_t first = A[i+1].first_bits();
 			const uint32_t dn = __shfl_down_sync(FULL, first, 1u);
 			if(valid) {
-				if(!has_left) fi[sn+rown+(uint64_t)(xl+L.xo)] = P::from_bits(first);
+				E* q = FX3D_AT(dir_y(i), dir_z(i), sn);
+				if(!has_left) q[dxl] = P::from_bits(first);
 				A[i+1].push_back(dn); // {mine x0..x0+2, right lane's x0+3}
-				if(has_right) A[i+1].store(fi+sn+rown+col); else A[i+1].store_0_2(fi+sn+rown+col);
+				if(has_right) A[i+1].store(q); else A[i+1].store_0_2(q);
 			}
 		}
 	});
+#undef FX3D_AT
 }
 
 // ================================================================================================================
@@ -256,7 +301,7 @@ __global__ void __launch_bounds__(128) k_stream_collide_v1(const Lattice L, cons
 	float rho_e = 1.0f, ux_e = 0.0f, uy_e = 0.0f, uz_e = 0.0f;
 	if(is_e) { rho_e = L.rho[n]; ux_e = L.u[n]; uy_e = L.u[N+n]; uz_e = L.u[2ull*N+n]; }
 	float rhon, uxn, uyn, uzn;
-	collide_cell<Q, COLL, VF>(f, is_e, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+	collide_cell<Q, COLL, VF, float>(f, 1.0f, 1.0f, is_e, false, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
 	if(L.upd!=0u && !is_e) { L.rho[n] = rhon; L.u[n] = uxn; L.u[N+n] = uyn; L.u[2ull*N+n] = uzn; }
 	io.push(L, L.odd, f);
 }
@@ -269,7 +314,7 @@ __global__ void __launch_bounds__(128) k_initialize(const Lattice L, const Regio
 	const uint64_t n = lin(L, x, y, z), N = cells(L);
 	if((L.flags[n]&TYPE_BO)==TYPE_S) { L.u[n] = 0.0f; L.u[N+n] = 0.0f; L.u[2ull*N+n] = 0.0f; }
 	float feq[Q];
-	equilibrium<Q>(L.rho[n], L.u[n], L.u[N+n], L.u[2ull*N+n], feq);
+	equilibrium<Q, float>(L.rho[n], L.u[n], L.u[N+n], L.u[2ull*N+n], 1.0f, feq);
 	CellIO<Q, ST> io; io.locate(L, x, y, z);
 	io.push(L, 1u, feq); // odd-step layout is baked in (:1429)
 }
@@ -419,6 +464,57 @@ __global__ void k_codec_decode(const uint16_t* in, float* out, uint64_t n) {
 	if(k<n) out[k] = Codec<ST>::decode(in[k]);
 }
 #if defined(FX3D_TU_RUNTIME)
+// packed-lane self-test: moments, equilibrium and the full cell update in F2 (two cells per operation) against the scalar
+// instantiation of the same templates, bit for bit, on pseudo-random populations (guards against instruction contraction)
+template<int Q, int COLL, bool VF> __global__ void k_selftest_lanes(unsigned long long samples_per_thread, float S, unsigned long long* mismatches) {
+	unsigned long long s = ((unsigned long long)blockIdx.x*blockDim.x+threadIdx.x)*0x9E3779B97F4A7C15ull+0x7654321ull, bad = 0ull;
+	auto next = [&]() { s ^= s<<13; s ^= s>>7; s ^= s<<17; return (uint32_t)(s>>16); };
+	auto rnd = [&]() { return (float)(next()&0xFFFFFFu)/16777216.0f-0.5f; };
+	const float inv = 1.0f/S;
+	for(unsigned long long k=0ull; k<samples_per_thread; k++) {
+		float fa[Q], fb[Q]; F2 f2[Q];
+		const float amp = (k&3ull)==0ull ? 0.0f : 0.02f; // every fourth sample is a fluid at rest (all-zero populations)
+		static_for<0, Q, 1>([&](auto I) { fa[I] = amp*rnd()*S; fb[I] = amp*rnd()*S; if(S!=1.0f) { fa[I] = rintf(fa[I]); fb[I] = rintf(fb[I]); } f2[I] = make_f2(fa[I], fb[I]); });
+		float ra, uxa, uya, uza, rb, uxb, uyb, uzb; F2 r2, ux2, uy2, uz2;
+		moments<Q, float>(fa, S, inv, ra, uxa, uya, uza); moments<Q, float>(fb, S, inv, rb, uxb, uyb, uzb); moments<Q, F2>(f2, S, inv, r2, ux2, uy2, uz2);
+		auto ne = [](float x, float y) { return __float_as_uint(x)!=__float_as_uint(y) ? 1ull : 0ull; };
+		bad += ne(f2_lo(r2), ra)+ne(f2_hi(r2), rb)+ne(f2_lo(ux2), uxa)+ne(f2_hi(ux2), uxb)+ne(f2_lo(uy2), uya)+ne(f2_hi(uy2), uyb)+ne(f2_lo(uz2), uza)+ne(f2_hi(uz2), uzb);
+		float ea[Q], eb[Q]; F2 e2[Q];
+		equilibrium<Q, float>(ra, uxa, uya, uza, S, ea); equilibrium<Q, float>(rb, uxb, uyb, uzb, S, eb); equilibrium<Q, F2>(r2, ux2, uy2, uz2, S, e2);
+		static_for<0, Q, 1>([&](auto I) { bad += ne(f2_lo(e2[I]), ea[I])+ne(f2_hi(e2[I]), eb[I]); });
+		float o0, o1, o2, o3; F2 p0, p1, p2, p3;
+		const bool e_lo = (k&7ull)==5ull, e_hi = (k&15ull)==9ull;
+		collide_cell<Q, COLL, VF, float>(fa, S, inv, e_lo, false, 1.01f, 0.02f, -0.03f, 0.04f, 1e-4f, -2e-4f, 3e-4f, 1.7f, o0, o1, o2, o3);
+		collide_cell<Q, COLL, VF, float>(fb, S, inv, e_hi, false, 0.99f, -0.01f, 0.05f, 0.0f, 1e-4f, -2e-4f, 3e-4f, 1.7f, o0, o1, o2, o3);
+		collide_cell<Q, COLL, VF, F2>(f2, S, inv, e_lo, e_hi, make_f2(1.01f, 0.99f), make_f2(0.02f, -0.01f), make_f2(-0.03f, 0.05f), make_f2(0.04f, 0.0f), 1e-4f, -2e-4f, 3e-4f, 1.7f, p0, p1, p2, p3);
+		static_for<0, Q, 1>([&](auto I) { bad += ne(f2_lo(f2[I]), fa[I])+ne(f2_hi(f2[I]), fb[I]); });
+	}
+	if(bad) atomicAdd(mismatches, bad);
+}
+// division self-test: the shared-reciprocal division of lbm_core.cuh against operator/ on pseudo-random and edge operands
+__global__ void k_selftest_division(unsigned long long samples_per_thread, unsigned long long* mismatches) {
+	unsigned long long s = ((unsigned long long)blockIdx.x*blockDim.x+threadIdx.x)*0x9E3779B97F4A7C15ull+0x1234567ull, bad = 0ull;
+	auto next = [&]() { s ^= s<<13; s ^= s>>7; s ^= s<<17; return (uint32_t)(s>>16); };
+	for(unsigned long long k=0ull; k<samples_per_thread; k++) {
+		const uint32_t r0 = next(), r1 = next(), r2 = next(), r3 = next(), mode = next()&7u;
+		// denominators: rho-like (0.5..2), scaled rho (2^14..2^16), or any exponent; numerators: tiny..moderate, zeros, denormals
+		const uint32_t eb = mode<4u ? 126u+(r0&1u) : mode<6u ? 141u+(r0&1u) : (r0>>8)&0xFFu;
+		const float b = __uint_as_float((r1&0x807FFFFFu)|(eb<<23));
+		const uint32_t ea = (mode&1u) ? 100u+(r2%60u) : (r2>>3)&0xFFu;
+		float a0 = __uint_as_float((r3&0x807FFFFFu)|(ea<<23)), a1 = __uint_as_float((next()&0x807FFFFFu)|(((ea+r0)%255u)<<23)), a2 = (mode==3u) ? 0.0f : __uint_as_float(next());
+		if(a0!=a0||a1!=a1||a2!=a2||b!=b) continue;
+		float q0, q1, q2;
+		vdiv3(a0, a1, a2, b, q0, q1, q2);
+		const float e0 = a0/b, e1 = a1/b, e2 = a2/b;
+		bad += (__float_as_uint(q0)!=__float_as_uint(e0) && e0==e0)+(__float_as_uint(q1)!=__float_as_uint(e1) && e1==e1)+(__float_as_uint(q2)!=__float_as_uint(e2) && e2==e2);
+		F2 p0, p1, p2;
+		vdiv3(make_f2(a0, a1), make_f2(a1, a2), make_f2(a2, a0), make_f2(b, b), p0, p1, p2);
+		bad += (__float_as_uint(f2_lo(p0))!=__float_as_uint(e0) && e0==e0)+(__float_as_uint(f2_hi(p0))!=__float_as_uint(e1) && e1==e1)+(__float_as_uint(f2_hi(p1))!=__float_as_uint(e2) && e2==e2);
+		const float h = vdiv1(0.5f, b), eh = 0.5f/b;
+		bad += (__float_as_uint(h)!=__float_as_uint(eh) && eh==eh);
+	}
+	if(bad) atomicAdd(mismatches, bad);
+}
 // exhaustive check over all 2^32 binary32 inputs: counts inputs where the one-multiply FP16C encode differs from
 // the reference's literal formula (and all 2^16 codes for decode); NaN payloads excluded for decode comparisons
 __global__ void k_fp16c_exhaustive(unsigned long long* mismatches, uint32_t* first_bad) {

@@ -139,6 +139,10 @@ int fx3d_rendezvous_check(int device, uint64_t* my_array, int n_slots); /* block
 int fx3d_codec_encode(int device, int storage, const float* in, uint16_t* out, size_t count, fx3d_stream stream);
 int fx3d_codec_decode(int device, int storage, const uint16_t* in, float* out, size_t count, fx3d_stream stream);
 int fx3d_codec_fp16c_exhaustive(int device, uint64_t* mismatches, uint32_t* first_bad_bits); /* blocking, all 2^32 inputs */
+/* the kernels divide by rho with a shared-reciprocal sequence; this compares it with IEEE division on `samples` operands */
+int fx3d_selftest_division(int device, uint64_t samples, uint64_t* mismatches);
+/* the vector kernel collides two cells per packed binary32x2 instruction; this compares every packed routine with its scalar twin */
+int fx3d_selftest_packed_math(int device, uint64_t samples, uint64_t* mismatches);
 
 #ifdef __cplusplus
 }

@@ -135,4 +135,7 @@ int fx3d_rendezvous_check(int, uint64_t* my_array, int) {
 
 int fx3d_codec_fp16c_exhaustive(int, uint64_t*, uint32_t*) { fx3d::set_error("emulation: the exhaustive codec check runs on the GPU only"); return FX3D_ERR_INVALID; }
 
+int fx3d_selftest_packed_math(int, uint64_t, uint64_t*) { fx3d::set_error("emulation: the packed-math self-test runs on the GPU only"); return FX3D_ERR_INVALID; }
+int fx3d_selftest_division(int, uint64_t, uint64_t*) { fx3d::set_error("emulation: the division self-test runs on the GPU only"); return FX3D_ERR_INVALID; }
+
 } // extern "C"

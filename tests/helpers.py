@@ -245,7 +245,8 @@ class HostSim:
 
     def fields(self):
         """(rho, ux, uy, uz, flags) on the global grid after update_fields (what lbm.u.read_from_device() returns)"""
-        self.update_fields()
+        if not (self.b.features & UPDATE_FIELDS):  # src/lbm.hpp:390-393: with UPDATE_FIELDS the fields are already current
+            self.update_fields()
         return (self.get_global("rho"), self.get_global("u", 0), self.get_global("u", 1), self.get_global("u", 2), self.get_global("flags"))
 
 
