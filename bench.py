@@ -133,7 +133,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--variant", type=int, default=0, help="1 forces the general one-cell-per-thread kernel")
+    ap.add_argument("--variant", type=int, default=0, help="kernel choice: 0 default, 1 general one-cell-per-thread, 2 or 4 cells per thread")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -223,7 +223,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": round(per_gpu_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(per_gpu_gbs / peak, 4),
-                "traffic": traffic, "peak_source": peak_src, "kernel": "k_stream_collide_v4" if args.variant == 0 else "k_stream_collide_v1",
+                "traffic": traffic, "peak_source": peak_src, "kernel": "k_stream_collide_v1" if args.variant == 1 else "k_stream_collide_vec",
                 "bytes_per_cell_per_step": bytes_per_cell, "cells_per_launch": cells // n_gpus}
     sim.close()
 

@@ -11,15 +11,17 @@ namespace fx3d {
 
 void set_error(const std::string& msg);       // stores the thread-local text returned by fx3d_last_error()
 extern std::atomic<uint64_t> g_launches;      // kernels launched so far (fx3d_launch_count)
-extern std::atomic<int> g_variant;            // 0 auto, 1 force the general one-cell-per-thread kernels
+extern std::atomic<int> g_variant;            // 0 auto, 1 general one-cell-per-thread kernel, 2 / 4 vector kernel with that many cells per thread
 
 #if defined(FX3D_HOST_EMULATION)
 // test-only build (tests/emul): kernels run as OS threads on host pointers; there is no device to select
 #define FX3D_LAUNCH(kernel, grid, block, stream, ...) do { ::fx3d::g_launches++; ::emul::launch((grid), (block), [&]() { kernel(__VA_ARGS__); }); } while(0)
+#define FX3D_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) do { ::fx3d::g_launches++; ::emul::launch((grid), (block), [&]() { kernel(__VA_ARGS__); }, (smem)); } while(0)
 inline int use_device(int) { return FX3D_OK; }
 inline int check_launch(const char*) { return FX3D_OK; }
 #else
 #define FX3D_LAUNCH(kernel, grid, block, stream, ...) do { ::fx3d::g_launches++; kernel<<<(grid), (block), 0, (cudaStream_t)(stream)>>>(__VA_ARGS__); } while(0)
+#define FX3D_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) do { ::fx3d::g_launches++; kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); } while(0)
 int use_device(int device);                   // cudaSetDevice with error translation
 int check_launch(const char* what);           // cudaGetLastError with error translation
 int cuda_fail(cudaError_t e, const char* what);
@@ -50,6 +52,6 @@ inline bool make_lattice(const fx3d_lattice* in, uint64_t t, float fx, float fy,
 inline size_t elem_bytes(uint32_t storage) { return storage==FX3D_FP32 ? 4u : 2u; }
 
 // stream_collide instantiations live in one translation unit per (velocity set, storage), see sc_inst.cu
-template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, bool vector4, int collision, bool volume_force, void* stream);
+template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, int cells_per_thread, int collision, bool volume_force, void* stream); // cells_per_thread 0: pipelined kernel
 
 } // namespace fx3d

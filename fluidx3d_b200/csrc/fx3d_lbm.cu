@@ -16,9 +16,8 @@ std::atomic<int> g_variant{0};
 
 // interior (non-halo) extent and the shell / interior split used to overlap the halo exchange with computation.
 // The shell is every non-halo cell within one cell (one 4-cell group along x for the vector kernel) of a halo layer.
-static void regions_of(const Lattice& L, int region, bool vector4, std::vector<Region>& out) {
-	const uint32_t K = vector4 ? 4u : 1u;
-	const uint32_t gx0 = vector4 ? 0u : L.Hx, gx1 = vector4 ? (L.Nx-2u*L.Hx)/K : L.Nx-L.Hx;
+static void regions_of(const Lattice& L, int region, uint32_t K, std::vector<Region>& out) { // K cells per thread along x
+	const uint32_t gx0 = K>1u ? 0u : L.Hx, gx1 = K>1u ? (L.Nx-2u*L.Hx)/K : L.Nx-L.Hx;
 	const uint32_t y0 = L.Hy, y1 = L.Ny-L.Hy, z0 = L.Hz, z1 = L.Nz-L.Hz;
 	if(region==FX3D_REGION_ALL || (L.Hx|L.Hy|L.Hz)==0u) {
 		if(region!=FX3D_REGION_SHELL) out.push_back(Region{ gx0, gx1, y0, y1, z0, z1 });
@@ -47,14 +46,29 @@ static inline Region all_cells(const Lattice& L) { return Region{ L.Hx, L.Nx-L.H
 	if(Qv==19u) { if(STv==FX3D_FP32) { constexpr int Q = 19, ST = ST_FP32; BODY } else if(STv==FX3D_FP16S) { constexpr int Q = 19, ST = ST_FP16S; BODY } else { constexpr int Q = 19, ST = ST_FP16C; BODY } } \
 	else        { if(STv==FX3D_FP32) { constexpr int Q = 27, ST = ST_FP32; BODY } else if(STv==FX3D_FP16S) { constexpr int Q = 27, ST = ST_FP16S; BODY } else { constexpr int Q = 27, ST = ST_FP16C; BODY } }
 
+static uint32_t default_cells_per_thread(int storage) { (void)storage; return 4u; } // tuned on B200, see DESIGN.md
+static bool default_pipelined() { return false; }
+
 static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int region, void* stream) {
-	const bool vector4 = g_variant.load()!=1 && ((L.Nx-2u*L.Hx)&3u)==0u && L.Nx-2u*L.Hx>=4u;
+	// cells per thread: the vector kernels need the non-halo row length to be a multiple of K; the general kernel takes any size
+	const uint32_t inner = L.Nx-2u*L.Hx;
+	const int want = g_variant.load();
+	uint32_t K = 1u;
+	bool pipelined = false;
+	if(want==8 || (want==0 && default_pipelined())) { // pipelined kernel: 8-byte vectors
+		const uint32_t k8 = lat->storage==FX3D_FP32 ? 2u : 4u;
+		if(inner%k8==0u) { K = k8; pipelined = true; }
+	}
+	if(!pipelined && want!=1) {
+		const uint32_t pref = want==2 ? 2u : want==4 ? 4u : default_cells_per_thread((int)lat->storage);
+		if(inner%pref==0u) K = pref; else if(inner%2u==0u) K = 2u;
+	}
 	std::vector<Region> regs;
-	regions_of(L, region, vector4, regs);
+	regions_of(L, region, K, regs);
 	const bool vf = (lat->features&FX3D_VOLUME_FORCE)!=0u;
 	for(const Region& R : regs) {
 		int rc;
-		FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, vector4, (int)lat->collision, vf, stream); })
+		FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, pipelined ? 0 : (int)K, (int)lat->collision, vf, stream); })
 		if(rc!=FX3D_OK) return rc;
 	}
 	return FX3D_OK;
@@ -66,7 +80,7 @@ using namespace fx3d;
 extern "C" {
 
 const char* fx3d_last_error(void) { return t_error.c_str(); }
-int fx3d_set_kernel_variant(int variant) { if(variant<0||variant>1) { set_error("variant must be 0 or 1"); return FX3D_ERR_INVALID; } g_variant = variant; return FX3D_OK; }
+int fx3d_set_kernel_variant(int variant) { if(variant!=0&&variant!=1&&variant!=2&&variant!=4&&variant!=8) { set_error("variant must be 0 (auto), 1 (general), 2 or 4 (cells per thread), 8 (pipelined)"); return FX3D_ERR_INVALID; } g_variant = variant; return FX3D_OK; }
 int fx3d_launch_count(uint64_t* launches) { if(!launches) return FX3D_ERR_INVALID; *launches = g_launches.load(); return FX3D_OK; }
 
 size_t fx3d_fi_bytes(const fx3d_lattice* lat) {

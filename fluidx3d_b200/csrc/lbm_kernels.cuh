@@ -16,7 +16,10 @@
 #include "lbm_core.cuh"
 
 #ifndef FX3D_V4_MINBLOCKS
-#define FX3D_V4_MINBLOCKS 3 // resident 128-thread blocks per SM the vector kernel is compiled for (register cap 65536/(128*n))
+#define FX3D_V4_MINBLOCKS 3 // resident 128-thread blocks per SM the 4-cell vector kernel is compiled for (register cap 65536/(128*n))
+#endif
+#ifndef FX3D_V2_MINBLOCKS
+#define FX3D_V2_MINBLOCKS 4 // the same for the 2-cell vector kernel
 #endif
 
 namespace fx3d {
@@ -58,13 +61,13 @@ FX3D_HD char* mad_wide(uint32_t a, uint32_t b, char* c) { // c + a*b with the pr
 // ---- 4 consecutive x-elements of one slot, as loaded; cells (0,1) and (2,3) form the two F2 lane pairs ----
 struct alignas(16) Raw16 { unsigned long long x, y; };
 struct alignas(8) Raw8 { uint32_t x, y; };
-template<int ST> struct Pack4;
-template<> struct Pack4<ST_FP32> {
+template<int ST, int K> struct Pack;
+template<> struct Pack<ST_FP32, 4> {
 	F2 p[2];
 	FX3D_HD void load(const float* q) { const Raw16 t = *reinterpret_cast<const Raw16*>(q); memcpy_bits(p[0], t.x); memcpy_bits(p[1], t.y); }
 	FX3D_HD void store(float* q) const { Raw16 t; t.x = bits64(p[0]); t.y = bits64(p[1]); *reinterpret_cast<Raw16*>(q) = t; }
-	FX3D_HD void store_1_3(float* q) const { q[1] = f2_hi(p[0]); *reinterpret_cast<unsigned long long*>(q+2) = bits64(p[1]); } // elements 1..3 only
-	FX3D_HD void store_0_2(float* q) const { *reinterpret_cast<unsigned long long*>(q) = bits64(p[0]); q[2] = f2_lo(p[1]); } // elements 0..2 only
+	FX3D_HD void store_tail(float* q) const { q[1] = f2_hi(p[0]); *reinterpret_cast<unsigned long long*>(q+2) = bits64(p[1]); } // all but the first element
+	FX3D_HD void store_head(float* q) const { *reinterpret_cast<unsigned long long*>(q) = bits64(p[0]); q[2] = f2_lo(p[1]); } // all but the last element
 	FX3D_HD uint32_t first_bits() const { return __float_as_uint(f2_lo(p[0])); }
 	FX3D_HD uint32_t last_bits() const { return __float_as_uint(f2_hi(p[1])); }
 	FX3D_HD void push_back(uint32_t b) { p[0] = make_f2(f2_hi(p[0]), f2_lo(p[1])); p[1] = make_f2(f2_hi(p[1]), __uint_as_float(b)); }  // {e1,e2,e3,b}
@@ -91,53 +94,88 @@ FX3D_HD uint32_t pack_half2_raw(F2 v) {
 	uint32_t r; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(f2_hi(v)), "f"(f2_lo(v))); return r; // one instruction converts and packs both lanes
 #endif
 }
-template<int ST> struct Pack4 {
+template<int ST> FX3D_HD F2 decode_half_pair(uint32_t r) { // two 16-bit elements -> working scale of Codec<ST>
+	if constexpr(ST==ST_FP16S) return unpack_half2_raw(r);
+	else return vmul(make_f2(__uint_as_float(fp16c_decode_bits(r&0xFFFFu)), __uint_as_float(fp16c_decode_bits(r>>16))), vsplat<F2>(0x1p112f));
+}
+template<int ST> FX3D_HD uint32_t encode_half_pair(F2 v) {
+	if constexpr(ST==ST_FP16S) return pack_half2_raw(v);
+	else { const F2 s = vmul_rz(v, vsplat<F2>(0x1p-112f)); return fp16c_encode_bits(f2_lo(s))|(fp16c_encode_bits(f2_hi(s))<<16); }
+}
+template<int ST> struct Pack<ST, 4> {
 	uint32_t r[2];
 	FX3D_HD void load(const uint16_t* q) { const Raw8 t = *reinterpret_cast<const Raw8*>(q); r[0] = t.x; r[1] = t.y; }
 	FX3D_HD void store(uint16_t* q) const { Raw8 t; t.x = r[0]; t.y = r[1]; *reinterpret_cast<Raw8*>(q) = t; }
-	FX3D_HD void store_1_3(uint16_t* q) const { q[1] = (uint16_t)(r[0]>>16); *reinterpret_cast<uint32_t*>(q+2) = r[1]; }
-	FX3D_HD void store_0_2(uint16_t* q) const { *reinterpret_cast<uint32_t*>(q) = r[0]; q[2] = (uint16_t)(r[1]&0xFFFFu); }
+	FX3D_HD void store_tail(uint16_t* q) const { q[1] = (uint16_t)(r[0]>>16); *reinterpret_cast<uint32_t*>(q+2) = r[1]; }
+	FX3D_HD void store_head(uint16_t* q) const { *reinterpret_cast<uint32_t*>(q) = r[0]; q[2] = (uint16_t)(r[1]&0xFFFFu); }
 	FX3D_HD uint32_t first_bits() const { return r[0]&0xFFFFu; }
 	FX3D_HD uint32_t last_bits() const { return r[1]>>16; }
 	FX3D_HD void push_back(uint32_t b) { r[0] = (r[0]>>16)|(r[1]<<16); r[1] = (r[1]>>16)|(b<<16); }
 	FX3D_HD void push_front(uint32_t b) { r[1] = (r[1]<<16)|(r[0]>>16); r[0] = (r[0]<<16)|(b&0xFFFFu); }
-	template<int k> FX3D_HD F2 get_pair() const { // to the working scale of Codec<ST>
-		if constexpr(ST==ST_FP16S) return unpack_half2_raw(r[k]);
-		else return vmul(make_f2(__uint_as_float(fp16c_decode_bits(r[k]&0xFFFFu)), __uint_as_float(fp16c_decode_bits(r[k]>>16))), vsplat<F2>(0x1p112f));
-	}
-	static FX3D_HD uint32_t encode_pair(F2 v) {
-		if constexpr(ST==ST_FP16S) return pack_half2_raw(v);
-		else { const F2 s = vmul_rz(v, vsplat<F2>(0x1p-112f)); return fp16c_encode_bits(f2_lo(s))|(fp16c_encode_bits(f2_hi(s))<<16); }
-	}
+	template<int k> FX3D_HD F2 get_pair() const { return decode_half_pair<ST>(r[k]); } // to the working scale of Codec<ST>
+	static FX3D_HD uint32_t encode_pair(F2 v) { return encode_half_pair<ST>(v); }
 	template<int k> FX3D_HD void set_pair(F2 v) { r[k] = encode_pair(v); }
 	template<int k> FX3D_HD void set_lanes(F2 v, bool lo, bool hi) { const uint32_t m = (lo ? 0x0000FFFFu : 0u)|(hi ? 0xFFFF0000u : 0u); r[k] = (encode_pair(v)&m)|(r[k]&~m); }
 	static FX3D_HD uint32_t bits(uint16_t v) { return (uint32_t)v; }
 	static FX3D_HD uint16_t from_bits(uint32_t b) { return (uint16_t)b; }
 };
 
+// ---- 2 consecutive x-elements of one slot: exactly one F2 lane pair ----
+template<> struct Pack<ST_FP32, 2> {
+	F2 p;
+	FX3D_HD void load(const float* q) { Pack<ST_FP32, 4>::memcpy_bits(p, *reinterpret_cast<const unsigned long long*>(q)); }
+	FX3D_HD void store(float* q) const { *reinterpret_cast<unsigned long long*>(q) = Pack<ST_FP32, 4>::bits64(p); }
+	FX3D_HD void store_tail(float* q) const { q[1] = f2_hi(p); }
+	FX3D_HD void store_head(float* q) const { q[0] = f2_lo(p); }
+	FX3D_HD uint32_t first_bits() const { return __float_as_uint(f2_lo(p)); }
+	FX3D_HD uint32_t last_bits() const { return __float_as_uint(f2_hi(p)); }
+	FX3D_HD void push_back(uint32_t b) { p = make_f2(f2_hi(p), __uint_as_float(b)); }
+	FX3D_HD void push_front(uint32_t b) { p = make_f2(__uint_as_float(b), f2_lo(p)); }
+	template<int k> FX3D_HD F2 get_pair() const { return p; }
+	template<int k> FX3D_HD void set_pair(F2 v) { p = v; }
+	template<int k> FX3D_HD void set_lanes(F2 v, bool lo, bool hi) { p = make_f2(lo ? f2_lo(v) : f2_lo(p), hi ? f2_hi(v) : f2_hi(p)); }
+	static FX3D_HD uint32_t bits(float v) { return __float_as_uint(v); }
+	static FX3D_HD float from_bits(uint32_t b) { return __uint_as_float(b); }
+};
+template<int ST> struct Pack<ST, 2> {
+	uint32_t r;
+	FX3D_HD void load(const uint16_t* q) { r = *reinterpret_cast<const uint32_t*>(q); }
+	FX3D_HD void store(uint16_t* q) const { *reinterpret_cast<uint32_t*>(q) = r; }
+	FX3D_HD void store_tail(uint16_t* q) const { q[1] = (uint16_t)(r>>16); }
+	FX3D_HD void store_head(uint16_t* q) const { q[0] = (uint16_t)(r&0xFFFFu); }
+	FX3D_HD uint32_t first_bits() const { return r&0xFFFFu; }
+	FX3D_HD uint32_t last_bits() const { return r>>16; }
+	FX3D_HD void push_back(uint32_t b) { r = (r>>16)|(b<<16); }
+	FX3D_HD void push_front(uint32_t b) { r = (r<<16)|(b&0xFFFFu); }
+	template<int k> FX3D_HD F2 get_pair() const { return decode_half_pair<ST>(r); }
+	template<int k> FX3D_HD void set_pair(F2 v) { r = encode_half_pair<ST>(v); }
+	template<int k> FX3D_HD void set_lanes(F2 v, bool lo, bool hi) { const uint32_t m = (lo ? 0x0000FFFFu : 0u)|(hi ? 0xFFFF0000u : 0u); r = (encode_half_pair<ST>(v)&m)|(r&~m); }
+	static FX3D_HD uint32_t bits(uint16_t v) { return (uint32_t)v; }
+	static FX3D_HD uint16_t from_bits(uint32_t b) { return (uint16_t)b; }
+};
+
 // ================================================================================================================
-// stream_collide, vector form: one thread owns 4 x-consecutive cells and moves every slot with one aligned
-// 16-byte (FP32) / 8-byte (FP16) access. Directions with an x component are misaligned by one element: the thread
+// stream_collide, vector form: one thread owns K (2 or 4) x-consecutive cells and moves every slot with one aligned
+// access of K elements (K=4: 16 bytes FP32 / 8 bytes FP16; K=2: 8 / 4 bytes). Directions with an x component are misaligned by one element: the thread
 // loads the aligned vector and obtains / hands over the straddling element by a warp shuffle; only at warp, block,
-// row or region ends does a lane fall back to one scalar access. The two cell pairs are collided in packed
+// row or region ends does a lane fall back to one scalar access. The cell pairs are collided in packed
 // binary32x2 arithmetic (F2). Every (cell,slot) is still read and written by exactly one thread (the Esoteric-Pull
 // invariant); solid cells' populations pass through unchanged.
 // ================================================================================================================
-template<int Q, int COLL, int ST, bool VF>
-__global__ void __launch_bounds__(128, FX3D_V4_MINBLOCKS) k_stream_collide_v4(const Lattice L, const Region R) {
-	constexpr int K = 4;
+template<int Q, int COLL, int ST, bool VF, int K>
+__global__ void __launch_bounds__(128, (K==4 ? FX3D_V4_MINBLOCKS : FX3D_V2_MINBLOCKS)) k_stream_collide_vec(const Lattice L, const Region R) {
 	constexpr unsigned FULL = 0xFFFFFFFFu;
 	typedef Codec<ST> C;
 	typedef typename C::elem_t E;
-	typedef Pack4<ST> P;
+	typedef Pack<ST, K> P;
 	const uint32_t g = R.g0+blockIdx.x*blockDim.x+threadIdx.x;
 	const uint32_t y = R.y0+blockIdx.y*blockDim.y+threadIdx.y;
 	const uint32_t z = R.z0+blockIdx.z;
 	const bool valid = g<R.g1 && y<R.y1;
 	if(!__any_sync(FULL, valid)) return; // warp-uniform
 	const uint32_t lane = (threadIdx.x+threadIdx.y*blockDim.x)&31u;
-	const bool has_right = valid && lane<31u && threadIdx.x+1u<blockDim.x && g+1u<R.g1; // lane+1 owns the next 4 cells of this row
-	const bool has_left = valid && lane>0u && threadIdx.x>0u;                           // lane-1 owns the previous 4 cells
+	const bool has_right = valid && lane<31u && threadIdx.x+1u<blockDim.x && g+1u<R.g1; // lane+1 owns the next K cells of this row
+	const bool has_left = valid && lane>0u && threadIdx.x>0u;                           // lane-1 owns the previous K cells
 	// Address of my vector in row (y+ey, z+ez) of slot s: one 64-bit pointer per distinct neighbour row, computed once,
 	// plus s*slot as a single 32x32+64 multiply-add (IMAD.WIDE.U32) on uniform operands. Lanes outside the region
 	// alias the last valid cell group for loads (clamped coordinates) and never store.
@@ -156,12 +194,17 @@ __global__ void __launch_bounds__(128, FX3D_V4_MINBLOCKS) k_stream_collide_v4(co
 	bool any_active = false;
 	if(valid) {
 		const uint8_t* fp = L.flags+lin(L, x0, yc, z);
-		if(((L.Nx|x0)&3u)==0u) { // rows are 4-byte aligned: one load for the 4 flags
-			const uint32_t f4 = *reinterpret_cast<const uint32_t*>(fp);
-			fl[0] = f4&0xFFu; fl[1] = (f4>>8)&0xFFu; fl[2] = (f4>>16)&0xFFu; fl[3] = f4>>24;
-		} else { fl[0] = fp[0]; fl[1] = fp[1]; fl[2] = fp[2]; fl[3] = fp[3]; }
-		any_active = (fl[0]&TYPE_BO)!=TYPE_S || (fl[1]&TYPE_BO)!=TYPE_S || (fl[2]&TYPE_BO)!=TYPE_S || (fl[3]&TYPE_BO)!=TYPE_S;
-	} else { fl[0] = fl[1] = fl[2] = fl[3] = TYPE_S; }
+		if constexpr(K==4) {
+			if(((L.Nx|x0)&3u)==0u) { // rows are 4-byte aligned: one load for the 4 flags
+				const uint32_t f4 = *reinterpret_cast<const uint32_t*>(fp);
+				fl[0] = f4&0xFFu; fl[1] = (f4>>8)&0xFFu; fl[2] = (f4>>16)&0xFFu; fl[3] = f4>>24;
+			} else { fl[0] = fp[0]; fl[1] = fp[1]; fl[2] = fp[2]; fl[3] = fp[3]; }
+		} else {
+			if(((L.Nx|x0)&1u)==0u) { const uint32_t f2 = *reinterpret_cast<const uint16_t*>(fp); fl[0] = f2&0xFFu; fl[1] = f2>>8; }
+			else { fl[0] = fp[0]; fl[1] = fp[1]; }
+		}
+		static_for<0, K, 1>([&](auto J) { any_active = any_active || (fl[J]&TYPE_BO)!=TYPE_S; });
+	} else { static_for<0, K, 1>([&](auto J) { fl[J] = TYPE_S; }); }
 	// ---- stream in: A[i] holds, per owned cell, the population that load_f() assigns to fhn[i] ----
 	P A[Q];
 	A[0].load(FX3D_AT(0, 0, 0u));
@@ -184,7 +227,7 @@ __global__ void __launch_bounds__(128, FX3D_V4_MINBLOCKS) k_stream_collide_v4(co
 	});
 
 	// ---- collide the two cell pairs in packed arithmetic ----
-	static_for<0, 2, 1>([&](auto Pp) {
+	static_for<0, K/2, 1>([&](auto Pp) {
 		constexpr int p = Pp;
 		const uint32_t fb_lo = fl[2*p]&TYPE_BO, fb_hi = fl[2*p+1]&TYPE_BO;
 		const bool act_lo = valid && fb_lo!=TYPE_S, act_hi = valid && fb_hi!=TYPE_S;
@@ -231,7 +274,7 @@ __global__ void __launch_bounds__(128, FX3D_V4_MINBLOCKS) k_stream_collide_v4(co
 				E* q = FX3D_AT(dir_y(i), dir_z(i), sn);
 				if(!has_right) q[dxr] = P::from_bits(last);
 				A[i+1].push_front(up); // {left lane's x0, mine x0+1..x0+3}
-				if(has_left) A[i+1].store(q); else A[i+1].store_1_3(q);
+				if(has_left) A[i+1].store(q); else A[i+1].store_tail(q);
 			}
 		} else { // my values belong to x0-1..x0+2
 			const uint32_t first = A[i+1].first_bits();
@@ -240,10 +283,222 @@ __global__ void __launch_bounds__(128, FX3D_V4_MINBLOCKS) k_stream_collide_v4(co
 				E* q = FX3D_AT(dir_y(i), dir_z(i), sn);
 				if(!has_left) q[dxl] = P::from_bits(first);
 				A[i+1].push_back(dn); // {mine x0..x0+2, right lane's x0+3}
-				if(has_right) A[i+1].store(q); else A[i+1].store_0_2(q);
+				if(has_right) A[i+1].store(q); else A[i+1].store_head(q);
 			}
 		}
 	});
+#undef FX3D_AT
+}
+
+// ================================================================================================================
+// stream_collide, pipelined form: the same per-tile work as the vector kernel, but every 128-thread block is persistent,
+// walks a strided list of tiles, and fetches the populations of the tile two iterations ahead with cp.async into its
+// shared-memory ring (each thread stages only its own 8-byte vectors, so no block barrier is needed: cp.async.wait_group
+// orders a thread's own copies). Loads therefore cost no registers while in flight and the memory system always has
+// (stages-1) tiles per warp outstanding, independent of occupancy. Vectors are 8 bytes: K=4 cells for 16-bit storage,
+// K=2 for FP32. In-place safety is unchanged: the addresses a tile reads are exactly the addresses it alone writes.
+// ================================================================================================================
+#ifndef FX3D_PIPE_MINBLOCKS
+#define FX3D_PIPE_MINBLOCKS 3
+#endif
+constexpr int PIPE_STAGES = 3;
+template<int Q> FX3D_HDC constexpr int x_dirs() { int n = 0; for(int i=1; i<Q; i+=2) if(dir_x(i)!=0) n++; return n; }
+template<int Q> FX3D_HDC constexpr int x_dir_rank(int i) { int n = 0; for(int k=1; k<i; k+=2) if(dir_x(k)!=0) n++; return n; } // position of odd direction i among the x-shifted ones
+template<int Q> FX3D_HDC constexpr uint32_t pipe_smem_bytes() { return (uint32_t)PIPE_STAGES*((uint32_t)Q*128u*8u+((uint32_t)x_dirs<Q>()+2u)*128u*4u); } // vectors, edge words, two flag words
+
+FX3D_HD void cp_async8(void* smem_dst, const void* gmem_src) {
+#if defined(FX3D_HOST_EMULATION)
+	std::memcpy(smem_dst, gmem_src, 8);
+#else
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+#endif
+}
+FX3D_HD void cp_async4(void* smem_dst, const void* gmem_src) {
+#if defined(FX3D_HOST_EMULATION)
+	std::memcpy(smem_dst, gmem_src, 4);
+#else
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+#endif
+}
+FX3D_HD void cp_async_commit() {
+#if !defined(FX3D_HOST_EMULATION)
+	asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template<int N> FX3D_HD void cp_async_wait() {
+#if !defined(FX3D_HOST_EMULATION)
+	asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+#endif
+}
+FX3D_HD unsigned char* dynamic_smem() {
+#if defined(FX3D_HOST_EMULATION)
+	return emul::block_smem();
+#else
+	extern __shared__ __align__(16) unsigned char fx3d_dynamic_smem[];
+	return fx3d_dynamic_smem;
+#endif
+}
+
+template<int Q, int COLL, int ST, bool VF>
+__global__ void __launch_bounds__(128, FX3D_PIPE_MINBLOCKS) k_stream_collide_pipe(const Lattice L, const Region R, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t ntiles) {
+	constexpr int K = ST==ST_FP32 ? 2 : 4; // 8-byte vectors
+	constexpr int S = PIPE_STAGES, NX = x_dirs<Q>();
+	constexpr unsigned FULL = 0xFFFFFFFFu;
+	typedef Codec<ST> C;
+	typedef typename C::elem_t E;
+	typedef Pack<ST, K> P;
+	static_assert(sizeof(E)*K==8, "pipelined kernel moves 8-byte vectors");
+	unsigned char* const smem = dynamic_smem();
+	const uint32_t tid = threadIdx.x+threadIdx.y*blockDim.x, lane = tid&31u;
+	auto vec_slot = [&](uint32_t stage, int i) -> unsigned char* { return smem+((size_t)(stage*(uint32_t)Q+(uint32_t)i)*128u+tid)*8u; };
+	auto edge_slot = [&](uint32_t stage, int k) -> uint32_t* { return reinterpret_cast<uint32_t*>(smem+(size_t)S*Q*128u*8u)+(stage*(uint32_t)(NX+2)+(uint32_t)k)*128u+tid; }; // k = NX, NX+1: flag words
+	const uint32_t odd = L.odd;
+
+	// tile T = xb + tiles_x*(yb + tiles_y*zt); this block owns T = blockIdx.x, blockIdx.x+gridDim.x, ...; coordinates advance by carries
+	struct Cursor { uint32_t T, xb, yb, zt; };
+	const uint32_t G = gridDim.x, sx = G%tiles_x, sy = (G/tiles_x)%tiles_y, sz = G/(tiles_x*tiles_y);
+	auto start = [&](uint32_t T) { return Cursor{ T, T%tiles_x, (T/tiles_x)%tiles_y, T/(tiles_x*tiles_y) }; };
+	auto advance = [&](Cursor& c) {
+		c.T += G; c.xb += sx; c.yb += sy; c.zt += sz;
+		if(c.xb>=tiles_x) { c.xb -= tiles_x; c.yb++; }
+		if(c.yb>=tiles_y) { c.yb -= tiles_y; c.zt++; }
+	};
+	// per-tile geometry of this thread
+	struct Geo { uint32_t g, y, z, x0, yc; bool valid, has_left, has_right; int dxr, dxl; char* rowp[3][3]; };
+	auto locate = [&](const Cursor& c, Geo& t) {
+		t.g = R.g0+c.xb*blockDim.x+threadIdx.x; t.y = R.y0+c.yb*blockDim.y+threadIdx.y; t.z = R.z0+c.zt;
+		t.valid = c.T<ntiles && t.g<R.g1 && t.y<R.y1;
+		t.has_right = t.valid && lane<31u && threadIdx.x+1u<blockDim.x && t.g+1u<R.g1;
+		t.has_left = t.valid && lane>0u && threadIdx.x>0u;
+		const uint32_t gc = t.g<R.g1 ? t.g : R.g1-1u, zc = t.z<R.z1 ? t.z : R.z1-1u;
+		t.yc = t.y<R.y1 ? t.y : R.y1-1u; t.z = zc;
+		t.x0 = L.Hx+(uint32_t)K*gc;
+		const uint32_t yy[3] = { dec(t.yc, L.Ny), t.yc, inc(t.yc, L.Ny) }, zz[3] = { dec(zc, L.Nz), zc, inc(zc, L.Nz) };
+		t.dxr = (t.x0+(uint32_t)K>=L.Nx ? 0 : (int)t.x0+K)-(int)t.x0;
+		t.dxl = (t.x0==0u ? (int)L.Nx-1 : (int)t.x0-1)-(int)t.x0;
+		static_for<0, 9, 1>([&](auto J) { constexpr int j = J; t.rowp[j/3][j%3] = reinterpret_cast<char*>(L.fi)+(row(L, yy[j/3], zz[j%3])+(uint64_t)(t.x0+L.xo))*sizeof(E); });
+	};
+#define FX3D_AT(t, ey, ez, s) reinterpret_cast<E*>(mad_wide(L.slot32, (s)*(uint32_t)sizeof(E), (t).rowp[(ey)+1][(ez)+1]))
+	// the 4-byte aligned word that holds the element `d` elements away from the vector start (16-bit storage: two elements per word)
+	auto edge_word = [&](E* q, int d) -> const void* { return reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(q+d)&~(uintptr_t)3u); };
+	auto edge_pick = [&](uint32_t w, E* q, int d) -> uint32_t { if constexpr(sizeof(E)==4) return w; else return (reinterpret_cast<uintptr_t>(q+d)&2u) ? w>>16 : w&0xFFFFu; };
+
+	auto issue = [&](const Cursor& c, uint32_t stage) { // start the copies of one tile: flag bytes (the one or two aligned words that hold them), vectors, edge words
+		Geo t; locate(c, t);
+		if(t.valid) {
+			const uintptr_t fa = reinterpret_cast<uintptr_t>(L.flags+lin(L, t.x0, t.yc, t.z));
+			cp_async4(edge_slot(stage, NX), reinterpret_cast<const void*>(fa&~(uintptr_t)3u));
+			if((fa&3u)+(uintptr_t)K>4u) cp_async4(edge_slot(stage, NX+1), reinterpret_cast<const void*>((fa&~(uintptr_t)3u)+4u));
+			cp_async8(vec_slot(stage, 0), FX3D_AT(t, 0, 0, 0u));
+			static_for<1, Q, 2>([&](auto I) {
+				constexpr int i = I;
+				cp_async8(vec_slot(stage, i), FX3D_AT(t, 0, 0, odd ? (uint32_t)i : (uint32_t)i+1u));
+				E* q = FX3D_AT(t, dir_y(i), dir_z(i), odd ? (uint32_t)i+1u : (uint32_t)i);
+				cp_async8(vec_slot(stage, i+1), q);
+				if constexpr(dir_x(i)>0) { if(!t.has_right) cp_async4(edge_slot(stage, x_dir_rank<Q>(i)), edge_word(q, t.dxr)); }
+				else if constexpr(dir_x(i)<0) { if(!t.has_left) cp_async4(edge_slot(stage, x_dir_rank<Q>(i)), edge_word(q, t.dxl)); }
+			});
+		}
+	};
+
+	Cursor ahead = start(blockIdx.x), cur = ahead;
+	issue(ahead, 0u); cp_async_commit(); advance(ahead);
+	issue(ahead, 1u); cp_async_commit(); advance(ahead);
+	for(uint32_t it=0u; cur.T<ntiles; it++) {
+		const uint32_t stage = it%(uint32_t)S;
+		issue(ahead, (it+2u)%(uint32_t)S); cp_async_commit(); advance(ahead);
+		cp_async_wait<S-1>(); // the copies of tile `cur` (two groups ago) have landed
+		Geo t; locate(cur, t);
+		uint32_t fl[K];
+		{
+			const uint32_t sh = 8u*(uint32_t)(reinterpret_cast<uintptr_t>(L.flags+lin(L, t.x0, t.yc, t.z))&3u);
+			const uint32_t w0 = *edge_slot(stage, NX), w1 = sh+8u*(uint32_t)K>32u ? *edge_slot(stage, NX+1) : 0u;
+			const uint32_t flags_word = sh==0u ? w0 : (w0>>sh)|(w1<<(32u-sh));
+			static_for<0, K, 1>([&](auto J) { fl[J] = t.valid ? (flags_word>>(8*J.value))&0xFFu : (uint32_t)TYPE_S; });
+		}
+		bool any_active = false;
+		static_for<0, K, 1>([&](auto J) { any_active = any_active || (t.valid && (fl[J]&TYPE_BO)!=TYPE_S); });
+
+		// ---- stream in from the ring ----
+		P A[Q];
+		static_for<0, Q, 1>([&](auto I) { A[I].load(reinterpret_cast<const E*>(vec_slot(stage, I))); });
+		static_for<1, Q, 2>([&](auto I) {
+			constexpr int i = I;
+			if constexpr(dir_x(i)>0) {
+				uint32_t b = __shfl_down_sync(FULL, A[i+1].first_bits(), 1u);
+				if(t.valid && !t.has_right) b = edge_pick(*edge_slot(stage, x_dir_rank<Q>(i)), FX3D_AT(t, dir_y(i), dir_z(i), odd ? (uint32_t)i+1u : (uint32_t)i), t.dxr);
+				A[i+1].push_back(b);
+			} else if constexpr(dir_x(i)<0) {
+				uint32_t b = __shfl_up_sync(FULL, A[i+1].last_bits(), 1u);
+				if(t.valid && !t.has_left) b = edge_pick(*edge_slot(stage, x_dir_rank<Q>(i)), FX3D_AT(t, dir_y(i), dir_z(i), odd ? (uint32_t)i+1u : (uint32_t)i), t.dxl);
+				A[i+1].push_front(b);
+			}
+		});
+
+		// ---- collide the cell pairs in packed arithmetic ----
+		static_for<0, K/2, 1>([&](auto Pp) {
+			constexpr int p = Pp;
+			const uint32_t fb_lo = fl[2*p]&TYPE_BO, fb_hi = fl[2*p+1]&TYPE_BO;
+			const bool act_lo = t.valid && fb_lo!=TYPE_S, act_hi = t.valid && fb_hi!=TYPE_S;
+			if(act_lo || act_hi) {
+				F2 f[Q];
+				static_for<0, Q, 1>([&](auto I) { f[I] = A[I].template get_pair<p>(); });
+				const bool e_lo = L.eb!=0u && act_lo && fb_lo==TYPE_E, e_hi = L.eb!=0u && act_hi && fb_hi==TYPE_E;
+				const uint64_t n = lin(L, t.x0+2u*(uint32_t)p, t.yc, t.z), N = cells(L);
+				F2 rho_e = vsplat<F2>(1.0f), ux_e = vsplat<F2>(0.0f), uy_e = ux_e, uz_e = ux_e;
+				if(e_lo || e_hi) {
+					const uint64_t nl = e_lo ? n : n+1ull, nh = e_hi ? n+1ull : n;
+					rho_e = make_f2(L.rho[nl], L.rho[nh]); ux_e = make_f2(L.u[nl], L.u[nh]); uy_e = make_f2(L.u[N+nl], L.u[N+nh]); uz_e = make_f2(L.u[2ull*N+nl], L.u[2ull*N+nh]);
+				}
+				F2 rhon, uxn, uyn, uzn;
+				collide_cell<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+				if(L.upd!=0u) {
+					if(act_lo && !e_lo) { L.rho[n] = f2_lo(rhon); L.u[n] = f2_lo(uxn); L.u[N+n] = f2_lo(uyn); L.u[2ull*N+n] = f2_lo(uzn); }
+					if(act_hi && !e_hi) { L.rho[n+1ull] = f2_hi(rhon); L.u[n+1ull] = f2_hi(uxn); L.u[N+n+1ull] = f2_hi(uyn); L.u[2ull*N+n+1ull] = f2_hi(uzn); }
+				}
+				if(act_lo && act_hi) {
+					A[0].template set_pair<p>(f[0]);
+					static_for<1, Q, 2>([&](auto I) { constexpr int i = I; A[i+1].template set_pair<p>(f[i]); A[i].template set_pair<p>(f[i+1]); });
+				} else {
+					A[0].template set_lanes<p>(f[0], act_lo, act_hi);
+					static_for<1, Q, 2>([&](auto I) { constexpr int i = I; A[i+1].template set_lanes<p>(f[i], act_lo, act_hi); A[i].template set_lanes<p>(f[i+1], act_lo, act_hi); });
+				}
+			}
+		});
+
+		// ---- stream out straight from registers (same addresses as stream in) ----
+		if(__any_sync(FULL, any_active)) {
+			if(t.valid) A[0].store(FX3D_AT(t, 0, 0, 0u));
+			static_for<1, Q, 2>([&](auto I) {
+				constexpr int i = I;
+				const uint32_t sl = odd ? (uint32_t)i : (uint32_t)i+1u, sn = odd ? (uint32_t)i+1u : (uint32_t)i;
+				if(t.valid) A[i].store(FX3D_AT(t, 0, 0, sl));
+				if constexpr(dir_x(i)==0) {
+					if(t.valid) A[i+1].store(FX3D_AT(t, dir_y(i), dir_z(i), sn));
+				} else if constexpr(dir_x(i)>0) {
+					const uint32_t last = A[i+1].last_bits();
+					const uint32_t up = __shfl_up_sync(FULL, last, 1u);
+					if(t.valid) {
+						E* q = FX3D_AT(t, dir_y(i), dir_z(i), sn);
+						if(!t.has_right) q[t.dxr] = P::from_bits(last);
+						A[i+1].push_front(up);
+						if(t.has_left) A[i+1].store(q); else A[i+1].store_tail(q);
+					}
+				} else {
+					const uint32_t first = A[i+1].first_bits();
+					const uint32_t dn = __shfl_down_sync(FULL, first, 1u);
+					if(t.valid) {
+						E* q = FX3D_AT(t, dir_y(i), dir_z(i), sn);
+						if(!t.has_left) q[t.dxl] = P::from_bits(first);
+						A[i+1].push_back(dn);
+						if(t.has_right) A[i+1].store(q); else A[i+1].store_head(q);
+					}
+				}
+			});
+		}
+		advance(cur);
+	}
+	cp_async_wait<0>();
 #undef FX3D_AT
 }
 

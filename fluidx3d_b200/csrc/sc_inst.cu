@@ -1,6 +1,7 @@
 // sc_inst.cu -- stream_collide instantiations for one (velocity set, storage) pair; compiled once per pair with
 // -DFX3D_Q=19|27 -DFX3D_ST=0|1|2 so that the six heavy translation units build in parallel.
 #include "fx3d_internal.cuh"
+#include <algorithm>
 
 namespace fx3d {
 
@@ -10,21 +11,52 @@ static inline dim3 block_shape(uint32_t nx) { // 128 threads; x extent = smalles
 	return dim3(bx, 128u/bx, 1u);
 }
 
-template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, bool vector4, int collision, bool volume_force, void* stream) {
+// persistent pipelined kernel: grid = resident blocks only (SM count x blocks per SM by shared memory), each block walks its tiles
+template<int Q, int COLL, int ST, bool VF> static int launch_pipe(const Lattice& L, const Region& R, const dim3& block, void* stream) {
+	const uint32_t tiles_x = (R.g1-R.g0+block.x-1u)/block.x, tiles_y = (R.y1-R.y0+block.y-1u)/block.y;
+	const uint64_t ntiles = (uint64_t)tiles_x*tiles_y*(R.z1-R.z0);
+	if(ntiles>0xFFFFFFFFull-65536ull) { set_error("region has too many tiles"); return FX3D_ERR_INVALID; }
+	constexpr uint32_t smem = pipe_smem_bytes<Q>();
+	int sms = 148, per_sm = (int)std::max(1u, std::min(3u, (227u*1024u)/(smem+1024u)));
+#if !defined(FX3D_HOST_EMULATION)
+	static bool configured = false; // per instantiation
+	int dev = 0; cudaGetDevice(&dev);
+	if(!configured) {
+		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_pipe<Q, COLL, ST, VF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if(e!=cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stream_collide_pipe)");
+		configured = true;
+	}
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#else
+	sms = 2; per_sm = 1;
+#endif
+	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, (uint64_t)sms*(uint64_t)per_sm), 1u, 1u);
+	FX3D_LAUNCH_SMEM((k_stream_collide_pipe<Q, COLL, ST, VF>), grid, block, smem, stream, L, R, tiles_x, tiles_y, (uint32_t)ntiles);
+	return check_launch("stream_collide (pipelined)");
+}
+
+template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, int cells_per_thread, int collision, bool volume_force, void* stream) {
 	if(R.g1<=R.g0||R.y1<=R.y0||R.z1<=R.z0) return FX3D_OK;
+	if(cells_per_thread==0) { // pipelined kernel; R.g0/g1 are in groups of K = 8 bytes / element size
+		const dim3 block = block_shape(R.g1-R.g0);
+		if(collision==COLL_SRT) return volume_force ? launch_pipe<Q, COLL_SRT, ST, true>(L, R, block, stream) : launch_pipe<Q, COLL_SRT, ST, false>(L, R, block, stream);
+		return volume_force ? launch_pipe<Q, COLL_TRT, ST, true>(L, R, block, stream) : launch_pipe<Q, COLL_TRT, ST, false>(L, R, block, stream);
+	}
 	const dim3 block = block_shape(R.g1-R.g0);
 	const dim3 grid((R.g1-R.g0+block.x-1u)/block.x, (R.y1-R.y0+block.y-1u)/block.y, R.z1-R.z0);
 #define FX3D_SC(KERNEL, COLL, VF) FX3D_LAUNCH((KERNEL<Q, COLL, ST, VF>), grid, block, stream, L, R)
-	if(vector4) {
-		if(collision==COLL_SRT) { if(volume_force) FX3D_SC(k_stream_collide_v4, COLL_SRT, true); else FX3D_SC(k_stream_collide_v4, COLL_SRT, false); }
-		else                    { if(volume_force) FX3D_SC(k_stream_collide_v4, COLL_TRT, true); else FX3D_SC(k_stream_collide_v4, COLL_TRT, false); }
-	} else {
-		if(collision==COLL_SRT) { if(volume_force) FX3D_SC(k_stream_collide_v1, COLL_SRT, true); else FX3D_SC(k_stream_collide_v1, COLL_SRT, false); }
-		else                    { if(volume_force) FX3D_SC(k_stream_collide_v1, COLL_TRT, true); else FX3D_SC(k_stream_collide_v1, COLL_TRT, false); }
-	}
+#define FX3D_SCV(K, COLL, VF) FX3D_LAUNCH((k_stream_collide_vec<Q, COLL, ST, VF, K>), grid, block, stream, L, R)
+#define FX3D_SC_ALL(MACRO, ARG) \
+	if(collision==COLL_SRT) { if(volume_force) MACRO(ARG, COLL_SRT, true); else MACRO(ARG, COLL_SRT, false); } \
+	else                    { if(volume_force) MACRO(ARG, COLL_TRT, true); else MACRO(ARG, COLL_TRT, false); }
+	if(cells_per_thread==4) { FX3D_SC_ALL(FX3D_SCV, 4) }
+	else if(cells_per_thread==2) { FX3D_SC_ALL(FX3D_SCV, 2) }
+	else { FX3D_SC_ALL(FX3D_SC, k_stream_collide_v1) }
+#undef FX3D_SC_ALL
+#undef FX3D_SCV
 #undef FX3D_SC
 	return check_launch("stream_collide");
 }
-template int launch_stream_collide<FX3D_Q, FX3D_ST>(const Lattice&, const Region&, bool, int, bool, void*);
+template int launch_stream_collide<FX3D_Q, FX3D_ST>(const Lattice&, const Region&, int, int, bool, void*);
 
 } // namespace fx3d

@@ -105,7 +105,8 @@ int fx3d_stream_collide(const fx3d_lattice* lattice, uint64_t t, float fx, float
 int fx3d_update_fields(const fx3d_lattice* lattice, uint64_t t, float fx, float fy, float fz, fx3d_stream stream);
 /* n consecutive stream_collide steps t0..t0+n-1 of a single (non-decomposed) domain, no host work in between */
 int fx3d_run_steps(const fx3d_lattice* lattice, uint64_t t0, uint64_t steps, float fx, float fy, float fz, fx3d_stream stream);
-/* force the general one-cell-per-thread kernel (1) or let the library choose (0, default); for tests and profiling */
+/* kernel choice for tests and profiling: 0 library default, 1 general one-cell-per-thread kernel, 2 or 4 vector kernel with
+ * that many cells per thread (falls back when the row length does not divide) */
 int fx3d_set_kernel_variant(int variant);
 int fx3d_launch_count(uint64_t* launches);                            /* kernels launched by this library so far */
 

@@ -44,7 +44,7 @@ struct WarpCtx {
 	int pred[32];
 	unsigned lanes;
 };
-struct ThreadCtx { WarpCtx* warp; unsigned lane; };
+struct ThreadCtx { WarpCtx* warp; unsigned lane; unsigned char* smem; };
 inline thread_local ThreadCtx tctx;
 }
 inline thread_local uint3_ threadIdx, blockIdx;
@@ -68,7 +68,8 @@ inline unsigned ballot(int p) {
 	w->bar->arrive_and_wait();
 	return m;
 }
-template<class F> void launch(dim3 grid, dim3 block, F&& body) {
+inline unsigned char* block_smem() { return tctx.smem; }
+template<class F> void launch(dim3 grid, dim3 block, F&& body, size_t smem_bytes=0) {
 	const unsigned nthreads = block.x*block.y*block.z, nwarps = (nthreads+31u)/32u;
 	for(unsigned bz=0u; bz<grid.z; bz++) for(unsigned by=0u; by<grid.y; by++) for(unsigned bx=0u; bx<grid.x; bx++) {
 		std::vector<WarpCtx> warps(nwarps);
@@ -76,13 +77,14 @@ template<class F> void launch(dim3 grid, dim3 block, F&& body) {
 			warps[wi].lanes = std::min(32u, nthreads-32u*wi);
 			warps[wi].bar = std::make_unique<std::barrier<>>((std::ptrdiff_t)warps[wi].lanes);
 		}
+		std::vector<unsigned char> smem(smem_bytes+16);
 		std::vector<std::thread> th;
 		th.reserve(nthreads);
 		for(unsigned tid=0u; tid<nthreads; tid++) th.emplace_back([&, tid]() {
 			threadIdx = uint3_{ tid%block.x, (tid/block.x)%block.y, tid/(block.x*block.y) };
 			blockIdx = uint3_{ bx, by, bz };
 			blockDim = block; gridDim = grid;
-			tctx.warp = &warps[tid/32u]; tctx.lane = tid%32u;
+			tctx.warp = &warps[tid/32u]; tctx.lane = tid%32u; tctx.smem = smem.data()+((16-reinterpret_cast<uintptr_t>(smem.data())%16)%16);
 			body();
 			tctx.warp->bar->arrive_and_drop(); // a thread that has returned no longer takes part in warp collectives
 		});

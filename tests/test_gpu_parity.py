@@ -57,7 +57,7 @@ VID = [f"q{v[0]}c{v[1]}s{v[2]}f{v[3]}" for v in VARIANTS]
 
 
 @pytest.mark.parametrize("v", VARIANTS, ids=VID)
-@pytest.mark.parametrize("variant", [0, 1], ids=["vector4", "general"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8], ids=["default", "general", "vector2", "vector4", "pipelined"])
 def test_fields_bit_exact_small(fx, v, variant):
     f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
     for dims, steps in [((32, 12, 10), 1), ((32, 12, 10), 2), ((32, 12, 10), 3), ((64, 9, 7), 10), ((20, 6, 5), 5), ((7, 5, 3), 4), ((132, 4, 3), 3)]:
@@ -66,12 +66,13 @@ def test_fields_bit_exact_small(fx, v, variant):
             assert np.array_equal(bits(a), bits(b)), (dims, steps)
 
 
+@pytest.mark.parametrize("variant", [4, 8], ids=["vector4", "pipelined"])
 @pytest.mark.parametrize("v", [(19, SRT, FP32, 0), (19, SRT, FP16S, 0), (19, SRT, FP16C, 0), (27, TRT, FP32, 3)], ids=["fp32", "fp16s", "fp16c", "q27trt"])
-def test_fields_bit_exact_medium_100_steps(fx, v):
+def test_fields_bit_exact_medium_100_steps(fx, v, variant):
     # SURVEY 8d parity fixtures: 64^3 and the non-cubic 96x64x48, perturbed IC, 100 steps
     f = (0.0, 1e-6, 0.0) if v[3] & 1 else (0.0, 0.0, 0.0)
     for dims in [(64, 64, 64), (96, 64, 48)]:
-        got, want = product(fx, v, dims, (1, 1, 1), 100, f), oracle(v, dims, (1, 1, 1), 100, f)
+        got, want = product(fx, v, dims, (1, 1, 1), 100, f, variant), oracle(v, dims, (1, 1, 1), 100, f)
         for a, b in zip(got, want):
             assert np.array_equal(bits(a), bits(b)), dims
 
@@ -103,7 +104,7 @@ def test_golden_vectors_from_reference_device_code(fx, path):
     g = np.load(path)
     Q, coll, st, feat, Nx, Ny, Nz, Dx, Dy, Dz, steps = (int(x) for x in g["meta"])
     f = tuple(float(x) for x in g["force"])
-    for variant in (0, 1):
+    for variant in (0, 1, 2, 4, 8):
         rho, ux, uy, uz, flags = product(fx, (Q, coll, st, feat), (Nx, Ny, Nz), (Dx, Dy, Dz), steps, f, variant, nu=float(g["nu"]), scen=(g["in_rho"], list(g["in_u"]), g["in_flags"]))
         assert np.array_equal(flags, g["out_flags"])
         assert np.array_equal(bits(rho), bits(g["out_rho"]))

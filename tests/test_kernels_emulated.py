@@ -52,7 +52,7 @@ CASES = [((19, SRT, FP32, 0), (16, 6, 4), (1, 1, 1)), ((19, SRT, FP16S, 0), (16,
 
 
 @pytest.mark.parametrize("v,dims,D", CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in CASES])
-@pytest.mark.parametrize("variant", [0, 1], ids=["vector4", "general"])
+@pytest.mark.parametrize("variant", [1, 2, 4, 8], ids=["general", "vector2", "vector4", "pipelined"])
 def test_emulated_kernels_match_oracle(emul, v, dims, D, variant):
     f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
     for steps in (1, 4):
