@@ -55,9 +55,8 @@ static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int re
 	const int want = g_variant.load();
 	uint32_t K = 1u;
 	bool pipelined = false;
-	if(want==8 || (want==0 && default_pipelined())) { // pipelined kernel: 8-byte vectors
-		const uint32_t k8 = lat->storage==FX3D_FP32 ? 2u : 4u;
-		if(inner%k8==0u) { K = k8; pipelined = true; }
+	if(want==8 || (want==0 && default_pipelined())) { // pipelined kernel: 4 cells per thread
+		if(inner%4u==0u) { K = 4u; pipelined = true; }
 	}
 	if(!pipelined && want!=1) {
 		const uint32_t pref = want==2 ? 2u : want==4 ? 4u : default_cells_per_thread((int)lat->storage);

@@ -15,6 +15,14 @@
 #pragma once
 #include "lbm_core.cuh"
 
+#ifndef FX3D_FUSED_COLLIDE
+#define FX3D_FUSED_COLLIDE 0 // 1: relax each direction pair as soon as its equilibrium exists (smaller live set)
+#endif
+#if FX3D_FUSED_COLLIDE
+#define FX3D_COLLIDE collide_cell_fused
+#else
+#define FX3D_COLLIDE collide_cell
+#endif
 #ifndef FX3D_V4_MINBLOCKS
 #define FX3D_V4_MINBLOCKS 3 // resident 128-thread blocks per SM the 4-cell vector kernel is compiled for (register cap 65536/(128*n))
 #endif
@@ -96,7 +104,7 @@ FX3D_HD uint32_t pack_half2_raw(F2 v) {
 }
 template<int ST> FX3D_HD F2 decode_half_pair(uint32_t r) { // two 16-bit elements -> working scale of Codec<ST>
 	if constexpr(ST==ST_FP16S) return unpack_half2_raw(r);
-	else return vmul(make_f2(__uint_as_float(fp16c_decode_bits(r&0xFFFFu)), __uint_as_float(fp16c_decode_bits(r>>16))), vsplat<F2>(0x1p112f));
+	else return vmul_packed(make_f2(__uint_as_float(fp16c_decode_bits(r&0xFFFFu)), __uint_as_float(fp16c_decode_bits(r>>16))), vsplat<F2>(0x1p112f)); // exact scaling
 }
 template<int ST> FX3D_HD uint32_t encode_half_pair(F2 v) {
 	if constexpr(ST==ST_FP16S) return pack_half2_raw(v);
@@ -162,7 +170,7 @@ template<int ST> struct Pack<ST, 2> {
 // binary32x2 arithmetic (F2). Every (cell,slot) is still read and written by exactly one thread (the Esoteric-Pull
 // invariant); solid cells' populations pass through unchanged.
 // ================================================================================================================
-template<int Q, int COLL, int ST, bool VF, int K>
+template<int Q, int COLL, int ST, bool VF, int K, int ODD>
 __global__ void __launch_bounds__(128, (K==4 ? FX3D_V4_MINBLOCKS : FX3D_V2_MINBLOCKS)) k_stream_collide_vec(const Lattice L, const Region R) {
 	constexpr unsigned FULL = 0xFFFFFFFFu;
 	typedef Codec<ST> C;
@@ -184,7 +192,7 @@ __global__ void __launch_bounds__(128, (K==4 ? FX3D_V4_MINBLOCKS : FX3D_V2_MINBL
 	const uint32_t yy[3] = { dec(yc, L.Ny), yc, inc(yc, L.Ny) }, zz[3] = { dec(z, L.Nz), z, inc(z, L.Nz) };
 	const int dxr = (x0+(uint32_t)K>=L.Nx ? 0 : (int)x0+K)-(int)x0; // element offset of the cell right of my vector (periodic wrap)
 	const int dxl = (x0==0u ? (int)L.Nx-1 : (int)x0-1)-(int)x0;     // element offset of the cell left of my vector
-	const uint32_t odd = L.odd;
+	constexpr uint32_t odd = (uint32_t)ODD; // step parity t&1 is a template parameter: slot numbers become immediates
 	char* rowp[3][3];
 	static_for<0, 9, 1>([&](auto J) { constexpr int j = J; rowp[j/3][j%3] = reinterpret_cast<char*>(L.fi)+(row(L, yy[j/3], zz[j%3])+(uint64_t)(x0+L.xo))*sizeof(E); });
 	auto at = [&](auto EY, auto EZ, uint32_t s) -> E* { return reinterpret_cast<E*>(mad_wide(L.slot32, s*(uint32_t)sizeof(E), rowp[EY.value+1][EZ.value+1])); };
@@ -242,7 +250,7 @@ __global__ void __launch_bounds__(128, (K==4 ? FX3D_V4_MINBLOCKS : FX3D_V2_MINBL
 				rho_e = make_f2(L.rho[nl], L.rho[nh]); ux_e = make_f2(L.u[nl], L.u[nh]); uy_e = make_f2(L.u[N+nl], L.u[N+nh]); uz_e = make_f2(L.u[2ull*N+nl], L.u[2ull*N+nh]);
 			}
 			F2 rhon, uxn, uyn, uzn;
-			collide_cell<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+			FX3D_COLLIDE<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
 			if(L.upd!=0u) {
 				if(act_lo && !e_lo) { L.rho[n] = f2_lo(rhon); L.u[n] = f2_lo(uxn); L.u[N+n] = f2_lo(uyn); L.u[2ull*N+n] = f2_lo(uzn); }
 				if(act_hi && !e_hi) { L.rho[n+1ull] = f2_hi(rhon); L.u[n+1ull] = f2_hi(uxn); L.u[N+n+1ull] = f2_hi(uyn); L.u[2ull*N+n+1ull] = f2_hi(uzn); }
@@ -293,18 +301,26 @@ __global__ void __launch_bounds__(128, (K==4 ? FX3D_V4_MINBLOCKS : FX3D_V2_MINBL
 // ================================================================================================================
 // stream_collide, pipelined form: the same per-tile work as the vector kernel, but every 128-thread block is persistent,
 // walks a strided list of tiles, and fetches the populations of the tile two iterations ahead with cp.async into its
-// shared-memory ring (each thread stages only its own 8-byte vectors, so no block barrier is needed: cp.async.wait_group
+// shared-memory ring (each thread stages only its own vectors, so no block barrier is needed: cp.async.wait_group
 // orders a thread's own copies). Loads therefore cost no registers while in flight and the memory system always has
-// (stages-1) tiles per warp outstanding, independent of occupancy. Vectors are 8 bytes: K=4 cells for 16-bit storage,
-// K=2 for FP32. In-place safety is unchanged: the addresses a tile reads are exactly the addresses it alone writes.
+// (stages-1) tiles per warp outstanding, independent of occupancy. Four cells per thread: 8-byte vectors for 16-bit
+// storage, 16-byte vectors for FP32. In-place safety is unchanged: the addresses a tile reads are exactly the addresses it alone writes.
 // ================================================================================================================
 #ifndef FX3D_PIPE_MINBLOCKS
 #define FX3D_PIPE_MINBLOCKS 3
 #endif
-constexpr int PIPE_STAGES = 3;
+#ifndef FX3D_PIPE_STAGES
+#define FX3D_PIPE_STAGES 3
+#endif
+constexpr int PIPE_STAGES = FX3D_PIPE_STAGES; // ring depth: tiles in flight per thread = stages-1
+template<int Q> FX3D_HDC constexpr bool row_used(int ey, int ez) { if(ey==0&&ez==0) return true; for(int i=1; i<Q; i+=2) if(dir_y(i)==ey&&dir_z(i)==ez) return true; return false; } // neighbour rows the odd directions reach
 template<int Q> FX3D_HDC constexpr int x_dirs() { int n = 0; for(int i=1; i<Q; i+=2) if(dir_x(i)!=0) n++; return n; }
 template<int Q> FX3D_HDC constexpr int x_dir_rank(int i) { int n = 0; for(int k=1; k<i; k+=2) if(dir_x(k)!=0) n++; return n; } // position of odd direction i among the x-shifted ones
-template<int Q> FX3D_HDC constexpr uint32_t pipe_smem_bytes() { return (uint32_t)PIPE_STAGES*((uint32_t)Q*128u*8u+((uint32_t)x_dirs<Q>()+2u)*128u*4u); } // vectors, edge words, two flag words
+// every thread moves 4 cells per tile: 8-byte vectors for 16-bit storage, 16-byte vectors for FP32 (which then affords only a 2-deep ring)
+template<int ST> FX3D_HDC constexpr int pipe_vector_bytes() { return ST==ST_FP32 ? 16 : 8; }
+template<int ST> FX3D_HDC constexpr int pipe_stages() { return ST==ST_FP32 ? 2 : PIPE_STAGES; }
+template<int ST> FX3D_HDC constexpr int pipe_blocks_per_sm() { return ST==ST_FP32 ? 2 : FX3D_PIPE_MINBLOCKS; } // also the register cap the kernel is compiled for
+template<int Q, int ST> FX3D_HDC constexpr uint32_t pipe_smem_bytes() { return (uint32_t)pipe_stages<ST>()*((uint32_t)Q*128u*(uint32_t)pipe_vector_bytes<ST>()+((uint32_t)x_dirs<Q>()+2u)*128u*4u); } // vectors, edge words, two flag words
 
 FX3D_HD void cp_async8(void* smem_dst, const void* gmem_src) {
 #if defined(FX3D_HOST_EMULATION)
@@ -313,6 +329,14 @@ FX3D_HD void cp_async8(void* smem_dst, const void* gmem_src) {
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 #endif
 }
+FX3D_HD void cp_async16(void* smem_dst, const void* gmem_src) {
+#if defined(FX3D_HOST_EMULATION)
+	std::memcpy(smem_dst, gmem_src, 16);
+#else
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+#endif
+}
+template<int BYTES> FX3D_HD void cp_async_vec(void* smem_dst, const void* gmem_src) { if constexpr(BYTES==16) cp_async16(smem_dst, gmem_src); else cp_async8(smem_dst, gmem_src); }
 FX3D_HD void cp_async4(void* smem_dst, const void* gmem_src) {
 #if defined(FX3D_HOST_EMULATION)
 	std::memcpy(smem_dst, gmem_src, 4);
@@ -339,167 +363,171 @@ FX3D_HD unsigned char* dynamic_smem() {
 #endif
 }
 
-template<int Q, int COLL, int ST, bool VF>
-__global__ void __launch_bounds__(128, FX3D_PIPE_MINBLOCKS) k_stream_collide_pipe(const Lattice L, const Region R, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t ntiles) {
-	constexpr int K = ST==ST_FP32 ? 2 : 4; // 8-byte vectors
-	constexpr int S = PIPE_STAGES, NX = x_dirs<Q>();
+template<int Q, int COLL, int ST, bool VF, int ODD>
+__global__ void __launch_bounds__(128, pipe_blocks_per_sm<ST>()) k_stream_collide_pipe(const Lattice L, const Region R, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t zchunk, const uint32_t nunits) {
+	// Work unit = one column of tiles (fixed x-group block and y rows) over a chunk of z planes; a block walks its units and, inside
+	// a unit, marches in z: the row pointers advance by one plane per tile instead of being rebuilt, and the tile S-1 planes ahead
+	// is addressed relative to them (uniform per-plane deltas, which also carry the periodic wrap).
+	constexpr int K = 4, VB = pipe_vector_bytes<ST>();
+	constexpr int S = pipe_stages<ST>(), NX = x_dirs<Q>();
 	constexpr unsigned FULL = 0xFFFFFFFFu;
+	constexpr uint32_t odd = (uint32_t)ODD;
 	typedef Codec<ST> C;
 	typedef typename C::elem_t E;
 	typedef Pack<ST, K> P;
-	static_assert(sizeof(E)*K==8, "pipelined kernel moves 8-byte vectors");
+	static_assert(sizeof(E)*K==VB, "vector size");
 	unsigned char* const smem = dynamic_smem();
 	const uint32_t tid = threadIdx.x+threadIdx.y*blockDim.x, lane = tid&31u;
-	auto vec_slot = [&](uint32_t stage, int i) -> unsigned char* { return smem+((size_t)(stage*(uint32_t)Q+(uint32_t)i)*128u+tid)*8u; };
-	auto edge_slot = [&](uint32_t stage, int k) -> uint32_t* { return reinterpret_cast<uint32_t*>(smem+(size_t)S*Q*128u*8u)+(stage*(uint32_t)(NX+2)+(uint32_t)k)*128u+tid; }; // k = NX, NX+1: flag words
-	const uint32_t odd = L.odd;
+	auto vec_slot = [&](uint32_t stage, int i) -> unsigned char* { return smem+((size_t)(stage*(uint32_t)Q+(uint32_t)i)*128u+tid)*(uint32_t)VB; };
+	auto edge_slot = [&](uint32_t stage, int k) -> uint32_t* { return reinterpret_cast<uint32_t*>(smem+(size_t)S*Q*128u*(uint32_t)VB)+(stage*(uint32_t)(NX+2)+(uint32_t)k)*128u+tid; }; // k = NX, NX+1: flag words
+	const uint32_t ncols = tiles_x*tiles_y;
+	const int64_t plane_bytes = (int64_t)((uint64_t)L.px*L.Ny*sizeof(E)), flag_plane = (int64_t)((uint64_t)L.Nx*L.Ny);
+	auto edge_word = [&](const char* q, int d) -> const void* { return reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(q+(int64_t)d*(int64_t)sizeof(E))&~(uintptr_t)3u); };
+	auto edge_pick = [&](uint32_t w, const char* q, int d) -> uint32_t { if constexpr(sizeof(E)==4) return w; else return (reinterpret_cast<uintptr_t>(q+(int64_t)d*(int64_t)sizeof(E))&2u) ? w>>16 : w&0xFFFFu; };
 
-	// tile T = xb + tiles_x*(yb + tiles_y*zt); this block owns T = blockIdx.x, blockIdx.x+gridDim.x, ...; coordinates advance by carries
-	struct Cursor { uint32_t T, xb, yb, zt; };
-	const uint32_t G = gridDim.x, sx = G%tiles_x, sy = (G/tiles_x)%tiles_y, sz = G/(tiles_x*tiles_y);
-	auto start = [&](uint32_t T) { return Cursor{ T, T%tiles_x, (T/tiles_x)%tiles_y, T/(tiles_x*tiles_y) }; };
-	auto advance = [&](Cursor& c) {
-		c.T += G; c.xb += sx; c.yb += sy; c.zt += sz;
-		if(c.xb>=tiles_x) { c.xb -= tiles_x; c.yb++; }
-		if(c.yb>=tiles_y) { c.yb -= tiles_y; c.zt++; }
-	};
-	// per-tile geometry of this thread
-	struct Geo { uint32_t g, y, z, x0, yc; bool valid, has_left, has_right; int dxr, dxl; char* rowp[3][3]; };
-	auto locate = [&](const Cursor& c, Geo& t) {
-		t.g = R.g0+c.xb*blockDim.x+threadIdx.x; t.y = R.y0+c.yb*blockDim.y+threadIdx.y; t.z = R.z0+c.zt;
-		t.valid = c.T<ntiles && t.g<R.g1 && t.y<R.y1;
-		t.has_right = t.valid && lane<31u && threadIdx.x+1u<blockDim.x && t.g+1u<R.g1;
-		t.has_left = t.valid && lane>0u && threadIdx.x>0u;
-		const uint32_t gc = t.g<R.g1 ? t.g : R.g1-1u, zc = t.z<R.z1 ? t.z : R.z1-1u;
-		t.yc = t.y<R.y1 ? t.y : R.y1-1u; t.z = zc;
-		t.x0 = L.Hx+(uint32_t)K*gc;
-		const uint32_t yy[3] = { dec(t.yc, L.Ny), t.yc, inc(t.yc, L.Ny) }, zz[3] = { dec(zc, L.Nz), zc, inc(zc, L.Nz) };
-		t.dxr = (t.x0+(uint32_t)K>=L.Nx ? 0 : (int)t.x0+K)-(int)t.x0;
-		t.dxl = (t.x0==0u ? (int)L.Nx-1 : (int)t.x0-1)-(int)t.x0;
-		static_for<0, 9, 1>([&](auto J) { constexpr int j = J; t.rowp[j/3][j%3] = reinterpret_cast<char*>(L.fi)+(row(L, yy[j/3], zz[j%3])+(uint64_t)(t.x0+L.xo))*sizeof(E); });
-	};
-#define FX3D_AT(t, ey, ez, s) reinterpret_cast<E*>(mad_wide(L.slot32, (s)*(uint32_t)sizeof(E), (t).rowp[(ey)+1][(ez)+1]))
-	// the 4-byte aligned word that holds the element `d` elements away from the vector start (16-bit storage: two elements per word)
-	auto edge_word = [&](E* q, int d) -> const void* { return reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(q+d)&~(uintptr_t)3u); };
-	auto edge_pick = [&](uint32_t w, E* q, int d) -> uint32_t { if constexpr(sizeof(E)==4) return w; else return (reinterpret_cast<uintptr_t>(q+d)&2u) ? w>>16 : w&0xFFFFu; };
-
-	auto issue = [&](const Cursor& c, uint32_t stage) { // start the copies of one tile: flag bytes (the one or two aligned words that hold them), vectors, edge words
-		Geo t; locate(c, t);
-		if(t.valid) {
-			const uintptr_t fa = reinterpret_cast<uintptr_t>(L.flags+lin(L, t.x0, t.yc, t.z));
+	for(uint32_t unit=blockIdx.x; unit<nunits; unit+=gridDim.x) {
+		// ---- column geometry (fixed for the whole unit) ----
+		const uint32_t col = unit%ncols, chunk = unit/ncols, xb = col%tiles_x, yb = col/tiles_x;
+		const uint32_t zs = R.z0+chunk*zchunk, ze = zs+zchunk<R.z1 ? zs+zchunk : R.z1;
+		const uint32_t g = R.g0+xb*blockDim.x+threadIdx.x, y = R.y0+yb*blockDim.y+threadIdx.y;
+		const bool valid = g<R.g1 && y<R.y1;
+		const bool has_right = valid && lane<31u && threadIdx.x+1u<blockDim.x && g+1u<R.g1;
+		const bool has_left = valid && lane>0u && threadIdx.x>0u;
+		const uint32_t gc = g<R.g1 ? g : R.g1-1u, yc = y<R.y1 ? y : R.y1-1u;
+		const uint32_t x0 = L.Hx+(uint32_t)K*gc;
+		const uint32_t yy[3] = { dec(yc, L.Ny), yc, inc(yc, L.Ny) };
+		const int dxr = (x0+(uint32_t)K>=L.Nx ? 0 : (int)x0+K)-(int)x0, dxl = (x0==0u ? (int)L.Nx-1 : (int)x0-1)-(int)x0;
+		const uint8_t* const flag_col = L.flags+((uint64_t)x0+(uint64_t)yc*L.Nx);
+		// rowp[ey][ez] points at my vector in row (yc+ey) of plane zref[ez]; slot s is added with one IMAD.WIDE
+		char* rowp[3][3];
+		uint32_t zref[3];
+		auto locate = [&](uint32_t z) {
+			zref[0] = dec(z, L.Nz); zref[1] = z; zref[2] = inc(z, L.Nz);
+			static_for<0, 9, 1>([&](auto J) { constexpr int j = J; if constexpr(row_used<Q>(j/3-1, j%3-1)) rowp[j/3][j%3] = reinterpret_cast<char*>(L.fi)+(row(L, yy[j/3], zref[j%3])+(uint64_t)(x0+L.xo))*sizeof(E); });
+		};
+		auto advance = [&](uint32_t z_next) { // z_next-1, z_next, z_next+1 are all inside [0,Nz): plain plane step
+			static_for<0, 9, 1>([&](auto J) { constexpr int j = J; if constexpr(row_used<Q>(j/3-1, j%3-1)) rowp[j/3][j%3] += plane_bytes; });
+			zref[0] = z_next-1u; zref[1] = z_next; zref[2] = z_next+1u;
+		};
+#define FX3D_AT(ey, ez, s) mad_wide(L.slot32, (s)*(uint32_t)sizeof(E), rowp[(ey)+1][(ez)+1])
+		auto issue = [&](uint32_t za, uint32_t stage) { // start the copies of the tile at plane za, addressed relative to the current row pointers
+			if(!valid) return;
+			const uint32_t zz[3] = { dec(za, L.Nz), za, inc(za, L.Nz) };
+			int64_t dz[3];
+			static_for<0, 3, 1>([&](auto J) { dz[J] = ((int64_t)zz[J]-(int64_t)zref[J])*plane_bytes; }); // uniform
+			const uintptr_t fa = reinterpret_cast<uintptr_t>(flag_col+(int64_t)za*flag_plane);
 			cp_async4(edge_slot(stage, NX), reinterpret_cast<const void*>(fa&~(uintptr_t)3u));
 			if((fa&3u)+(uintptr_t)K>4u) cp_async4(edge_slot(stage, NX+1), reinterpret_cast<const void*>((fa&~(uintptr_t)3u)+4u));
-			cp_async8(vec_slot(stage, 0), FX3D_AT(t, 0, 0, 0u));
+			cp_async_vec<VB>(vec_slot(stage, 0), FX3D_AT(0, 0, 0u)+dz[1]);
 			static_for<1, Q, 2>([&](auto I) {
 				constexpr int i = I;
-				cp_async8(vec_slot(stage, i), FX3D_AT(t, 0, 0, odd ? (uint32_t)i : (uint32_t)i+1u));
-				E* q = FX3D_AT(t, dir_y(i), dir_z(i), odd ? (uint32_t)i+1u : (uint32_t)i);
-				cp_async8(vec_slot(stage, i+1), q);
-				if constexpr(dir_x(i)>0) { if(!t.has_right) cp_async4(edge_slot(stage, x_dir_rank<Q>(i)), edge_word(q, t.dxr)); }
-				else if constexpr(dir_x(i)<0) { if(!t.has_left) cp_async4(edge_slot(stage, x_dir_rank<Q>(i)), edge_word(q, t.dxl)); }
+				cp_async_vec<VB>(vec_slot(stage, i), FX3D_AT(0, 0, odd ? (uint32_t)i : (uint32_t)i+1u)+dz[1]);
+				const char* q = FX3D_AT(dir_y(i), dir_z(i), odd ? (uint32_t)i+1u : (uint32_t)i)+dz[dir_z(i)+1];
+				cp_async_vec<VB>(vec_slot(stage, i+1), q);
+				if constexpr(dir_x(i)>0) { if(!has_right) cp_async4(edge_slot(stage, x_dir_rank<Q>(i)), edge_word(q, dxr)); }
+				else if constexpr(dir_x(i)<0) { if(!has_left) cp_async4(edge_slot(stage, x_dir_rank<Q>(i)), edge_word(q, dxl)); }
 			});
-		}
-	};
+		};
 
-	Cursor ahead = start(blockIdx.x), cur = ahead;
-	issue(ahead, 0u); cp_async_commit(); advance(ahead);
-	issue(ahead, 1u); cp_async_commit(); advance(ahead);
-	for(uint32_t it=0u; cur.T<ntiles; it++) {
-		const uint32_t stage = it%(uint32_t)S;
-		issue(ahead, (it+2u)%(uint32_t)S); cp_async_commit(); advance(ahead);
-		cp_async_wait<S-1>(); // the copies of tile `cur` (two groups ago) have landed
-		Geo t; locate(cur, t);
-		uint32_t fl[K];
-		{
-			const uint32_t sh = 8u*(uint32_t)(reinterpret_cast<uintptr_t>(L.flags+lin(L, t.x0, t.yc, t.z))&3u);
-			const uint32_t w0 = *edge_slot(stage, NX), w1 = sh+8u*(uint32_t)K>32u ? *edge_slot(stage, NX+1) : 0u;
-			const uint32_t flags_word = sh==0u ? w0 : (w0>>sh)|(w1<<(32u-sh));
-			static_for<0, K, 1>([&](auto J) { fl[J] = t.valid ? (flags_word>>(8*J.value))&0xFFu : (uint32_t)TYPE_S; });
-		}
-		bool any_active = false;
-		static_for<0, K, 1>([&](auto J) { any_active = any_active || (t.valid && (fl[J]&TYPE_BO)!=TYPE_S); });
-
-		// ---- stream in from the ring ----
-		P A[Q];
-		static_for<0, Q, 1>([&](auto I) { A[I].load(reinterpret_cast<const E*>(vec_slot(stage, I))); });
-		static_for<1, Q, 2>([&](auto I) {
-			constexpr int i = I;
-			if constexpr(dir_x(i)>0) {
-				uint32_t b = __shfl_down_sync(FULL, A[i+1].first_bits(), 1u);
-				if(t.valid && !t.has_right) b = edge_pick(*edge_slot(stage, x_dir_rank<Q>(i)), FX3D_AT(t, dir_y(i), dir_z(i), odd ? (uint32_t)i+1u : (uint32_t)i), t.dxr);
-				A[i+1].push_back(b);
-			} else if constexpr(dir_x(i)<0) {
-				uint32_t b = __shfl_up_sync(FULL, A[i+1].last_bits(), 1u);
-				if(t.valid && !t.has_left) b = edge_pick(*edge_slot(stage, x_dir_rank<Q>(i)), FX3D_AT(t, dir_y(i), dir_z(i), odd ? (uint32_t)i+1u : (uint32_t)i), t.dxl);
-				A[i+1].push_front(b);
+		locate(zs);
+		for(uint32_t k=0u; k<(uint32_t)(S-1); k++) { if(zs+k<ze) issue(zs+k, k); cp_async_commit(); }
+		for(uint32_t z=zs, it=0u; z<ze; z++, it++) {
+			const uint32_t stage = it%(uint32_t)S;
+			if(z+(uint32_t)(S-1)<ze) issue(z+(uint32_t)(S-1), (it+(uint32_t)(S-1))%(uint32_t)S);
+			cp_async_commit();
+			cp_async_wait<S-1>(); // the copies of plane z have landed
+			uint32_t fl[K];
+			{
+				const uint32_t sh = 8u*(uint32_t)(reinterpret_cast<uintptr_t>(flag_col+(int64_t)z*flag_plane)&3u);
+				const uint32_t w0 = *edge_slot(stage, NX), w1 = sh+8u*(uint32_t)K>32u ? *edge_slot(stage, NX+1) : 0u;
+				const uint32_t flags_word = sh==0u ? w0 : (w0>>sh)|(w1<<(32u-sh));
+				static_for<0, K, 1>([&](auto J) { fl[J] = valid ? (flags_word>>(8*J.value))&0xFFu : (uint32_t)TYPE_S; });
 			}
-		});
+			bool any_active = false;
+			static_for<0, K, 1>([&](auto J) { any_active = any_active || (fl[J]&TYPE_BO)!=TYPE_S; });
 
-		// ---- collide the cell pairs in packed arithmetic ----
-		static_for<0, K/2, 1>([&](auto Pp) {
-			constexpr int p = Pp;
-			const uint32_t fb_lo = fl[2*p]&TYPE_BO, fb_hi = fl[2*p+1]&TYPE_BO;
-			const bool act_lo = t.valid && fb_lo!=TYPE_S, act_hi = t.valid && fb_hi!=TYPE_S;
-			if(act_lo || act_hi) {
-				F2 f[Q];
-				static_for<0, Q, 1>([&](auto I) { f[I] = A[I].template get_pair<p>(); });
-				const bool e_lo = L.eb!=0u && act_lo && fb_lo==TYPE_E, e_hi = L.eb!=0u && act_hi && fb_hi==TYPE_E;
-				const uint64_t n = lin(L, t.x0+2u*(uint32_t)p, t.yc, t.z), N = cells(L);
-				F2 rho_e = vsplat<F2>(1.0f), ux_e = vsplat<F2>(0.0f), uy_e = ux_e, uz_e = ux_e;
-				if(e_lo || e_hi) {
-					const uint64_t nl = e_lo ? n : n+1ull, nh = e_hi ? n+1ull : n;
-					rho_e = make_f2(L.rho[nl], L.rho[nh]); ux_e = make_f2(L.u[nl], L.u[nh]); uy_e = make_f2(L.u[N+nl], L.u[N+nh]); uz_e = make_f2(L.u[2ull*N+nl], L.u[2ull*N+nh]);
-				}
-				F2 rhon, uxn, uyn, uzn;
-				collide_cell<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
-				if(L.upd!=0u) {
-					if(act_lo && !e_lo) { L.rho[n] = f2_lo(rhon); L.u[n] = f2_lo(uxn); L.u[N+n] = f2_lo(uyn); L.u[2ull*N+n] = f2_lo(uzn); }
-					if(act_hi && !e_hi) { L.rho[n+1ull] = f2_hi(rhon); L.u[n+1ull] = f2_hi(uxn); L.u[N+n+1ull] = f2_hi(uyn); L.u[2ull*N+n+1ull] = f2_hi(uzn); }
-				}
-				if(act_lo && act_hi) {
-					A[0].template set_pair<p>(f[0]);
-					static_for<1, Q, 2>([&](auto I) { constexpr int i = I; A[i+1].template set_pair<p>(f[i]); A[i].template set_pair<p>(f[i+1]); });
-				} else {
-					A[0].template set_lanes<p>(f[0], act_lo, act_hi);
-					static_for<1, Q, 2>([&](auto I) { constexpr int i = I; A[i+1].template set_lanes<p>(f[i], act_lo, act_hi); A[i].template set_lanes<p>(f[i+1], act_lo, act_hi); });
-				}
-			}
-		});
-
-		// ---- stream out straight from registers (same addresses as stream in) ----
-		if(__any_sync(FULL, any_active)) {
-			if(t.valid) A[0].store(FX3D_AT(t, 0, 0, 0u));
+			// ---- stream in from the ring ----
+			P A[Q];
+			static_for<0, Q, 1>([&](auto I) { A[I].load(reinterpret_cast<const E*>(vec_slot(stage, I))); });
 			static_for<1, Q, 2>([&](auto I) {
 				constexpr int i = I;
-				const uint32_t sl = odd ? (uint32_t)i : (uint32_t)i+1u, sn = odd ? (uint32_t)i+1u : (uint32_t)i;
-				if(t.valid) A[i].store(FX3D_AT(t, 0, 0, sl));
-				if constexpr(dir_x(i)==0) {
-					if(t.valid) A[i+1].store(FX3D_AT(t, dir_y(i), dir_z(i), sn));
-				} else if constexpr(dir_x(i)>0) {
-					const uint32_t last = A[i+1].last_bits();
-					const uint32_t up = __shfl_up_sync(FULL, last, 1u);
-					if(t.valid) {
-						E* q = FX3D_AT(t, dir_y(i), dir_z(i), sn);
-						if(!t.has_right) q[t.dxr] = P::from_bits(last);
-						A[i+1].push_front(up);
-						if(t.has_left) A[i+1].store(q); else A[i+1].store_tail(q);
+				if constexpr(dir_x(i)>0) {
+					uint32_t b = __shfl_down_sync(FULL, A[i+1].first_bits(), 1u);
+					if(valid && !has_right) b = edge_pick(*edge_slot(stage, x_dir_rank<Q>(i)), FX3D_AT(dir_y(i), dir_z(i), odd ? (uint32_t)i+1u : (uint32_t)i), dxr);
+					A[i+1].push_back(b);
+				} else if constexpr(dir_x(i)<0) {
+					uint32_t b = __shfl_up_sync(FULL, A[i+1].last_bits(), 1u);
+					if(valid && !has_left) b = edge_pick(*edge_slot(stage, x_dir_rank<Q>(i)), FX3D_AT(dir_y(i), dir_z(i), odd ? (uint32_t)i+1u : (uint32_t)i), dxl);
+					A[i+1].push_front(b);
+				}
+			});
+
+			// ---- collide the cell pairs in packed arithmetic ----
+			static_for<0, K/2, 1>([&](auto Pp) {
+				constexpr int p = Pp;
+				const uint32_t fb_lo = fl[2*p]&TYPE_BO, fb_hi = fl[2*p+1]&TYPE_BO;
+				const bool act_lo = fb_lo!=TYPE_S, act_hi = fb_hi!=TYPE_S; // lanes outside the region carry TYPE_S
+				if(act_lo || act_hi) {
+					F2 f[Q];
+					static_for<0, Q, 1>([&](auto I) { f[I] = A[I].template get_pair<p>(); });
+					const bool e_lo = L.eb!=0u && act_lo && fb_lo==TYPE_E, e_hi = L.eb!=0u && act_hi && fb_hi==TYPE_E;
+					const uint64_t n = lin(L, x0+2u*(uint32_t)p, yc, z), N = cells(L);
+					F2 rho_e = vsplat<F2>(1.0f), ux_e = vsplat<F2>(0.0f), uy_e = ux_e, uz_e = ux_e;
+					if(e_lo || e_hi) {
+						const uint64_t nl = e_lo ? n : n+1ull, nh = e_hi ? n+1ull : n;
+						rho_e = make_f2(L.rho[nl], L.rho[nh]); ux_e = make_f2(L.u[nl], L.u[nh]); uy_e = make_f2(L.u[N+nl], L.u[N+nh]); uz_e = make_f2(L.u[2ull*N+nl], L.u[2ull*N+nh]);
 					}
-				} else {
-					const uint32_t first = A[i+1].first_bits();
-					const uint32_t dn = __shfl_down_sync(FULL, first, 1u);
-					if(t.valid) {
-						E* q = FX3D_AT(t, dir_y(i), dir_z(i), sn);
-						if(!t.has_left) q[t.dxl] = P::from_bits(first);
-						A[i+1].push_back(dn);
-						if(t.has_right) A[i+1].store(q); else A[i+1].store_head(q);
+					F2 rhon, uxn, uyn, uzn;
+					FX3D_COLLIDE<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+					if(L.upd!=0u) {
+						if(act_lo && !e_lo) { L.rho[n] = f2_lo(rhon); L.u[n] = f2_lo(uxn); L.u[N+n] = f2_lo(uyn); L.u[2ull*N+n] = f2_lo(uzn); }
+						if(act_hi && !e_hi) { L.rho[n+1ull] = f2_hi(rhon); L.u[n+1ull] = f2_hi(uxn); L.u[N+n+1ull] = f2_hi(uyn); L.u[2ull*N+n+1ull] = f2_hi(uzn); }
+					}
+					if(act_lo && act_hi) {
+						A[0].template set_pair<p>(f[0]);
+						static_for<1, Q, 2>([&](auto I) { constexpr int i = I; A[i+1].template set_pair<p>(f[i]); A[i].template set_pair<p>(f[i+1]); });
+					} else {
+						A[0].template set_lanes<p>(f[0], act_lo, act_hi);
+						static_for<1, Q, 2>([&](auto I) { constexpr int i = I; A[i+1].template set_lanes<p>(f[i], act_lo, act_hi); A[i].template set_lanes<p>(f[i+1], act_lo, act_hi); });
 					}
 				}
 			});
+
+			// ---- stream out straight from registers (same addresses as stream in) ----
+			if(__any_sync(FULL, any_active)) {
+				if(valid) A[0].store(reinterpret_cast<E*>(FX3D_AT(0, 0, 0u)));
+				static_for<1, Q, 2>([&](auto I) {
+					constexpr int i = I;
+					const uint32_t sl = odd ? (uint32_t)i : (uint32_t)i+1u, sn = odd ? (uint32_t)i+1u : (uint32_t)i;
+					if(valid) A[i].store(reinterpret_cast<E*>(FX3D_AT(0, 0, sl)));
+					if constexpr(dir_x(i)==0) {
+						if(valid) A[i+1].store(reinterpret_cast<E*>(FX3D_AT(dir_y(i), dir_z(i), sn)));
+					} else if constexpr(dir_x(i)>0) {
+						const uint32_t last = A[i+1].last_bits();
+						const uint32_t up = __shfl_up_sync(FULL, last, 1u);
+						if(valid) {
+							E* q = reinterpret_cast<E*>(FX3D_AT(dir_y(i), dir_z(i), sn));
+							if(!has_right) q[dxr] = P::from_bits(last);
+							A[i+1].push_front(up);
+							if(has_left) A[i+1].store(q); else A[i+1].store_tail(q);
+						}
+					} else {
+						const uint32_t first = A[i+1].first_bits();
+						const uint32_t dn = __shfl_down_sync(FULL, first, 1u);
+						if(valid) {
+							E* q = reinterpret_cast<E*>(FX3D_AT(dir_y(i), dir_z(i), sn));
+							if(!has_left) q[dxl] = P::from_bits(first);
+							A[i+1].push_back(dn);
+							if(has_right) A[i+1].store(q); else A[i+1].store_head(q);
+						}
+					}
+				});
+			}
+			if(z+1u<ze) { if(z+2u<L.Nz && z>=0u && zref[0]+1u==z) advance(z+1u); else locate(z+1u); } // plain plane step unless a periodic wrap is involved
 		}
-		advance(cur);
-	}
-	cp_async_wait<0>();
+		cp_async_wait<0>();
 #undef FX3D_AT
+	}
 }
 
 // ================================================================================================================

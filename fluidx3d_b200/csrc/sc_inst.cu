@@ -12,17 +12,15 @@ static inline dim3 block_shape(uint32_t nx) { // 128 threads; x extent = smalles
 }
 
 // persistent pipelined kernel: grid = resident blocks only (SM count x blocks per SM by shared memory), each block walks its tiles
-template<int Q, int COLL, int ST, bool VF> static int launch_pipe(const Lattice& L, const Region& R, const dim3& block, void* stream) {
-	const uint32_t tiles_x = (R.g1-R.g0+block.x-1u)/block.x, tiles_y = (R.y1-R.y0+block.y-1u)/block.y;
-	const uint64_t ntiles = (uint64_t)tiles_x*tiles_y*(R.z1-R.z0);
-	if(ntiles>0xFFFFFFFFull-65536ull) { set_error("region has too many tiles"); return FX3D_ERR_INVALID; }
-	constexpr uint32_t smem = pipe_smem_bytes<Q>();
-	int sms = 148, per_sm = (int)std::max(1u, std::min(3u, (227u*1024u)/(smem+1024u)));
+template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_pipe_parity(const Lattice& L, const Region& R, const dim3& block, void* stream) {
+	const uint32_t tiles_x = (R.g1-R.g0+block.x-1u)/block.x, tiles_y = (R.y1-R.y0+block.y-1u)/block.y, nz = R.z1-R.z0;
+	constexpr uint32_t smem = pipe_smem_bytes<Q, ST>();
+	int sms = 148, per_sm = (int)std::max(1u, std::min((uint32_t)pipe_blocks_per_sm<ST>(), (227u*1024u)/(smem+1024u)));
 #if !defined(FX3D_HOST_EMULATION)
 	static bool configured = false; // per instantiation
 	int dev = 0; cudaGetDevice(&dev);
 	if(!configured) {
-		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_pipe<Q, COLL, ST, VF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_pipe<Q, COLL, ST, VF, ODD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if(e!=cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stream_collide_pipe)");
 		configured = true;
 	}
@@ -30,14 +28,24 @@ template<int Q, int COLL, int ST, bool VF> static int launch_pipe(const Lattice&
 #else
 	sms = 2; per_sm = 1;
 #endif
-	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, (uint64_t)sms*(uint64_t)per_sm), 1u, 1u);
-	FX3D_LAUNCH_SMEM((k_stream_collide_pipe<Q, COLL, ST, VF>), grid, block, smem, stream, L, R, tiles_x, tiles_y, (uint32_t)ntiles);
+	// units = columns of tiles x chunks of z planes: enough units per resident block for balance, chunks long enough to amortise the pipeline fill
+	const uint64_t blocks = (uint64_t)sms*(uint64_t)per_sm, ncols = (uint64_t)tiles_x*tiles_y;
+	uint32_t zchunk = nz;
+	while(zchunk>16u && ncols*((nz+zchunk-1u)/zchunk)<8ull*blocks) zchunk = (zchunk+1u)/2u;
+	const uint64_t nunits = ncols*((nz+zchunk-1u)/zchunk);
+	if(nunits>0xFFFFFFFFull-65536ull) { set_error("region has too many tiles"); return FX3D_ERR_INVALID; }
+	const dim3 grid((uint32_t)std::min<uint64_t>(nunits, blocks), 1u, 1u);
+	FX3D_LAUNCH_SMEM((k_stream_collide_pipe<Q, COLL, ST, VF, ODD>), grid, block, smem, stream, L, R, tiles_x, tiles_y, zchunk, (uint32_t)nunits);
 	return check_launch("stream_collide (pipelined)");
+}
+
+template<int Q, int COLL, int ST, bool VF> static int launch_pipe(const Lattice& L, const Region& R, const dim3& block, void* stream) {
+	return L.odd ? launch_pipe_parity<Q, COLL, ST, VF, 1>(L, R, block, stream) : launch_pipe_parity<Q, COLL, ST, VF, 0>(L, R, block, stream);
 }
 
 template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, int cells_per_thread, int collision, bool volume_force, void* stream) {
 	if(R.g1<=R.g0||R.y1<=R.y0||R.z1<=R.z0) return FX3D_OK;
-	if(cells_per_thread==0) { // pipelined kernel; R.g0/g1 are in groups of K = 8 bytes / element size
+	if(cells_per_thread==0) { // pipelined kernel; R.g0/g1 are in groups of 4 cells
 		const dim3 block = block_shape(R.g1-R.g0);
 		if(collision==COLL_SRT) return volume_force ? launch_pipe<Q, COLL_SRT, ST, true>(L, R, block, stream) : launch_pipe<Q, COLL_SRT, ST, false>(L, R, block, stream);
 		return volume_force ? launch_pipe<Q, COLL_TRT, ST, true>(L, R, block, stream) : launch_pipe<Q, COLL_TRT, ST, false>(L, R, block, stream);
@@ -45,7 +53,7 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 	const dim3 block = block_shape(R.g1-R.g0);
 	const dim3 grid((R.g1-R.g0+block.x-1u)/block.x, (R.y1-R.y0+block.y-1u)/block.y, R.z1-R.z0);
 #define FX3D_SC(KERNEL, COLL, VF) FX3D_LAUNCH((KERNEL<Q, COLL, ST, VF>), grid, block, stream, L, R)
-#define FX3D_SCV(K, COLL, VF) FX3D_LAUNCH((k_stream_collide_vec<Q, COLL, ST, VF, K>), grid, block, stream, L, R)
+#define FX3D_SCV(K, COLL, VF) do { if(L.odd) FX3D_LAUNCH((k_stream_collide_vec<Q, COLL, ST, VF, K, 1>), grid, block, stream, L, R); else FX3D_LAUNCH((k_stream_collide_vec<Q, COLL, ST, VF, K, 0>), grid, block, stream, L, R); } while(0)
 #define FX3D_SC_ALL(MACRO, ARG) \
 	if(collision==COLL_SRT) { if(volume_force) MACRO(ARG, COLL_SRT, true); else MACRO(ARG, COLL_SRT, false); } \
 	else                    { if(volume_force) MACRO(ARG, COLL_TRT, true); else MACRO(ARG, COLL_TRT, false); }

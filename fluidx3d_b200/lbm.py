@@ -381,7 +381,13 @@ class LBM:
         self.initialized = True
 
     def do_time_step(self):
-        for _, dom in self.local_domains(): dom.enqueue_stream_collide()
+        if self.overlap and self.get_D() > 1:
+            # shell first (the cells whose output the neighbours pull), then the interior; the two regions never touch the same
+            # (cell, slot), and the exchange only reads what the shell wrote
+            for _, dom in self.local_domains(): dom.enqueue_stream_collide(REGION_SHELL)
+            for _, dom in self.local_domains(): dom.enqueue_stream_collide(REGION_INTERIOR)
+        else:
+            for _, dom in self.local_domains(): dom.enqueue_stream_collide()
         if self.get_D() > 1: self.communicate_fi()
         for _, dom in self.local_domains(): dom.increment_time_step()
 
