@@ -47,7 +47,7 @@ static inline Region all_cells(const Lattice& L) { return Region{ L.Hx, L.Nx-L.H
 	else        { if(STv==FX3D_FP32) { constexpr int Q = 27, ST = ST_FP32; BODY } else if(STv==FX3D_FP16S) { constexpr int Q = 27, ST = ST_FP16S; BODY } else { constexpr int Q = 27, ST = ST_FP16C; BODY } }
 
 static uint32_t default_cells_per_thread(int storage) { (void)storage; return 4u; } // tuned on B200, see DESIGN.md
-static bool default_pipelined() { return false; }
+static bool default_pipelined(int region) { return region!=FX3D_REGION_SHELL; } // the persistent pipelined kernel marches in z; the one-cell shell slabs go to the vector kernel
 
 static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int region, void* stream) {
 	// cells per thread: the vector kernels need the non-halo row length to be a multiple of K; the general kernel takes any size
@@ -55,7 +55,7 @@ static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int re
 	const int want = g_variant.load();
 	uint32_t K = 1u;
 	bool pipelined = false;
-	if(want==8 || (want==0 && default_pipelined())) { // pipelined kernel: 4 cells per thread
+	if(want==8 || (want==0 && default_pipelined(region))) { // pipelined kernel: 4 cells per thread
 		if(inner%4u==0u) { K = 4u; pipelined = true; }
 	}
 	if(!pipelined && want!=1) {

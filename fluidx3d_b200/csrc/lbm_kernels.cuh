@@ -83,6 +83,7 @@ template<> struct Pack<ST_FP32, 4> {
 	template<int k> FX3D_HD F2 get_pair() const { return p[k]; }
 	template<int k> FX3D_HD void set_pair(F2 v) { p[k] = v; }
 	template<int k> FX3D_HD void set_lanes(F2 v, bool lo, bool hi) { p[k] = make_f2(lo ? f2_lo(v) : f2_lo(p[k]), hi ? f2_hi(v) : f2_hi(p[k])); }
+	template<int k> FX3D_HD void set_masked(F2 v, uint32_t m) { set_lanes<k>(v, (m&0xFFFFu)!=0u, (m>>16)!=0u); } // m: 0xFFFF per lane to overwrite
 	static FX3D_HD uint32_t bits(float v) { return __float_as_uint(v); }
 	static FX3D_HD float from_bits(uint32_t b) { return __uint_as_float(b); }
 #if defined(FX3D_HOST_EMULATION)
@@ -124,6 +125,7 @@ template<int ST> struct Pack<ST, 4> {
 	static FX3D_HD uint32_t encode_pair(F2 v) { return encode_half_pair<ST>(v); }
 	template<int k> FX3D_HD void set_pair(F2 v) { r[k] = encode_pair(v); }
 	template<int k> FX3D_HD void set_lanes(F2 v, bool lo, bool hi) { const uint32_t m = (lo ? 0x0000FFFFu : 0u)|(hi ? 0xFFFF0000u : 0u); r[k] = (encode_pair(v)&m)|(r[k]&~m); }
+	template<int k> FX3D_HD void set_masked(F2 v, uint32_t m) { r[k] = (encode_pair(v)&m)|(r[k]&~m); } // one LOP3; m: 0xFFFF per lane to overwrite
 	static FX3D_HD uint32_t bits(uint16_t v) { return (uint32_t)v; }
 	static FX3D_HD uint16_t from_bits(uint32_t b) { return (uint16_t)b; }
 };
@@ -142,6 +144,7 @@ template<> struct Pack<ST_FP32, 2> {
 	template<int k> FX3D_HD F2 get_pair() const { return p; }
 	template<int k> FX3D_HD void set_pair(F2 v) { p = v; }
 	template<int k> FX3D_HD void set_lanes(F2 v, bool lo, bool hi) { p = make_f2(lo ? f2_lo(v) : f2_lo(p), hi ? f2_hi(v) : f2_hi(p)); }
+	template<int k> FX3D_HD void set_masked(F2 v, uint32_t m) { set_lanes<k>(v, (m&0xFFFFu)!=0u, (m>>16)!=0u); }
 	static FX3D_HD uint32_t bits(float v) { return __float_as_uint(v); }
 	static FX3D_HD float from_bits(uint32_t b) { return __uint_as_float(b); }
 };
@@ -158,6 +161,7 @@ template<int ST> struct Pack<ST, 2> {
 	template<int k> FX3D_HD F2 get_pair() const { return decode_half_pair<ST>(r); }
 	template<int k> FX3D_HD void set_pair(F2 v) { r = encode_half_pair<ST>(v); }
 	template<int k> FX3D_HD void set_lanes(F2 v, bool lo, bool hi) { const uint32_t m = (lo ? 0x0000FFFFu : 0u)|(hi ? 0xFFFF0000u : 0u); r = (encode_half_pair<ST>(v)&m)|(r&~m); }
+	template<int k> FX3D_HD void set_masked(F2 v, uint32_t m) { r = (encode_half_pair<ST>(v)&m)|(r&~m); }
 	static FX3D_HD uint32_t bits(uint16_t v) { return (uint32_t)v; }
 	static FX3D_HD uint16_t from_bits(uint32_t b) { return (uint16_t)b; }
 };
@@ -307,11 +311,15 @@ __global__ void __launch_bounds__(128, (K==4 ? FX3D_V4_MINBLOCKS : FX3D_V2_MINBL
 // storage, 16-byte vectors for FP32. In-place safety is unchanged: the addresses a tile reads are exactly the addresses it alone writes.
 // ================================================================================================================
 #ifndef FX3D_PIPE_MINBLOCKS
-#define FX3D_PIPE_MINBLOCKS 3
+#define FX3D_PIPE_MINBLOCKS 4
 #endif
 #ifndef FX3D_PIPE_STAGES
-#define FX3D_PIPE_STAGES 3
+#define FX3D_PIPE_STAGES 2
 #endif
+#ifndef FX3D_PIPE_COLLIDE // collision formulation of the pipelined kernel: 0 collide_cell (all Q populations and equilibria live), 1 collide_cell_fused
+#define FX3D_PIPE_COLLIDE -1 // (relax pair by pair), 2 collide_cell_stream (populations unpacked on demand); -1: per storage, as measured on B200
+#endif
+template<int ST> FX3D_HDC constexpr int pipe_collide_mode() { return FX3D_PIPE_COLLIDE>=0 ? FX3D_PIPE_COLLIDE : ST==ST_FP32 ? 1 : 2; }
 constexpr int PIPE_STAGES = FX3D_PIPE_STAGES; // ring depth: tiles in flight per thread = stages-1
 template<int Q> FX3D_HDC constexpr bool row_used(int ey, int ez) { if(ey==0&&ez==0) return true; for(int i=1; i<Q; i+=2) if(dir_y(i)==ey&&dir_z(i)==ez) return true; return false; } // neighbour rows the odd directions reach
 template<int Q> FX3D_HDC constexpr int x_dirs() { int n = 0; for(int i=1; i<Q; i+=2) if(dir_x(i)!=0) n++; return n; }
@@ -319,7 +327,7 @@ template<int Q> FX3D_HDC constexpr int x_dir_rank(int i) { int n = 0; for(int k=
 // every thread moves 4 cells per tile: 8-byte vectors for 16-bit storage, 16-byte vectors for FP32 (which then affords only a 2-deep ring)
 template<int ST> FX3D_HDC constexpr int pipe_vector_bytes() { return ST==ST_FP32 ? 16 : 8; }
 template<int ST> FX3D_HDC constexpr int pipe_stages() { return ST==ST_FP32 ? 2 : PIPE_STAGES; }
-template<int ST> FX3D_HDC constexpr int pipe_blocks_per_sm() { return ST==ST_FP32 ? 2 : FX3D_PIPE_MINBLOCKS; } // also the register cap the kernel is compiled for
+template<int Q, int ST> FX3D_HDC constexpr int pipe_blocks_per_sm() { return ST==ST_FP32 ? 2 : (Q>19 && FX3D_PIPE_MINBLOCKS>3) ? 3 : FX3D_PIPE_MINBLOCKS; } // also the register cap the kernel is compiled for
 template<int Q, int ST> FX3D_HDC constexpr uint32_t pipe_smem_bytes() { return (uint32_t)pipe_stages<ST>()*((uint32_t)Q*128u*(uint32_t)pipe_vector_bytes<ST>()+((uint32_t)x_dirs<Q>()+2u)*128u*4u); } // vectors, edge words, two flag words
 
 FX3D_HD void cp_async8(void* smem_dst, const void* gmem_src) {
@@ -364,7 +372,7 @@ FX3D_HD unsigned char* dynamic_smem() {
 }
 
 template<int Q, int COLL, int ST, bool VF, int ODD>
-__global__ void __launch_bounds__(128, pipe_blocks_per_sm<ST>()) k_stream_collide_pipe(const Lattice L, const Region R, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t zchunk, const uint32_t nunits) {
+__global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_collide_pipe(const Lattice L, const Region R, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t zchunk, const uint32_t nunits) {
 	// Work unit = one column of tiles (fixed x-group block and y rows) over a chunk of z planes; a block walks its units and, inside
 	// a unit, marches in z: the row pointers advance by one plane per tile instead of being rebuilt, and the tile S-1 planes ahead
 	// is addressed relative to them (uniform per-plane deltas, which also carry the periodic wrap).
@@ -398,31 +406,25 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<ST>()) k_stream_collid
 		const uint32_t yy[3] = { dec(yc, L.Ny), yc, inc(yc, L.Ny) };
 		const int dxr = (x0+(uint32_t)K>=L.Nx ? 0 : (int)x0+K)-(int)x0, dxl = (x0==0u ? (int)L.Nx-1 : (int)x0-1)-(int)x0;
 		const uint8_t* const flag_col = L.flags+((uint64_t)x0+(uint64_t)yc*L.Nx);
-		// rowp[ey][ez] points at my vector in row (yc+ey) of plane zref[ez]; slot s is added with one IMAD.WIDE
-		char* rowp[3][3];
-		uint32_t zref[3];
+		// colp[ey] points at my vector in row (yc+ey) of the current plane z; slot s is added with one IMAD.WIDE, the neighbour
+		// planes z-1 / z+1 (periodic wrap included) with a uniform byte offset
+		char* colp[3];
 		auto locate = [&](uint32_t z) {
-			zref[0] = dec(z, L.Nz); zref[1] = z; zref[2] = inc(z, L.Nz);
-			static_for<0, 9, 1>([&](auto J) { constexpr int j = J; if constexpr(row_used<Q>(j/3-1, j%3-1)) rowp[j/3][j%3] = reinterpret_cast<char*>(L.fi)+(row(L, yy[j/3], zref[j%3])+(uint64_t)(x0+L.xo))*sizeof(E); });
+			static_for<0, 3, 1>([&](auto J) { colp[J] = reinterpret_cast<char*>(L.fi)+(row(L, yy[J], z)+(uint64_t)(x0+L.xo))*sizeof(E); });
 		};
-		auto advance = [&](uint32_t z_next) { // z_next-1, z_next, z_next+1 are all inside [0,Nz): plain plane step
-			static_for<0, 9, 1>([&](auto J) { constexpr int j = J; if constexpr(row_used<Q>(j/3-1, j%3-1)) rowp[j/3][j%3] += plane_bytes; });
-			zref[0] = z_next-1u; zref[1] = z_next; zref[2] = z_next+1u;
-		};
-#define FX3D_AT(ey, ez, s) mad_wide(L.slot32, (s)*(uint32_t)sizeof(E), rowp[(ey)+1][(ez)+1])
-		auto issue = [&](uint32_t za, uint32_t stage) { // start the copies of the tile at plane za, addressed relative to the current row pointers
+		auto plane_delta = [&](uint32_t zfrom, uint32_t zto) -> int64_t { return ((int64_t)zto-(int64_t)zfrom)*plane_bytes; }; // uniform
+#define FX3D_AT(ey, s) mad_wide(L.slot32, (s)*(uint32_t)sizeof(E), colp[(ey)+1])
+		auto issue = [&](uint32_t zcur, uint32_t za, uint32_t stage) { // start the copies of the tile at plane za, addressed relative to the pointers of plane zcur
 			if(!valid) return;
-			const uint32_t zz[3] = { dec(za, L.Nz), za, inc(za, L.Nz) };
-			int64_t dz[3];
-			static_for<0, 3, 1>([&](auto J) { dz[J] = ((int64_t)zz[J]-(int64_t)zref[J])*plane_bytes; }); // uniform
+			const int64_t dz[3] = { plane_delta(zcur, dec(za, L.Nz)), plane_delta(zcur, za), plane_delta(zcur, inc(za, L.Nz)) };
 			const uintptr_t fa = reinterpret_cast<uintptr_t>(flag_col+(int64_t)za*flag_plane);
 			cp_async4(edge_slot(stage, NX), reinterpret_cast<const void*>(fa&~(uintptr_t)3u));
 			if((fa&3u)+(uintptr_t)K>4u) cp_async4(edge_slot(stage, NX+1), reinterpret_cast<const void*>((fa&~(uintptr_t)3u)+4u));
-			cp_async_vec<VB>(vec_slot(stage, 0), FX3D_AT(0, 0, 0u)+dz[1]);
+			cp_async_vec<VB>(vec_slot(stage, 0), FX3D_AT(0, 0u)+dz[1]);
 			static_for<1, Q, 2>([&](auto I) {
 				constexpr int i = I;
-				cp_async_vec<VB>(vec_slot(stage, i), FX3D_AT(0, 0, odd ? (uint32_t)i : (uint32_t)i+1u)+dz[1]);
-				const char* q = FX3D_AT(dir_y(i), dir_z(i), odd ? (uint32_t)i+1u : (uint32_t)i)+dz[dir_z(i)+1];
+				cp_async_vec<VB>(vec_slot(stage, i), FX3D_AT(0, odd ? (uint32_t)i : (uint32_t)i+1u)+dz[1]);
+				const char* q = FX3D_AT(dir_y(i), odd ? (uint32_t)i+1u : (uint32_t)i)+dz[dir_z(i)+1];
 				cp_async_vec<VB>(vec_slot(stage, i+1), q);
 				if constexpr(dir_x(i)>0) { if(!has_right) cp_async4(edge_slot(stage, x_dir_rank<Q>(i)), edge_word(q, dxr)); }
 				else if constexpr(dir_x(i)<0) { if(!has_left) cp_async4(edge_slot(stage, x_dir_rank<Q>(i)), edge_word(q, dxl)); }
@@ -430,10 +432,11 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<ST>()) k_stream_collid
 		};
 
 		locate(zs);
-		for(uint32_t k=0u; k<(uint32_t)(S-1); k++) { if(zs+k<ze) issue(zs+k, k); cp_async_commit(); }
+		for(uint32_t k=0u; k<(uint32_t)(S-1); k++) { if(zs+k<ze) issue(zs, zs+k, k); cp_async_commit(); }
 		for(uint32_t z=zs, it=0u; z<ze; z++, it++) {
 			const uint32_t stage = it%(uint32_t)S;
-			if(z+(uint32_t)(S-1)<ze) issue(z+(uint32_t)(S-1), (it+(uint32_t)(S-1))%(uint32_t)S);
+			if(z+(uint32_t)(S-1)<ze) issue(z, z+(uint32_t)(S-1), (it+(uint32_t)(S-1))%(uint32_t)S);
+			const int64_t dzn[3] = { plane_delta(z, dec(z, L.Nz)), 0, plane_delta(z, inc(z, L.Nz)) }; // neighbour planes of this tile
 			cp_async_commit();
 			cp_async_wait<S-1>(); // the copies of plane z have landed
 			uint32_t fl[K];
@@ -453,11 +456,11 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<ST>()) k_stream_collid
 				constexpr int i = I;
 				if constexpr(dir_x(i)>0) {
 					uint32_t b = __shfl_down_sync(FULL, A[i+1].first_bits(), 1u);
-					if(valid && !has_right) b = edge_pick(*edge_slot(stage, x_dir_rank<Q>(i)), FX3D_AT(dir_y(i), dir_z(i), odd ? (uint32_t)i+1u : (uint32_t)i), dxr);
+					if(valid && !has_right) b = edge_pick(*edge_slot(stage, x_dir_rank<Q>(i)), FX3D_AT(dir_y(i), odd ? (uint32_t)i+1u : (uint32_t)i)+dzn[dir_z(i)+1], dxr);
 					A[i+1].push_back(b);
 				} else if constexpr(dir_x(i)<0) {
 					uint32_t b = __shfl_up_sync(FULL, A[i+1].last_bits(), 1u);
-					if(valid && !has_left) b = edge_pick(*edge_slot(stage, x_dir_rank<Q>(i)), FX3D_AT(dir_y(i), dir_z(i), odd ? (uint32_t)i+1u : (uint32_t)i), dxl);
+					if(valid && !has_left) b = edge_pick(*edge_slot(stage, x_dir_rank<Q>(i)), FX3D_AT(dir_y(i), odd ? (uint32_t)i+1u : (uint32_t)i)+dzn[dir_z(i)+1], dxl);
 					A[i+1].push_front(b);
 				}
 			});
@@ -468,8 +471,6 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<ST>()) k_stream_collid
 				const uint32_t fb_lo = fl[2*p]&TYPE_BO, fb_hi = fl[2*p+1]&TYPE_BO;
 				const bool act_lo = fb_lo!=TYPE_S, act_hi = fb_hi!=TYPE_S; // lanes outside the region carry TYPE_S
 				if(act_lo || act_hi) {
-					F2 f[Q];
-					static_for<0, Q, 1>([&](auto I) { f[I] = A[I].template get_pair<p>(); });
 					const bool e_lo = L.eb!=0u && act_lo && fb_lo==TYPE_E, e_hi = L.eb!=0u && act_hi && fb_hi==TYPE_E;
 					const uint64_t n = lin(L, x0+2u*(uint32_t)p, yc, z), N = cells(L);
 					F2 rho_e = vsplat<F2>(1.0f), ux_e = vsplat<F2>(0.0f), uy_e = ux_e, uz_e = ux_e;
@@ -478,35 +479,59 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<ST>()) k_stream_collid
 						rho_e = make_f2(L.rho[nl], L.rho[nh]); ux_e = make_f2(L.u[nl], L.u[nh]); uy_e = make_f2(L.u[N+nl], L.u[N+nh]); uz_e = make_f2(L.u[2ull*N+nl], L.u[2ull*N+nh]);
 					}
 					F2 rhon, uxn, uyn, uzn;
-					FX3D_COLLIDE<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
-					if(L.upd!=0u) {
-						if(act_lo && !e_lo) { L.rho[n] = f2_lo(rhon); L.u[n] = f2_lo(uxn); L.u[N+n] = f2_lo(uyn); L.u[2ull*N+n] = f2_lo(uzn); }
-						if(act_hi && !e_hi) { L.rho[n+1ull] = f2_hi(rhon); L.u[n+1ull] = f2_hi(uxn); L.u[N+n+1ull] = f2_hi(uyn); L.u[2ull*N+n+1ull] = f2_hi(uzn); }
-					}
-					if(act_lo && act_hi) {
+					const bool both = act_lo && act_hi;
+					if constexpr(pipe_collide_mode<ST>()==2) {
+					// populations are unpacked on demand and the results packed straight into the slot they stream out through:
+					// store_f() sends fhn[i] to the neighbour-side slot (A[i+1]) and fhn[i+1] to the local slot (A[i])
+					auto get = [&](auto I) { return A[I.value].template get_pair<p>(); };
+					const uint32_t am = (act_lo ? 0x0000FFFFu : 0u)|(act_hi ? 0xFFFF0000u : 0u), em = (e_lo ? 0x0000FFFFu : 0u)|(e_hi ? 0xFFFF0000u : 0u);
+					auto put = [&](auto I, F2 v) { // lanes that are not collided here keep what they streamed in
+						constexpr int i = I.value;
+						constexpr int dst = i==0 ? 0 : (i&1) ? i+1 : i-1;
+						if constexpr(sizeof(E)==2) A[dst].template set_masked<p>(v, am);
+						else { if(both) A[dst].template set_pair<p>(v); else A[dst].template set_lanes<p>(v, act_lo, act_hi); }
+					};
+					auto put_e = [&](auto I, F2 v) { // equilibrium-boundary lanes only
+						constexpr int i = I.value;
+						constexpr int dst = i==0 ? 0 : (i&1) ? i+1 : i-1;
+						A[dst].template set_masked<p>(v, em);
+					};
+					// within a direction pair both members are read before either is written, so the in-place swap is safe
+					collide_cell_stream<Q, COLL, VF, F2>(get, put, put_e, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+					} else {
+					F2 f[Q];
+					static_for<0, Q, 1>([&](auto I) { f[I] = A[I].template get_pair<p>(); });
+					if constexpr(pipe_collide_mode<ST>()==1) collide_cell_fused<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+					else collide_cell<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+					if(both) {
 						A[0].template set_pair<p>(f[0]);
 						static_for<1, Q, 2>([&](auto I) { constexpr int i = I; A[i+1].template set_pair<p>(f[i]); A[i].template set_pair<p>(f[i+1]); });
 					} else {
 						A[0].template set_lanes<p>(f[0], act_lo, act_hi);
 						static_for<1, Q, 2>([&](auto I) { constexpr int i = I; A[i+1].template set_lanes<p>(f[i], act_lo, act_hi); A[i].template set_lanes<p>(f[i+1], act_lo, act_hi); });
 					}
+					}
+					if(L.upd!=0u) {
+						if(act_lo && !e_lo) { L.rho[n] = f2_lo(rhon); L.u[n] = f2_lo(uxn); L.u[N+n] = f2_lo(uyn); L.u[2ull*N+n] = f2_lo(uzn); }
+						if(act_hi && !e_hi) { L.rho[n+1ull] = f2_hi(rhon); L.u[n+1ull] = f2_hi(uxn); L.u[N+n+1ull] = f2_hi(uyn); L.u[2ull*N+n+1ull] = f2_hi(uzn); }
+					}
 				}
 			});
 
 			// ---- stream out straight from registers (same addresses as stream in) ----
 			if(__any_sync(FULL, any_active)) {
-				if(valid) A[0].store(reinterpret_cast<E*>(FX3D_AT(0, 0, 0u)));
+				if(valid) A[0].store(reinterpret_cast<E*>(FX3D_AT(0, 0u)));
 				static_for<1, Q, 2>([&](auto I) {
 					constexpr int i = I;
 					const uint32_t sl = odd ? (uint32_t)i : (uint32_t)i+1u, sn = odd ? (uint32_t)i+1u : (uint32_t)i;
-					if(valid) A[i].store(reinterpret_cast<E*>(FX3D_AT(0, 0, sl)));
+					if(valid) A[i].store(reinterpret_cast<E*>(FX3D_AT(0, sl)));
 					if constexpr(dir_x(i)==0) {
-						if(valid) A[i+1].store(reinterpret_cast<E*>(FX3D_AT(dir_y(i), dir_z(i), sn)));
+						if(valid) A[i+1].store(reinterpret_cast<E*>(FX3D_AT(dir_y(i), sn)+dzn[dir_z(i)+1]));
 					} else if constexpr(dir_x(i)>0) {
 						const uint32_t last = A[i+1].last_bits();
 						const uint32_t up = __shfl_up_sync(FULL, last, 1u);
 						if(valid) {
-							E* q = reinterpret_cast<E*>(FX3D_AT(dir_y(i), dir_z(i), sn));
+							E* q = reinterpret_cast<E*>(FX3D_AT(dir_y(i), sn)+dzn[dir_z(i)+1]);
 							if(!has_right) q[dxr] = P::from_bits(last);
 							A[i+1].push_front(up);
 							if(has_left) A[i+1].store(q); else A[i+1].store_tail(q);
@@ -515,7 +540,7 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<ST>()) k_stream_collid
 						const uint32_t first = A[i+1].first_bits();
 						const uint32_t dn = __shfl_down_sync(FULL, first, 1u);
 						if(valid) {
-							E* q = reinterpret_cast<E*>(FX3D_AT(dir_y(i), dir_z(i), sn));
+							E* q = reinterpret_cast<E*>(FX3D_AT(dir_y(i), sn)+dzn[dir_z(i)+1]);
 							if(!has_left) q[dxl] = P::from_bits(first);
 							A[i+1].push_back(dn);
 							if(has_right) A[i+1].store(q); else A[i+1].store_head(q);
@@ -523,7 +548,7 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<ST>()) k_stream_collid
 					}
 				});
 			}
-			if(z+1u<ze) { if(z+2u<L.Nz && z>=0u && zref[0]+1u==z) advance(z+1u); else locate(z+1u); } // plain plane step unless a periodic wrap is involved
+			static_for<0, 3, 1>([&](auto J) { colp[J] += plane_bytes; }); // next plane (z+1 <= ze-1 < Nz, so no wrap here)
 		}
 		cp_async_wait<0>();
 #undef FX3D_AT

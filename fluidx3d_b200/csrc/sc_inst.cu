@@ -15,7 +15,7 @@ static inline dim3 block_shape(uint32_t nx) { // 128 threads; x extent = smalles
 template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_pipe_parity(const Lattice& L, const Region& R, const dim3& block, void* stream) {
 	const uint32_t tiles_x = (R.g1-R.g0+block.x-1u)/block.x, tiles_y = (R.y1-R.y0+block.y-1u)/block.y, nz = R.z1-R.z0;
 	constexpr uint32_t smem = pipe_smem_bytes<Q, ST>();
-	int sms = 148, per_sm = (int)std::max(1u, std::min((uint32_t)pipe_blocks_per_sm<ST>(), (227u*1024u)/(smem+1024u)));
+	int sms = 148, per_sm = (int)std::max(1u, std::min((uint32_t)pipe_blocks_per_sm<Q, ST>(), (227u*1024u)/(smem+1024u)));
 #if !defined(FX3D_HOST_EMULATION)
 	static bool configured = false; // per instantiation
 	int dev = 0; cudaGetDevice(&dev);
