@@ -439,15 +439,13 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_col
 			const int64_t dzn[3] = { plane_delta(z, dec(z, L.Nz)), 0, plane_delta(z, inc(z, L.Nz)) }; // neighbour planes of this tile
 			cp_async_commit();
 			cp_async_wait<S-1>(); // the copies of plane z have landed
-			uint32_t fl[K];
+			uint32_t flags4; // the flag bytes of my 4 cells, kept packed (one register); lanes outside the region carry TYPE_S
 			{
 				const uint32_t sh = 8u*(uint32_t)(reinterpret_cast<uintptr_t>(flag_col+(int64_t)z*flag_plane)&3u);
 				const uint32_t w0 = *edge_slot(stage, NX), w1 = sh+8u*(uint32_t)K>32u ? *edge_slot(stage, NX+1) : 0u;
-				const uint32_t flags_word = sh==0u ? w0 : (w0>>sh)|(w1<<(32u-sh));
-				static_for<0, K, 1>([&](auto J) { fl[J] = valid ? (flags_word>>(8*J.value))&0xFFu : (uint32_t)TYPE_S; });
+				flags4 = valid ? (sh==0u ? w0 : (w0>>sh)|(w1<<(32u-sh))) : 0x01010101u*(uint32_t)TYPE_S;
 			}
-			bool any_active = false;
-			static_for<0, K, 1>([&](auto J) { any_active = any_active || (fl[J]&TYPE_BO)!=TYPE_S; });
+			const bool any_active = ((flags4&(0x01010101u*(uint32_t)TYPE_BO))^(0x01010101u*(uint32_t)TYPE_S))!=0u;
 
 			// ---- stream in from the ring ----
 			P A[Q];
@@ -468,10 +466,10 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_col
 			// ---- collide the cell pairs in packed arithmetic ----
 			static_for<0, K/2, 1>([&](auto Pp) {
 				constexpr int p = Pp;
-				const uint32_t fb_lo = fl[2*p]&TYPE_BO, fb_hi = fl[2*p+1]&TYPE_BO;
-				const bool act_lo = fb_lo!=TYPE_S, act_hi = fb_hi!=TYPE_S; // lanes outside the region carry TYPE_S
+				const uint32_t fb_lo = (flags4>>(16*p))&TYPE_BO, fb_hi = (flags4>>(16*p+8))&TYPE_BO;
+				const bool act_lo = fb_lo!=TYPE_S, act_hi = fb_hi!=TYPE_S;
 				if(act_lo || act_hi) {
-					const bool e_lo = L.eb!=0u && act_lo && fb_lo==TYPE_E, e_hi = L.eb!=0u && act_hi && fb_hi==TYPE_E;
+					const bool e_lo = L.eb!=0u && fb_lo==TYPE_E, e_hi = L.eb!=0u && fb_hi==TYPE_E;
 					const uint64_t n = lin(L, x0+2u*(uint32_t)p, yc, z), N = cells(L);
 					F2 rho_e = vsplat<F2>(1.0f), ux_e = vsplat<F2>(0.0f), uy_e = ux_e, uz_e = ux_e;
 					if(e_lo || e_hi) {

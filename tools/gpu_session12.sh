@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+exec > >(tee gpurun_out/session12.log) 2>&1
+echo "=== full gpu suite"; timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
+for wl in d3q19_srt_fp16s_512 d3q19_srt_fp16c_512 d3q19_srt_fp32_512 d3q19_srt_fp32_256 d3q27_trt_fp32_windtunnel; do
+  echo "=== bench $wl"; timeout 600 python bench.py --workload $wl --no-cpu-baseline --no-e2e | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['roofline']['frac'], d['ms_per_step'])"
+done
+echo "=== default bench"; timeout 900 python bench.py
+echo "=== ncu default"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_stream_collide_pipe -s 4 -c 1 -o gpurun_out/prof12_fp16s_512_pipe python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu12.log 2>&1
+echo "=== host binary"; (cd fluidx3d_b200/host && ls bin/ && FX3D_BENCHMARK_SIZE=256 timeout 120 bin/FluidX3D 2>&1 | tail -15)
