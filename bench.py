@@ -33,7 +33,8 @@ WORKLOADS = {
     "d3q27_trt_fp32_windtunnel": (27, "trt", "fp32", 3, (256, 512, 256), "D3Q27 TRT FP32 wind tunnel with sphere, TYPE_E faces + VOLUME_FORCE (BASELINE configs[2], half size)"),
 }
 DEFAULT_WORKLOAD = "d3q19_srt_fp16s_512"
-SPLITS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+# weak scaling: every GPU keeps the full per-GPU box; domains are stacked along z first, then y (faces that are contiguous in memory)
+SPLITS = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (1, 2, 4)}
 
 
 def measured_peaks():
@@ -133,7 +134,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--variant", type=int, default=0, help="kernel choice: 0 default, 1 general one-cell-per-thread, 2 or 4 cells per thread")
+    ap.add_argument("--split", default="", help="Dx,Dy,Dz domain grid for multi-GPU runs (default: z first, then y)")
+    ap.add_argument("--variant", type=int, default=0, help="kernel choice: 0 default (pipelined), 1 general one-cell-per-thread, 2 or 4 cells per thread, 8 pipelined")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -164,6 +166,9 @@ def main():
     if n_gpus not in SPLITS:
         raise SystemExit(f"--gpus must be one of {sorted(SPLITS)}")
     Dx, Dy, Dz = SPLITS[n_gpus] if world > 1 else (1, 1, 1)
+    if args.split:
+        Dx, Dy, Dz = (int(v) for v in args.split.split(","))
+        if Dx * Dy * Dz != n_gpus: raise SystemExit("--split must multiply to the number of GPUs")
     if world == 1 and n_gpus > 1:
         raise SystemExit("launch multi-GPU runs with torchrun (one process per GPU)")
     Nx, Ny, Nz = box[0] * Dx, box[1] * Dy, box[2] * Dz
@@ -223,7 +228,7 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": round(per_gpu_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(per_gpu_gbs / peak, 4),
-                "traffic": traffic, "peak_source": peak_src, "kernel": "k_stream_collide_v1" if args.variant == 1 else "k_stream_collide_vec",
+                "traffic": traffic, "peak_source": peak_src, "kernel": {0: "k_stream_collide_pipe", 8: "k_stream_collide_pipe", 1: "k_stream_collide_v1"}.get(args.variant, "k_stream_collide_vec"),
                 "bytes_per_cell_per_step": bytes_per_cell, "cells_per_launch": cells // n_gpus}
     sim.close()
 

@@ -76,6 +76,10 @@ LBM_Domain::LBM_Domain(const Device_Info& device_info, fx3d_stream shared_stream
 	flags = Memory<uchar>(device, N);
 	if(get_D()>1u) rendezvous = Memory<ulong>(device, 64ull, 1u, false);
 	lattice.fi = fi.device_data(); lattice.rho = rho.device_data(); lattice.u = u.device_data(); lattice.flags = flags.device_data();
+	if(Dx>1u) {
+		staging_bytes = ((ulong)fx3d_transfer_bytes(&lattice)+255ull)/256ull*256ull;
+		staging = Memory<char>(device, 2ull*staging_bytes, 1u, false);
+	}
 }
 uint LBM_Domain::get_velocity_set() const { return velocity_set; }
 
@@ -90,8 +94,14 @@ void LBM_Domain::enqueue_update_fields() {
 	}
 #endif
 }
+void LBM_Domain::enqueue_pack_x_faces() {
+	fx3d_check(fx3d_transfer_extract_fi(&lattice, 0u, t, staging.device_data(), staging.device_data()+staging_bytes, device.get_stream()), "halo exchange (pack x faces)");
+}
 void LBM_Domain::enqueue_exchange_fi(const uint axis, const LBM_Domain& plus, const LBM_Domain& minus) {
-	fx3d_check(fx3d_exchange_fi(&lattice, axis, t, plus.lattice.fi, minus.lattice.fi, device.get_stream()), "halo exchange (fi)");
+	if(axis==0u) // my +x halo receives what the +x neighbour packed for its -x side, and vice versa (coalesced peer reads)
+		fx3d_check(fx3d_transfer_insert_fi(&lattice, 0u, t, plus.staging.device_data()+plus.staging_bytes, minus.staging.device_data(), device.get_stream()), "halo exchange (fi, x)");
+	else
+		fx3d_check(fx3d_exchange_fi(&lattice, axis, t, plus.lattice.fi, minus.lattice.fi, device.get_stream()), "halo exchange (fi)");
 }
 void LBM_Domain::enqueue_exchange_rho_u_flags(const uint axis, const LBM_Domain& plus, const LBM_Domain& minus) {
 	fx3d_check(fx3d_exchange_rho_u_flags(&lattice, axis, plus.lattice.rho, plus.lattice.u, plus.lattice.flags, minus.lattice.rho, minus.lattice.u, minus.lattice.flags, device.get_stream()), "halo exchange (rho, u, flags)");
@@ -264,6 +274,7 @@ void LBM::rendezvous() { // every domain tells its face neighbours "I am here" a
 void LBM::communicate_field(const bool ddfs) { // x, then y, then z, so that edges and corners travel with later faces
 	const uint Dn[3] = { Dx, Dy, Dz };
 	for(uint axis=0u; axis<3u; axis++) if(Dn[axis]>1u) {
+		if(ddfs && axis==0u) for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_pack_x_faces();
 		rendezvous(); // what this phase reads (stream_collide output, or the previous axis' halos) is complete everywhere
 		for(uint d=0u; d<get_D(); d++) {
 			LBM_Domain& plus = *lbm_domain[neighbour(d, axis, +1)]; LBM_Domain& minus = *lbm_domain[neighbour(d, axis, -1)];

@@ -32,6 +32,8 @@ public:
 	Memory<float> u;          // velocity of every cell (x, y, z planes)
 	Memory<uchar> flags;      // flags of every cell
 	Memory<ulong> rendezvous; // 64 counters, written by the neighbouring domains (device side only)
+	Memory<char> staging;     // x faces only: linear buffers [+x | -x] the neighbours pull from (x faces are strided in memory)
+	ulong staging_bytes = 0ull;
 
 	LBM_Domain(const Device_Info& device_info, fx3d_stream shared_stream, const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const int Ox, const int Oy, const int Oz, const float nu, const float fx, const float fy, const float fz);
 
@@ -40,6 +42,7 @@ public:
 	void enqueue_run_steps(const ulong steps); // D==1 only: `steps` stream_collide launches without host work in between
 	void enqueue_update_fields();
 	void enqueue_exchange_fi(const uint axis, const LBM_Domain& plus, const LBM_Domain& minus);
+	void enqueue_pack_x_faces(); // stage my outgoing x layers (transfer_extract_fi) before the rendezvous
 	void enqueue_exchange_rho_u_flags(const uint axis, const LBM_Domain& plus, const LBM_Domain& minus);
 	void enqueue_rendezvous_signal(const vector<LBM_Domain*>& peers, const uint my_index, const ulong value);
 	void enqueue_rendezvous_wait(const vector<uint>& peer_indices, const ulong value);

@@ -94,11 +94,16 @@ class LBM_Domain:
         if not host_fields:  # benchmark path: default fields (rho=1, u=0, flags=0) are produced on the device
             lib.fill_f32(device, self.rho.device_ptr, C.c_float(1.0), N, stream)
         self.lat.fi, self.lat.rho, self.lat.u, self.lat.flags = self.fi.device_ptr, self.rho.device_ptr, self.u.device_ptr, self.flags.device_ptr
-        self.sync_array = None
-        if Dx * Dy * Dz > 1:  # allocate_transfer(), src/lbm.cpp:1308-1337: here only the rendezvous counters
+        self.sync_array, self.xfer, self.xfer_bytes = None, None, 0
+        if Dx * Dy * Dz > 1:  # allocate_transfer(), src/lbm.cpp:1308-1337: the rendezvous counters ...
             p = C.c_void_p()
             lib.malloc(device, 64 * 8, C.byref(p))
             self.sync_array = p.value
+        if Dx > 1:  # ... and, for x faces only (one element per row: strided), a pair of linear staging buffers [+x | -x]
+            self.xfer_bytes = (lib.transfer_bytes(C.byref(self.lat)) + 255) // 256 * 256
+            p = C.c_void_p()
+            lib.malloc(device, 2 * self.xfer_bytes, C.byref(p))
+            self.xfer = p.value
 
     def get_N(self): return self.Nx * self.Ny * self.Nz
     def get_D(self): return self.Dx * self.Dy * self.Dz
@@ -135,6 +140,8 @@ class LBM_Domain:
             m.free()
         if self.sync_array:
             self.lib.free(self.device, self.sync_array); self.sync_array = None
+        if self.xfer:
+            self.lib.free(self.device, self.xfer); self.xfer = None
 
 
 class Memory_Container:
@@ -309,8 +316,9 @@ class LBM:
 
     def _connect_peers(self):
         """table d -> {fi, rho, u, flags, sync} device pointers for every domain this process needs to read or signal"""
-        peers = {d: dict(fi=dom.fi.device_ptr, rho=dom.rho.device_ptr, u=dom.u.device_ptr, flags=dom.flags.device_ptr, sync=dom.sync_array, device=dom.device)
+        peers = {d: dict(fi=dom.fi.device_ptr, rho=dom.rho.device_ptr, u=dom.u.device_ptr, flags=dom.flags.device_ptr, sync=dom.sync_array, xfer=dom.xfer, device=dom.device)
                  for d, dom in self.lbm_domain.items()}
+        shared = ("fi", "rho", "u", "flags", "sync") + (("xfer",) if self.Dx > 1 else ())
         if self.comm is None:
             devs = sorted({dom.device for dom in self.lbm_domain.values()})
             for a in devs:
@@ -319,7 +327,7 @@ class LBM:
         else:  # one process per GPU: exchange CUDA IPC handles of the five buffers
             (d, dom), = self.lbm_domain.items()
             mine = {}
-            for k in ("fi", "rho", "u", "flags", "sync"):
+            for k in shared:
                 h = C.create_string_buffer(64)
                 self.lib.ipc_get_handle(dom.device, peers[d][k], h)
                 mine[k] = h.raw
@@ -327,7 +335,7 @@ class LBM:
             needed = {self._neighbour(d, a, s) for a in range(3) for s in (1, -1) if (self.Dx, self.Dy, self.Dz)[a] > 1} - {d}
             for r in needed:
                 entry = {"device": dom.device}
-                for k in ("fi", "rho", "u", "flags", "sync"):
+                for k in shared:
                     p = C.c_void_p()
                     self.lib.ipc_open_handle(dom.device, everyone[r][k], C.byref(p))
                     entry[k] = p.value
@@ -351,10 +359,16 @@ class LBM:
     def _communicate(self, field):
         for axis, Dn in enumerate((self.Dx, self.Dy, self.Dz)):
             if Dn <= 1: continue
+            staged = axis == 0 and field == "fi"
+            if staged:  # x faces: pack my two outgoing layers into my linear buffers first, so that the peer reads below are coalesced
+                for d, dom in self.local_domains():
+                    self.lib.transfer_extract_fi(C.byref(dom.lat), 0, dom.t, dom.xfer, dom.xfer + dom.xfer_bytes, dom.stream)
             self._barrier(axis)  # producers of this phase (stream_collide or the previous axis' pull) are done everywhere
             for d, dom in self.local_domains():
                 p, m = self._peers[self._neighbour(d, axis, +1)], self._peers[self._neighbour(d, axis, -1)]
-                if field == "fi":
+                if staged:  # my +x halo receives what the +x neighbour packed for its -x side, and vice versa
+                    self.lib.transfer_insert_fi(C.byref(dom.lat), 0, dom.t, p["xfer"] + dom.xfer_bytes, m["xfer"], dom.stream)
+                elif field == "fi":
                     self.lib.exchange_fi(C.byref(dom.lat), axis, dom.t, p["fi"], m["fi"], dom.stream)
                 else:
                     self.lib.exchange_rho_u_flags(C.byref(dom.lat), axis, p["rho"], p["u"], p["flags"], m["rho"], m["u"], m["flags"], dom.stream)
