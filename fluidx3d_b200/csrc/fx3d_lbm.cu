@@ -174,14 +174,14 @@ int fx3d_transfer_extract_fi(const fx3d_lattice* lat, uint32_t axis, uint64_t t,
 	Lattice L; dim3 g, b;
 	if(!face_setup(lat, axis, t, L, g, b)) return FX3D_ERR_INVALID;
 	if(int rc = use_device(lat->device)) return rc;
-	FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { FX3D_LAUNCH((k_transfer_fi<Q, ST, true>), g, b, stream, L, axis, bp, bm); })
+	FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { g.y = (uint32_t)transfers<Q>(); FX3D_LAUNCH((k_transfer_fi<Q, ST, true>), g, b, stream, L, axis, bp, bm); })
 	return check_launch("transfer_extract_fi");
 }
 int fx3d_transfer_insert_fi(const fx3d_lattice* lat, uint32_t axis, uint64_t t, const void* bp, const void* bm, fx3d_stream stream) {
 	Lattice L; dim3 g, b;
 	if(!face_setup(lat, axis, t, L, g, b)) return FX3D_ERR_INVALID;
 	if(int rc = use_device(lat->device)) return rc;
-	FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { FX3D_LAUNCH((k_transfer_fi<Q, ST, false>), g, b, stream, L, axis, const_cast<void*>(bp), const_cast<void*>(bm)); })
+	FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { g.y = (uint32_t)transfers<Q>(); FX3D_LAUNCH((k_transfer_fi<Q, ST, false>), g, b, stream, L, axis, const_cast<void*>(bp), const_cast<void*>(bm)); })
 	return check_launch("transfer_insert_fi");
 }
 int fx3d_transfer_extract_rho_u_flags(const fx3d_lattice* lat, uint32_t axis, uint64_t t, void* bp, void* bm, fx3d_stream stream) {
@@ -203,7 +203,7 @@ int fx3d_exchange_fi(const fx3d_lattice* lat, uint32_t axis, uint64_t t, const v
 	if(!face_setup(lat, axis, t, L, g, b)) return FX3D_ERR_INVALID;
 	if(!fi_plus||!fi_minus) { set_error("neighbour DDF buffers are null"); return FX3D_ERR_INVALID; }
 	if(int rc = use_device(lat->device)) return rc;
-	FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { FX3D_LAUNCH((k_exchange_fi<Q, ST>), g, b, stream, L, axis, fi_plus, fi_minus); })
+	FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { g.y = (uint32_t)transfers<Q>(); FX3D_LAUNCH((k_exchange_fi<Q, ST>), g, b, stream, L, axis, fi_plus, fi_minus); })
 	return check_launch("exchange_fi");
 }
 int fx3d_exchange_rho_u_flags(const fx3d_lattice* lat, uint32_t axis, const float* rho_plus, const float* u_plus, const uint8_t* flags_plus,

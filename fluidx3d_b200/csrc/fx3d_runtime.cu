@@ -3,6 +3,7 @@
 // its in-order queue (:284-340), Memory<T> allocation and transfers (:361-388,510-531,608-611), and the finish_queue
 // barriers of the halo exchange (src/lbm.cpp:1357,1366,1375). CUDA only; there is no host fallback.
 #define FX3D_TU_RUNTIME
+#include <atomic>
 #include "fx3d_internal.cuh"
 #include <cstring>
 #include <algorithm>
@@ -76,8 +77,9 @@ int fx3d_device_get_info(int device, fx3d_device_info* info) {
 	std::memset(info, 0, sizeof(*info));
 	std::strncpy(info->name, p.name, sizeof(info->name)-1);
 	info->id = device; info->cc_major = p.major; info->cc_minor = p.minor; info->sm_count = p.multiProcessorCount;
-	int khz = 0;
-	cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+	static std::atomic<int> clock_khz[64]; // cudaDevAttrClockRate is not cached by the runtime (a query costs milliseconds): ask once per device
+	int khz = device>=0&&device<64 ? clock_khz[device].load() : 0;
+	if(khz==0) { cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device); if(device>=0&&device<64) clock_khz[device] = khz; }
 	info->clock_mhz = khz/1000;
 	info->memory_bytes = (uint64_t)p.totalGlobalMem; info->l2_bytes = (uint64_t)p.l2CacheSize;
 	info->tflops_fp32 = (float)p.multiProcessorCount*128.0f*2.0f*(float)info->clock_mhz*1E-6f; // 128 FP32 lanes per SM, FMA = 2 flops
@@ -243,8 +245,9 @@ int fx3d_rendezvous_wait(int device, uint64_t* my_array, const int* peer_indices
 	if(int rc = use_device(device)) return rc;
 	IndexList il;
 	for(int k=0; k<32; k++) il.idx[k] = k<n_peers ? peer_indices[k] : 0;
-	int khz = 0;
-	cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+	static std::atomic<int> clock_khz[64]; // cudaDevAttrClockRate is not cached by the runtime (a query costs milliseconds): ask once per device
+	int khz = device>=0&&device<64 ? clock_khz[device].load() : 0;
+	if(khz==0) { cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device); if(device>=0&&device<64) clock_khz[device] = khz; }
 	const long long cycles = (long long)(timeout_ms>0 ? timeout_ms : 10000)*(long long)(khz>0 ? khz : 1900000);
 	FX3D_LAUNCH(k_rendezvous_wait, dim3(1u), dim3(32u), stream, my_array, il, n_peers, 63, value, cycles);
 	return check_launch("rendezvous_wait");

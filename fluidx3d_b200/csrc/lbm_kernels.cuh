@@ -681,21 +681,24 @@ FX3D_HD uint64_t insert_addr(const Lattice& L, uint32_t odd, int i, uint32_t x, 
 // the building block of host-staged exchange): EXTRACT=true transfer_extract_fi, false transfer__insert_fi
 template<int Q, int ST, bool EXTRACT>
 __global__ void __launch_bounds__(128) k_transfer_fi(const Lattice L, const uint32_t axis, void* buf_p, void* buf_m) {
+	// one thread per (face cell a, transferred direction b = blockIdx.y); the loads of both sides are issued before the stores
 	typedef typename Codec<ST>::elem_t E;
 	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x, A = face_area(L, axis), len = axis_len(L, axis);
 	if(a>=A) return;
+	const int b = (int)blockIdx.y;
 	E* fi = reinterpret_cast<E*>(L.fi);
 	E* bp = reinterpret_cast<E*>(buf_p); E* bm = reinterpret_cast<E*>(buf_m);
-	uint32_t x, y, z;
-	face_coords(L, axis, a, EXTRACT ? len-2u : len-1u, x, y, z);
-	for(int b=0; b<transfers<Q>(); b++) {
-		const int i = xfer_dir<Q>(2*(int)axis, b);
-		if(EXTRACT) bp[(uint64_t)b*A+a] = fi[extract_addr(L, L.odd, i, x, y, z)]; else fi[insert_addr(L, L.odd, i, x, y, z)] = bp[(uint64_t)b*A+a];
-	}
-	face_coords(L, axis, a, EXTRACT ? 1u : 0u, x, y, z);
-	for(int b=0; b<transfers<Q>(); b++) {
-		const int i = xfer_dir<Q>(2*(int)axis+1, b);
-		if(EXTRACT) bm[(uint64_t)b*A+a] = fi[extract_addr(L, L.odd, i, x, y, z)]; else fi[insert_addr(L, L.odd, i, x, y, z)] = bm[(uint64_t)b*A+a];
+	uint32_t xp, yp, zp, xm, ym, zm;
+	face_coords(L, axis, a, EXTRACT ? len-2u : len-1u, xp, yp, zp);
+	face_coords(L, axis, a, EXTRACT ? 1u : 0u, xm, ym, zm);
+	const int ip = xfer_dir<Q>(2*(int)axis, b), im = xfer_dir<Q>(2*(int)axis+1, b);
+	const uint64_t k = (uint64_t)b*A+a;
+	if(EXTRACT) {
+		const E vp = fi[extract_addr(L, L.odd, ip, xp, yp, zp)], vm = fi[extract_addr(L, L.odd, im, xm, ym, zm)];
+		bp[k] = vp; bm[k] = vm;
+	} else {
+		const E vp = bp[k], vm = bm[k];
+		fi[insert_addr(L, L.odd, ip, xp, yp, zp)] = vp; fi[insert_addr(L, L.odd, im, xm, ym, zm)] = vm;
 	}
 }
 // rho/u/flags halo: 4 float planes then one byte plane at byte 16*A, src/kernel.cpp:2133-2158
@@ -726,18 +729,23 @@ __global__ void __launch_bounds__(128) k_transfer_rho_u_flags(const Lattice L, c
 // All domains have identical local geometry, so the neighbour's addresses follow from my Lattice.
 template<int Q, int ST>
 __global__ void __launch_bounds__(128) k_exchange_fi(const Lattice L, const uint32_t axis, const void* fi_plus, const void* fi_minus) {
+	// one thread per (face cell a, transferred direction b = blockIdx.y): two independent peer loads in flight per thread
 	typedef typename Codec<ST>::elem_t E;
 	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x, A = face_area(L, axis), len = axis_len(L, axis);
 	if(a>=A) return;
+	const int b = (int)blockIdx.y;
 	E* fi = reinterpret_cast<E*>(L.fi);
 	const E* fp = reinterpret_cast<const E*>(fi_plus); const E* fm = reinterpret_cast<const E*>(fi_minus);
+	const int ip = xfer_dir<Q>(2*(int)axis, b), im = xfer_dir<Q>(2*(int)axis+1, b);
 	uint32_t xi, yi, zi, xe, ye, ze;
-	face_coords(L, axis, a, len-1u, xi, yi, zi); face_coords(L, axis, a, 1u, xe, ye, ze);
-	for(int b=0; b<transfers<Q>(); b++)
-		fi[insert_addr(L, L.odd, xfer_dir<Q>(2*(int)axis, b), xi, yi, zi)] = fp[extract_addr(L, L.odd, xfer_dir<Q>(2*(int)axis+1, b), xe, ye, ze)];
-	face_coords(L, axis, a, 0u, xi, yi, zi); face_coords(L, axis, a, len-2u, xe, ye, ze);
-	for(int b=0; b<transfers<Q>(); b++)
-		fi[insert_addr(L, L.odd, xfer_dir<Q>(2*(int)axis+1, b), xi, yi, zi)] = fm[extract_addr(L, L.odd, xfer_dir<Q>(2*(int)axis, b), xe, ye, ze)];
+	face_coords(L, axis, a, 1u, xe, ye, ze);
+	const E vp = fp[extract_addr(L, L.odd, im, xe, ye, ze)]; // what the +neighbour sends towards -axis lands in my +halo
+	face_coords(L, axis, a, len-2u, xe, ye, ze);
+	const E vm = fm[extract_addr(L, L.odd, ip, xe, ye, ze)];
+	face_coords(L, axis, a, len-1u, xi, yi, zi);
+	fi[insert_addr(L, L.odd, ip, xi, yi, zi)] = vp;
+	face_coords(L, axis, a, 0u, xi, yi, zi);
+	fi[insert_addr(L, L.odd, im, xi, yi, zi)] = vm;
 }
 struct PeerFields { const float* rho; const float* u; const uint8_t* flags; };
 #if defined(FX3D_TU_LBM) // non-template kernels are defined in exactly one translation unit

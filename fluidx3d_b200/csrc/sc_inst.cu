@@ -1,5 +1,6 @@
 // sc_inst.cu -- stream_collide instantiations for one (velocity set, storage) pair; compiled once per pair with
 // -DFX3D_Q=19|27 -DFX3D_ST=0|1|2 so that the six heavy translation units build in parallel.
+#include <atomic>
 #include "fx3d_internal.cuh"
 #include <algorithm>
 
@@ -17,12 +18,12 @@ template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_pipe_parit
 	constexpr uint32_t smem = pipe_smem_bytes<Q, ST>();
 	int sms = 148, per_sm = (int)std::max(1u, std::min((uint32_t)pipe_blocks_per_sm<Q, ST>(), (227u*1024u)/(smem+1024u)));
 #if !defined(FX3D_HOST_EMULATION)
-	static bool configured = false; // per instantiation
+	static std::atomic<uint64_t> configured{0ull}; // per instantiation: bit d = the opt-in shared memory size is set on device d
 	int dev = 0; cudaGetDevice(&dev);
-	if(!configured) {
+	if(dev>=64 || !((configured.load()>>dev)&1ull)) {
 		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_pipe<Q, COLL, ST, VF, ODD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if(e!=cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stream_collide_pipe)");
-		configured = true;
+		if(dev<64) configured.fetch_or(1ull<<dev);
 	}
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 #else
