@@ -203,7 +203,13 @@ int fx3d_exchange_fi(const fx3d_lattice* lat, uint32_t axis, uint64_t t, const v
 	if(!face_setup(lat, axis, t, L, g, b)) return FX3D_ERR_INVALID;
 	if(!fi_plus||!fi_minus) { set_error("neighbour DDF buffers are null"); return FX3D_ERR_INVALID; }
 	if(int rc = use_device(lat->device)) return rc;
-	FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { g.y = (uint32_t)transfers<Q>(); FX3D_LAUNCH((k_exchange_fi<Q, ST>), g, b, stream, L, axis, fi_plus, fi_minus); })
+	if(axis==0u) { // x faces are one element per row
+		FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { g.y = (uint32_t)transfers<Q>(); FX3D_LAUNCH((k_exchange_fi<Q, ST>), g, b, stream, L, axis, fi_plus, fi_minus); })
+	} else { // y and z faces are whole x-rows: vector copies
+		const uint32_t rows = axis==1u ? L.Nz : L.Ny, nvec = L.px*(uint32_t)elem_bytes(lat->storage)/16u;
+		b = dim3(nvec>=128u ? 128u : nvec>=64u ? 64u : 32u, 1u, 1u);
+		FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { g = dim3(rows, (uint32_t)transfers<Q>(), 2u); FX3D_LAUNCH((k_exchange_fi_rows<Q, ST>), g, b, stream, L, axis, fi_plus, fi_minus); })
+	}
 	return check_launch("exchange_fi");
 }
 int fx3d_exchange_rho_u_flags(const fx3d_lattice* lat, uint32_t axis, const float* rho_plus, const float* u_plus, const uint8_t* flags_plus,

@@ -747,6 +747,27 @@ __global__ void __launch_bounds__(128) k_exchange_fi(const Lattice L, const uint
 	face_coords(L, axis, a, 0u, xi, yi, zi);
 	fi[insert_addr(L, L.odd, im, xi, yi, zi)] = vm;
 }
+// y and z faces: for a fixed face row and direction the transferred elements are one whole x-row of one slot, and the row the
+// neighbour extracts from and the row I insert into carry the same x shift -- so the exchange of a (row, direction, side) is a
+// copy of the full pitch row, done with aligned 16-byte vectors (512 bytes per warp request over NVLink).
+// grid = (face rows, transfers, 2 sides), any 1-D block.
+template<int Q, int ST>
+__global__ void __launch_bounds__(128) k_exchange_fi_rows(const Lattice L, const uint32_t axis, const void* fi_plus, const void* fi_minus) {
+	typedef typename Codec<ST>::elem_t E;
+	const uint32_t r = blockIdx.x, len = axis_len(L, axis);
+	const int b = (int)blockIdx.y;
+	const bool plus = blockIdx.z==0u;
+	const int ip = xfer_dir<Q>(2*(int)axis, b), im = xfer_dir<Q>(2*(int)axis+1, b);
+	// a face cell of this row (x = 0): the rows of its source and destination elements are the rows of everything in the row
+	uint32_t xe = 0u, ye = axis==1u ? (plus ? 1u : len-2u) : r, ze = axis==1u ? r : (plus ? 1u : len-2u);
+	uint32_t xi = 0u, yi = axis==1u ? (plus ? len-1u : 0u) : r, zi = axis==1u ? r : (plus ? len-1u : 0u);
+	const uint64_t src = extract_addr(L, L.odd, plus ? im : ip, xe, ye, ze), dst = insert_addr(L, L.odd, plus ? ip : im, xi, yi, zi);
+	const uint64_t src_row = src-src%L.px, dst_row = dst-dst%L.px; // slot and rows are multiples of the pitch
+	const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const E*>(plus ? fi_plus : fi_minus)+src_row);
+	uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<E*>(L.fi)+dst_row);
+	const uint32_t nvec = L.px*(uint32_t)sizeof(E)/16u;
+	for(uint32_t v=threadIdx.x; v<nvec; v+=blockDim.x) dp[v] = sp[v];
+}
 struct PeerFields { const float* rho; const float* u; const uint8_t* flags; };
 #if defined(FX3D_TU_LBM) // non-template kernels are defined in exactly one translation unit
 __global__ void __launch_bounds__(128) k_exchange_rho_u_flags(const Lattice L, const uint32_t axis, const PeerFields plus, const PeerFields minus) {
