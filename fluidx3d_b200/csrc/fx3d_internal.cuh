@@ -27,8 +27,9 @@ int check_launch(const char* what);           // cudaGetLastError with error tra
 int cuda_fail(cudaError_t e, const char* what);
 #endif
 
-// DDF layout rules (see lbm_kernels.cuh): pitch multiple of 64 elements, x offset 7 when the x axis has a halo so that
-// the first non-halo cell (x=1) lands on element 8 of its row
+// DDF layout rules (see lbm_kernels.cuh): pitch multiple of 64 elements, x offset 63 when the x axis has a halo so that
+// the first non-halo cell (x=1) lands on element 64 of its row: every warp's vector access then starts on a 128-byte line
+// (with offset 7 / 16-byte alignment a 512^3 FP16S domain moved 15 % more sectors and ran 25 % slower)
 inline bool make_lattice(const fx3d_lattice* in, uint64_t t, float fx, float fy, float fz, Lattice& L) {
 	if(!in) { set_error("lattice is null"); return false; }
 	if(in->Nx==0u||in->Ny==0u||in->Nz==0u) { set_error("lattice size is 0"); return false; }
@@ -37,7 +38,7 @@ inline bool make_lattice(const fx3d_lattice* in, uint64_t t, float fx, float fy,
 	L.Nx = in->Nx; L.Ny = in->Ny; L.Nz = in->Nz;
 	L.Hx = in->Dx>1u; L.Hy = in->Dy>1u; L.Hz = in->Dz>1u;
 	if((L.Hx&&in->Nx<3u)||(L.Hy&&in->Ny<3u)||(L.Hz&&in->Nz<3u)) { set_error("a decomposed axis needs at least 3 cells (halo + 1 + halo)"); return false; }
-	L.xo = L.Hx ? 7u : 0u;
+	L.xo = L.Hx ? 63u : 0u;
 	L.px = ((in->Nx+L.xo+63u)/64u)*64u;
 	L.slot = (uint64_t)L.px*in->Ny*in->Nz;
 	if(L.slot>0xFFFFFFFFull) { set_error("a domain may hold at most 2^32-1 (padded) cells"); return false; }
