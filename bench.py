@@ -30,6 +30,7 @@ WORKLOADS = {
     "d3q19_srt_fp32_512": (19, "srt", "fp32", 0, (512, 512, 512), "D3Q19 SRT FP32 512^3 periodic box"),
     "d3q19_srt_fp16c_512": (19, "srt", "fp16c", 0, (512, 512, 512), "D3Q19 SRT FP16C 512^3 periodic box"),
     "d3q19_srt_fp16s_256": (19, "srt", "fp16s", 0, (256, 256, 256), "D3Q19 SRT FP16S 256^3 periodic box"),
+    "d3q19_srt_fp16c_1024": (19, "srt", "fp16c", 0, (1024, 1024, 1024), "D3Q19 SRT FP16C 1024^3 per GPU; with --gpus 8 --split 2,2,2 the 2048^3 domain of BASELINE configs[3] (run with --no-e2e: 18 GB of host fields per GPU)"),
     "d3q27_trt_fp32_windtunnel": (27, "trt", "fp32", 3, (256, 512, 256), "D3Q27 TRT FP32 wind tunnel with sphere, TYPE_E faces + VOLUME_FORCE (BASELINE configs[2], half size)"),
 }
 DEFAULT_WORKLOAD = "d3q19_srt_fp16s_512"

@@ -55,8 +55,9 @@ static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int re
 	const int want = g_variant.load();
 	uint32_t K = 1u;
 	bool pipelined = false;
-	if(want==8 || (want==0 && default_pipelined(region))) { // pipelined kernel: 4 cells per thread
-		if(inner%4u==0u) { K = 4u; pipelined = true; }
+	if(want==8 || (want==0 && default_pipelined(region))) { // pipelined kernel: 4 cells per thread (2 for D3Q27 FP32)
+		const uint32_t pk = pipe_cells_of(lat->velocity_set, lat->storage);
+		if(inner%pk==0u) { K = pk; pipelined = true; }
 	}
 	if(!pipelined && want!=1) {
 		const uint32_t pref = want==2 ? 2u : want==4 ? 4u : default_cells_per_thread((int)lat->storage);

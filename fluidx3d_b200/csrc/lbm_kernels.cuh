@@ -319,16 +319,18 @@ __global__ void __launch_bounds__(128, (K==4 ? FX3D_V4_MINBLOCKS : FX3D_V2_MINBL
 #ifndef FX3D_PIPE_COLLIDE // collision formulation of the pipelined kernel: 0 collide_cell (all Q populations and equilibria live), 1 collide_cell_fused
 #define FX3D_PIPE_COLLIDE -1 // (relax pair by pair), 2 collide_cell_stream (populations unpacked on demand); -1: per storage, as measured on B200
 #endif
-template<int ST> FX3D_HDC constexpr int pipe_collide_mode() { return FX3D_PIPE_COLLIDE>=0 ? FX3D_PIPE_COLLIDE : ST==ST_FP32 ? 1 : 2; }
+template<int Q, int ST> FX3D_HDC constexpr int pipe_collide_mode() { return FX3D_PIPE_COLLIDE>=0 ? FX3D_PIPE_COLLIDE : (ST==ST_FP32 && Q==19) ? 1 : 2; }
 constexpr int PIPE_STAGES = FX3D_PIPE_STAGES; // ring depth: tiles in flight per thread = stages-1
 template<int Q> FX3D_HDC constexpr bool row_used(int ey, int ez) { if(ey==0&&ez==0) return true; for(int i=1; i<Q; i+=2) if(dir_y(i)==ey&&dir_z(i)==ez) return true; return false; } // neighbour rows the odd directions reach
 template<int Q> FX3D_HDC constexpr int x_dirs() { int n = 0; for(int i=1; i<Q; i+=2) if(dir_x(i)!=0) n++; return n; }
 template<int Q> FX3D_HDC constexpr int x_dir_rank(int i) { int n = 0; for(int k=1; k<i; k+=2) if(dir_x(k)!=0) n++; return n; } // position of odd direction i among the x-shifted ones
-// every thread moves 4 cells per tile: 8-byte vectors for 16-bit storage, 16-byte vectors for FP32 (which then affords only a 2-deep ring)
-template<int ST> FX3D_HDC constexpr int pipe_vector_bytes() { return ST==ST_FP32 ? 16 : 8; }
+// every thread moves 4 cells per tile: 8-byte vectors for 16-bit storage, 16-byte vectors for FP32 (which then affords only a
+// 2-deep ring with 2 blocks per SM). D3Q27 FP32 would leave room for a single block that way, so it moves 2 cells per thread.
+template<int Q, int ST> FX3D_HDC constexpr int pipe_cells() { return (ST==ST_FP32 && Q>19) ? 2 : 4; }
+template<int Q, int ST> FX3D_HDC constexpr int pipe_vector_bytes() { return pipe_cells<Q, ST>()*(ST==ST_FP32 ? 4 : 2); }
 template<int ST> FX3D_HDC constexpr int pipe_stages() { return ST==ST_FP32 ? 2 : PIPE_STAGES; }
-template<int Q, int ST> FX3D_HDC constexpr int pipe_blocks_per_sm() { return ST==ST_FP32 ? 2 : (Q>19 && FX3D_PIPE_MINBLOCKS>3) ? 3 : FX3D_PIPE_MINBLOCKS; } // also the register cap the kernel is compiled for
-template<int Q, int ST> FX3D_HDC constexpr uint32_t pipe_smem_bytes() { return (uint32_t)pipe_stages<ST>()*((uint32_t)Q*128u*(uint32_t)pipe_vector_bytes<ST>()+((uint32_t)x_dirs<Q>()+2u)*128u*4u); } // vectors, edge words, two flag words
+template<int Q, int ST> FX3D_HDC constexpr int pipe_blocks_per_sm() { return ST==ST_FP32 ? (Q>19 ? 3 : 2) : (Q>19 && FX3D_PIPE_MINBLOCKS>3) ? 3 : FX3D_PIPE_MINBLOCKS; } // also the register cap the kernel is compiled for
+template<int Q, int ST> FX3D_HDC constexpr uint32_t pipe_smem_bytes() { return (uint32_t)pipe_stages<ST>()*((uint32_t)Q*128u*(uint32_t)pipe_vector_bytes<Q, ST>()+((uint32_t)x_dirs<Q>()+2u)*128u*4u); } // vectors, edge words, two flag words
 
 FX3D_HD void cp_async8(void* smem_dst, const void* gmem_src) {
 #if defined(FX3D_HOST_EMULATION)
@@ -372,11 +374,11 @@ FX3D_HD unsigned char* dynamic_smem() {
 }
 
 template<int Q, int COLL, int ST, bool VF, int ODD>
-__global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_collide_pipe(const Lattice L, const Region R, const uint32_t tiles_x, const uint32_t tiles_y, const uint32_t zchunk, const uint32_t nunits) {
-	// Work unit = one column of tiles (fixed x-group block and y rows) over a chunk of z planes; a block walks its units and, inside
+__global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_collide_pipe(const Lattice L, const Region R, const uint32_t tiles_x, const uint32_t tiles_y) {
+	// Work unit = a run of z planes of one column of tiles (fixed x-group block and y rows); a block walks its units and, inside
 	// a unit, marches in z: the row pointers advance by one plane per tile instead of being rebuilt, and the tile S-1 planes ahead
 	// is addressed relative to them (uniform per-plane deltas, which also carry the periodic wrap).
-	constexpr int K = 4, VB = pipe_vector_bytes<ST>();
+	constexpr int K = pipe_cells<Q, ST>(), VB = pipe_vector_bytes<Q, ST>();
 	constexpr int S = pipe_stages<ST>(), NX = x_dirs<Q>();
 	constexpr unsigned FULL = 0xFFFFFFFFu;
 	constexpr uint32_t odd = (uint32_t)ODD;
@@ -393,10 +395,17 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_col
 	auto edge_word = [&](const char* q, int d) -> const void* { return reinterpret_cast<const void*>(reinterpret_cast<uintptr_t>(q+(int64_t)d*(int64_t)sizeof(E))&~(uintptr_t)3u); };
 	auto edge_pick = [&](uint32_t w, const char* q, int d) -> uint32_t { if constexpr(sizeof(E)==4) return w; else return (reinterpret_cast<uintptr_t>(q+(int64_t)d*(int64_t)sizeof(E))&2u) ? w>>16 : w&0xFFFFu; };
 
-	for(uint32_t unit=blockIdx.x; unit<nunits; unit+=gridDim.x) {
-		// ---- column geometry (fixed for the whole unit) ----
-		const uint32_t col = unit%ncols, chunk = unit/ncols, xb = col%tiles_x, yb = col/tiles_x;
-		const uint32_t zs = R.z0+chunk*zchunk, ze = zs+zchunk<R.z1 ? zs+zchunk : R.z1;
+	// The (column, plane) tiles, linearised column-major, are cut into gridDim.x equal contiguous shares: every block walks at most
+	// one partial column, then whole columns, then one partial column -- perfectly balanced, and only a handful of pipeline fills.
+	const uint32_t nz = R.z1-R.z0;
+	const uint64_t ntiles = (uint64_t)ncols*nz;
+	uint64_t tile = ntiles*blockIdx.x/gridDim.x;
+	const uint64_t tile_end = ntiles*(blockIdx.x+1u)/gridDim.x;
+	while(tile<tile_end) {
+		// ---- column geometry (fixed for the whole unit = the part of one column that belongs to this block) ----
+		const uint32_t col = (uint32_t)(tile/nz), zoff = (uint32_t)(tile%nz), xb = col%tiles_x, yb = col/tiles_x;
+		const uint32_t zs = R.z0+zoff, ze = (uint64_t)(nz-zoff)<=tile_end-tile ? R.z1 : zs+(uint32_t)(tile_end-tile);
+		tile += ze-zs;
 		const uint32_t g = R.g0+xb*blockDim.x+threadIdx.x, y = R.y0+yb*blockDim.y+threadIdx.y;
 		const bool valid = g<R.g1 && y<R.y1;
 		const bool has_right = valid && lane<31u && threadIdx.x+1u<blockDim.x && g+1u<R.g1;
@@ -444,6 +453,7 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_col
 				const uint32_t sh = 8u*(uint32_t)(reinterpret_cast<uintptr_t>(flag_col+(int64_t)z*flag_plane)&3u);
 				const uint32_t w0 = *edge_slot(stage, NX), w1 = sh+8u*(uint32_t)K>32u ? *edge_slot(stage, NX+1) : 0u;
 				flags4 = valid ? (sh==0u ? w0 : (w0>>sh)|(w1<<(32u-sh))) : 0x01010101u*(uint32_t)TYPE_S;
+				if constexpr(K==2) flags4 = (flags4&0x0000FFFFu)|(0x01010000u*(uint32_t)TYPE_S); // bytes 2,3 belong to the neighbouring thread
 			}
 			const bool any_active = ((flags4&(0x01010101u*(uint32_t)TYPE_BO))^(0x01010101u*(uint32_t)TYPE_S))!=0u;
 
@@ -478,7 +488,7 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_col
 					}
 					F2 rhon, uxn, uyn, uzn;
 					const bool both = act_lo && act_hi;
-					if constexpr(pipe_collide_mode<ST>()==2) {
+					if constexpr(pipe_collide_mode<Q, ST>()==2) {
 					// populations are unpacked on demand and the results packed straight into the slot they stream out through:
 					// store_f() sends fhn[i] to the neighbour-side slot (A[i+1]) and fhn[i+1] to the local slot (A[i])
 					auto get = [&](auto I) { return A[I.value].template get_pair<p>(); };
@@ -499,7 +509,7 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_col
 					} else {
 					F2 f[Q];
 					static_for<0, Q, 1>([&](auto I) { f[I] = A[I].template get_pair<p>(); });
-					if constexpr(pipe_collide_mode<ST>()==1) collide_cell_fused<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+					if constexpr(pipe_collide_mode<Q, ST>()==1) collide_cell_fused<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
 					else collide_cell<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
 					if(both) {
 						A[0].template set_pair<p>(f[0]);

@@ -29,14 +29,11 @@ template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_pipe_parit
 #else
 	sms = 2; per_sm = 1;
 #endif
-	// units = columns of tiles x chunks of z planes: enough units per resident block for balance, chunks long enough to amortise the pipeline fill
-	const uint64_t blocks = (uint64_t)sms*(uint64_t)per_sm, ncols = (uint64_t)tiles_x*tiles_y;
-	uint32_t zchunk = nz;
-	while(zchunk>16u && ncols*((nz+zchunk-1u)/zchunk)<8ull*blocks) zchunk = (zchunk+1u)/2u;
-	const uint64_t nunits = ncols*((nz+zchunk-1u)/zchunk);
-	if(nunits>0xFFFFFFFFull-65536ull) { set_error("region has too many tiles"); return FX3D_ERR_INVALID; }
-	const dim3 grid((uint32_t)std::min<uint64_t>(nunits, blocks), 1u, 1u);
-	FX3D_LAUNCH_SMEM((k_stream_collide_pipe<Q, COLL, ST, VF, ODD>), grid, block, smem, stream, L, R, tiles_x, tiles_y, zchunk, (uint32_t)nunits);
+	const uint64_t blocks = (uint64_t)sms*(uint64_t)per_sm, ntiles = (uint64_t)tiles_x*tiles_y*nz;
+	if((uint64_t)tiles_x*tiles_y>0xFFFFFFFFull) { set_error("region has too many tile columns"); return FX3D_ERR_INVALID; }
+	if(ntiles==0ull) return FX3D_OK;
+	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, blocks), 1u, 1u); // every block takes an equal contiguous share of the tiles
+	FX3D_LAUNCH_SMEM((k_stream_collide_pipe<Q, COLL, ST, VF, ODD>), grid, block, smem, stream, L, R, tiles_x, tiles_y);
 	return check_launch("stream_collide (pipelined)");
 }
 
