@@ -33,6 +33,7 @@ WORKLOADS = {
     "d3q19_srt_fp16c_1024": (19, "srt", "fp16c", 0, (1024, 1024, 1024), "D3Q19 SRT FP16C 1024^3 per GPU; with --gpus 8 --split 2,2,2 the 2048^3 domain of BASELINE configs[3] (run with --no-e2e: 18 GB of host fields per GPU)"),
     "d3q27_trt_fp32_windtunnel": (27, "trt", "fp32", 3, (256, 512, 256), "D3Q27 TRT FP32 wind tunnel with sphere, TYPE_E faces + VOLUME_FORCE (BASELINE configs[2], half size)"),
 }
+DEFAULT_OVERLAP = False  # multi-GPU step: overlap the halo exchange with the interior cells
 DEFAULT_WORKLOAD = "d3q19_srt_fp16s_512"
 # weak scaling: every GPU keeps the full per-GPU box; domains are stacked along z first, then y (faces that are contiguous in memory)
 SPLITS = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (1, 2, 4)}
@@ -135,6 +136,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--overlap", type=int, default=-1, help="multi-GPU: 1 = shell/exchange on one stream, interior on another; 0 = one stream; -1 = library default")
+    ap.add_argument("--reserve", type=int, default=-1, help="resident-block slots the interior kernel leaves free for the exchange (with --overlap 1)")
     ap.add_argument("--split", default="", help="Dx,Dy,Dz domain grid for multi-GPU runs (default: z first, then y)")
     ap.add_argument("--variant", type=int, default=0, help="kernel choice: 0 default (pipelined), 1 general one-cell-per-thread, 2 or 4 cells per thread, 8 pipelined")
     args = ap.parse_args()
@@ -180,10 +183,12 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    overlap = DEFAULT_OVERLAP if args.overlap < 0 else bool(args.overlap)
+    if args.reserve >= 0: lib.set_interior_reserve(args.reserve)
     # ---------------- device-resident arm: `value` ----------------
     force = (0.0, 1e-6, 0.0) if feat & 1 else (0.0, 0.0, 0.0)
     sim = fx.LBM(Nx, Ny, Nz, 1.0, *force, Dx=Dx, Dy=Dy, Dz=Dz, velocity_set=Q, collision=collision, storage=storage, features=feat,
-                 comm=comm, devices=None if comm else [device], host_fields=bool(feat & 2), benchmark=True)
+                 comm=comm, devices=None if comm else [device], host_fields=bool(feat & 2), benchmark=True, overlap=overlap)
     if feat & 2:  # wind tunnel: sphere + TYPE_E faces
         zz, yy, xx = np.meshgrid(np.arange(Nz), np.arange(Ny), np.arange(Nx), indexing="ij", sparse=True)
         flags = np.zeros((Nz, Ny, Nx), np.uint8)
@@ -237,7 +242,7 @@ def main():
     e2e = None
     if not args.no_e2e:
         sim = fx.LBM(Nx, Ny, Nz, 1.0, *force, Dx=Dx, Dy=Dy, Dz=Dz, velocity_set=Q, collision=collision, storage=storage, features=feat,
-                     comm=comm, devices=None if comm else [device], host_fields=True, benchmark=True)
+                     comm=comm, devices=None if comm else [device], host_fields=True, benchmark=True, overlap=overlap)
         if feat & 2:
             sim.flags.set_global(flags); sim.u.set_global(np.where(flags == fx.TYPE_S, 0.0, 0.075).astype(np.float32), 1)
         (d0, dom), = sim.local_domains()
@@ -268,7 +273,7 @@ def main():
                 "ms_per_step": round(ms_total / K, 5), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": round(mlups / published[args.workload], 4) if (args.workload in published and n_gpus == 1) else None,
                 "dtype": "f32 arithmetic, " + st + " DDF storage", "data": "synthetic",
-                "config": {"workload": args.workload, "description": desc, "global_grid": [Nx, Ny, Nz], "domains": [Dx, Dy, Dz],
+                "config": {"workload": args.workload, "description": desc, "global_grid": [Nx, Ny, Nz], "domains": [Dx, Dy, Dz], "overlap": bool(overlap and n_gpus > 1),
                            "cache": "DDF working set per GPU (%.1f GB) is far larger than the 126 MB L2; no flush needed" % (cells / n_gpus * Q * (4 if st == "fp32" else 2) * 1e-9)},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)

@@ -65,6 +65,7 @@ _SIGS = {
     "fx3d_relaxation_rate": (_F, [_F], False),
     "fx3d_bytes_per_cell_per_step": (_U32, [_LP], False),
     "fx3d_initialize": (_I, [_LP, _VP], True),
+    "fx3d_set_interior_reserve": (_I, [_I], True),
     "fx3d_stream_collide": (_I, [_LP, _U64, _F, _F, _F, _I, _VP], True),
     "fx3d_update_fields": (_I, [_LP, _U64, _F, _F, _F, _VP], True),
     "fx3d_run_steps": (_I, [_LP, _U64, _U64, _F, _F, _F, _VP], True),

@@ -54,6 +54,6 @@ inline size_t elem_bytes(uint32_t storage) { return storage==FX3D_FP32 ? 4u : 2u
 
 // stream_collide instantiations live in one translation unit per (velocity set, storage), see sc_inst.cu
 inline uint32_t pipe_cells_of(uint32_t velocity_set, uint32_t storage) { return (storage==FX3D_FP32 && velocity_set>19u) ? 2u : 4u; } // = pipe_cells<Q,ST>()
-template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, int cells_per_thread, int collision, bool volume_force, void* stream); // cells_per_thread 0: pipelined kernel
+template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, int cells_per_thread, int collision, bool volume_force, void* stream, int reserve=0); // cells_per_thread 0: pipelined kernel, leaving `reserve` resident-block slots free
 
 } // namespace fx3d

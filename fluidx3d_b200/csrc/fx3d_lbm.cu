@@ -13,6 +13,7 @@ static thread_local std::string t_error;
 void set_error(const std::string& msg) { t_error = msg; }
 std::atomic<uint64_t> g_launches{0ull};
 std::atomic<int> g_variant{0};
+std::atomic<int> g_interior_reserve{8};
 
 // interior (non-halo) extent and the shell / interior split used to overlap the halo exchange with computation.
 // The shell is every non-halo cell within one cell (one 4-cell group along x for the vector kernel) of a halo layer.
@@ -68,7 +69,7 @@ static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int re
 	const bool vf = (lat->features&FX3D_VOLUME_FORCE)!=0u;
 	for(const Region& R : regs) {
 		int rc;
-		FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, pipelined ? 0 : (int)K, (int)lat->collision, vf, stream); })
+		FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, pipelined ? 0 : (int)K, (int)lat->collision, vf, stream, region==FX3D_REGION_INTERIOR ? g_interior_reserve.load() : 0); })
 		if(rc!=FX3D_OK) return rc;
 	}
 	return FX3D_OK;
@@ -81,6 +82,7 @@ extern "C" {
 
 const char* fx3d_last_error(void) { return t_error.c_str(); }
 int fx3d_set_kernel_variant(int variant) { if(variant!=0&&variant!=1&&variant!=2&&variant!=4&&variant!=8) { set_error("variant must be 0 (auto), 1 (general), 2 or 4 (cells per thread), 8 (pipelined)"); return FX3D_ERR_INVALID; } g_variant = variant; return FX3D_OK; }
+int fx3d_set_interior_reserve(int blocks) { if(blocks<0||blocks>1024) { set_error("reserve must be 0..1024 blocks"); return FX3D_ERR_INVALID; } g_interior_reserve = blocks; return FX3D_OK; }
 int fx3d_launch_count(uint64_t* launches) { if(!launches) return FX3D_ERR_INVALID; *launches = g_launches.load(); return FX3D_OK; }
 
 size_t fx3d_fi_bytes(const fx3d_lattice* lat) {

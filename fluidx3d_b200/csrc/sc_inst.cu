@@ -13,7 +13,7 @@ static inline dim3 block_shape(uint32_t nx) { // 128 threads; x extent = smalles
 }
 
 // persistent pipelined kernel: grid = resident blocks only (SM count x blocks per SM by shared memory), each block walks its tiles
-template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_pipe_parity(const Lattice& L, const Region& R, const dim3& block, void* stream) {
+template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_pipe_parity(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
 	const uint32_t tiles_x = (R.g1-R.g0+block.x-1u)/block.x, tiles_y = (R.y1-R.y0+block.y-1u)/block.y, nz = R.z1-R.z0;
 	constexpr uint32_t smem = pipe_smem_bytes<Q, ST>();
 	int sms = 148, per_sm = (int)std::max(1u, std::min((uint32_t)pipe_blocks_per_sm<Q, ST>(), (227u*1024u)/(smem+1024u)));
@@ -29,7 +29,7 @@ template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_pipe_parit
 #else
 	sms = 2; per_sm = 1;
 #endif
-	const uint64_t blocks = (uint64_t)sms*(uint64_t)per_sm, ntiles = (uint64_t)tiles_x*tiles_y*nz;
+	const uint64_t all_blocks = (uint64_t)sms*(uint64_t)per_sm, blocks = all_blocks>2ull*(uint64_t)std::max(reserve, 0) ? all_blocks-(uint64_t)std::max(reserve, 0) : all_blocks, ntiles = (uint64_t)tiles_x*tiles_y*nz;
 	if((uint64_t)tiles_x*tiles_y>0xFFFFFFFFull) { set_error("region has too many tile columns"); return FX3D_ERR_INVALID; }
 	if(ntiles==0ull) return FX3D_OK;
 	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, blocks), 1u, 1u); // every block takes an equal contiguous share of the tiles
@@ -37,16 +37,16 @@ template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_pipe_parit
 	return check_launch("stream_collide (pipelined)");
 }
 
-template<int Q, int COLL, int ST, bool VF> static int launch_pipe(const Lattice& L, const Region& R, const dim3& block, void* stream) {
-	return L.odd ? launch_pipe_parity<Q, COLL, ST, VF, 1>(L, R, block, stream) : launch_pipe_parity<Q, COLL, ST, VF, 0>(L, R, block, stream);
+template<int Q, int COLL, int ST, bool VF> static int launch_pipe(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
+	return L.odd ? launch_pipe_parity<Q, COLL, ST, VF, 1>(L, R, block, stream, reserve) : launch_pipe_parity<Q, COLL, ST, VF, 0>(L, R, block, stream, reserve);
 }
 
-template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, int cells_per_thread, int collision, bool volume_force, void* stream) {
+template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, int cells_per_thread, int collision, bool volume_force, void* stream, int reserve) {
 	if(R.g1<=R.g0||R.y1<=R.y0||R.z1<=R.z0) return FX3D_OK;
 	if(cells_per_thread==0) { // pipelined kernel; R.g0/g1 are in groups of 4 cells
 		const dim3 block = block_shape(R.g1-R.g0);
-		if(collision==COLL_SRT) return volume_force ? launch_pipe<Q, COLL_SRT, ST, true>(L, R, block, stream) : launch_pipe<Q, COLL_SRT, ST, false>(L, R, block, stream);
-		return volume_force ? launch_pipe<Q, COLL_TRT, ST, true>(L, R, block, stream) : launch_pipe<Q, COLL_TRT, ST, false>(L, R, block, stream);
+		if(collision==COLL_SRT) return volume_force ? launch_pipe<Q, COLL_SRT, ST, true>(L, R, block, stream, reserve) : launch_pipe<Q, COLL_SRT, ST, false>(L, R, block, stream, reserve);
+		return volume_force ? launch_pipe<Q, COLL_TRT, ST, true>(L, R, block, stream, reserve) : launch_pipe<Q, COLL_TRT, ST, false>(L, R, block, stream, reserve);
 	}
 	const dim3 block = block_shape(R.g1-R.g0);
 	const dim3 grid((R.g1-R.g0+block.x-1u)/block.x, (R.y1-R.y0+block.y-1u)/block.y, R.z1-R.z0);
@@ -63,6 +63,6 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 #undef FX3D_SC
 	return check_launch("stream_collide");
 }
-template int launch_stream_collide<FX3D_Q, FX3D_ST>(const Lattice&, const Region&, int, int, bool, void*);
+template int launch_stream_collide<FX3D_Q, FX3D_ST>(const Lattice&, const Region&, int, int, bool, void*, int);
 
 } // namespace fx3d

@@ -255,7 +255,7 @@ class LBM:
                 devices = {d: 0 for d in range(D)}
         elif not isinstance(devices, dict):
             devices = {d: devices[i] for i, d in enumerate(owned)}
-        self._streams = {}
+        self._streams, self._streams2, self._events = {}, {}, {}
         self.lbm_domain = {}
         lx, ly, lz = NDx // Dx + 2 * self.Hx, NDy // Dy + 2 * self.Hy, NDz // Dz + 2 * self.Hz
         for d in owned:
@@ -266,6 +266,12 @@ class LBM:
             self.lbm_domain[d] = LBM_Domain(self.lib, dev, self._streams[dev], lx, ly, lz, Dx, Dy, Dz,
                                             x * NDx // Dx - self.Hx, y * NDy // Dy - self.Hy, z * NDz // Dz - self.Hz,
                                             nu, fx, fy, fz, velocity_set, collision, storage, features, host_fields)
+        if overlap and D > 1:  # second in-order stream per device for the interior cells, and the two events that order it with the first
+            for dev in self._streams:
+                s2 = C.c_void_p(); self.lib.stream_create(dev, C.byref(s2)); self._streams2[dev] = s2.value
+                e1, e2 = C.c_void_p(), C.c_void_p()
+                self.lib.event_create(dev, C.byref(e1)); self.lib.event_create(dev, C.byref(e2))
+                self._events[dev] = (e1.value, e2.value)
         self.host_fields = host_fields
         self.rho = Memory_Container(self, "rho", 1)
         self.u = Memory_Container(self, "u", 3)
@@ -396,14 +402,26 @@ class LBM:
 
     def do_time_step(self):
         if self.overlap and self.get_D() > 1:
-            # shell first (the cells whose output the neighbours pull), then the interior; the two regions never touch the same
-            # (cell, slot), and the exchange only reads what the shell wrote
+            # Shell first (the cells whose output the neighbours pull) on the main stream, followed there by the halo exchange;
+            # the interior runs meanwhile on the second stream. The two regions never touch the same (cell, slot), the exchange
+            # only reads what the shell wrote and only writes halo cells. Ordering between steps:
+            # shell(n) after interior(n-1), interior(n) after shell(n) (hence after exchange(n-1), in stream order).
+            devs = sorted(self._streams)
+            for dev in devs: self.lib.stream_wait_event(dev, self._streams[dev], self._events[dev][1])
             for _, dom in self.local_domains(): dom.enqueue_stream_collide(REGION_SHELL)
-            for _, dom in self.local_domains(): dom.enqueue_stream_collide(REGION_INTERIOR)
+            for dev in devs:
+                self.lib.event_record(dev, self._events[dev][0], self._streams[dev])
+                self.lib.stream_wait_event(dev, self._streams2[dev], self._events[dev][0])
+            for _, dom in self.local_domains(): dom.enqueue_stream_collide(REGION_INTERIOR, stream=self._streams2[dom.device])
+            for dev in devs: self.lib.event_record(dev, self._events[dev][1], self._streams2[dev])
         else:
             for _, dom in self.local_domains(): dom.enqueue_stream_collide()
         if self.get_D() > 1: self.communicate_fi()
         for _, dom in self.local_domains(): dom.increment_time_step()
+
+    def _join_streams(self):
+        """everything enqueued after this on the main stream also follows the interior stream's work"""
+        for dev in self._streams2: self.lib.stream_wait_event(dev, self._streams[dev], self._events[dev][1])
 
     def run(self, steps=max_ulong, total_steps=max_ulong, sync=True):
         """run(steps): first call initialises; run(0) initialises only (src/lbm.cpp:955-975). Unlike the reference there is no
@@ -417,14 +435,17 @@ class LBM:
             i = 0
             while i < steps:
                 self.do_time_step(); i += 1
+            if self._streams2 and steps > 0: self._join_streams()
         if sync: self.finish()
 
     def finish(self):
+        if self._streams2: self._join_streams()
         for _, dom in self.local_domains(): dom.finish_queue()
         if self.get_D() > 1:
             for _, dom in self.local_domains(): self.lib.rendezvous_check(dom.device, dom.sync_array, 64)
 
     def update_fields(self):
+        if self._streams2: self._join_streams()
         for _, dom in self.local_domains(): dom.enqueue_update_fields()
         for _, dom in self.local_domains(): dom.finish_queue()
 
@@ -469,13 +490,15 @@ class LBM:
         if self.comm is not None and getattr(self, "_ipc_opened", None):
             (_, dom), = self.lbm_domain.items()
             for entry in self._ipc_opened.values():
-                for k in ("fi", "rho", "u", "flags", "sync"):
-                    self.lib.ipc_close_handle(dom.device, entry[k])
+                for k in ("fi", "rho", "u", "flags", "sync", "xfer"):
+                    if entry.get(k): self.lib.ipc_close_handle(dom.device, entry[k])
             self._ipc_opened = None
             self.comm.barrier()
         for _, dom in self.local_domains(): dom.free()
         for dev, s in self._streams.items(): self.lib.stream_destroy(dev, s)
-        self.lbm_domain, self._streams = {}, {}
+        for dev, s in self._streams2.items(): self.lib.stream_destroy(dev, s)
+        for dev, (e1, e2) in self._events.items(): self.lib.event_destroy(dev, e1); self.lib.event_destroy(dev, e2)
+        self.lbm_domain, self._streams, self._streams2, self._events = {}, {}, {}, {}
 
 
 class TorchComm:

@@ -108,6 +108,9 @@ int fx3d_run_steps(const fx3d_lattice* lattice, uint64_t t0, uint64_t steps, flo
 /* kernel choice for tests and profiling: 0 library default, 1 general one-cell-per-thread kernel, 2 or 4 vector kernel with
  * that many cells per thread (falls back when the row length does not divide) */
 int fx3d_set_kernel_variant(int variant);
+/* FX3D_REGION_INTERIOR launches of the persistent kernel leave this many resident-block slots free, so that the halo exchange
+ * kernels enqueued on another stream find room beside it (default 8; 0 = occupy every slot) */
+int fx3d_set_interior_reserve(int blocks);
 int fx3d_launch_count(uint64_t* launches);                            /* kernels launched by this library so far */
 
 /* halo transfer through linear buffers, layout and semantics of transfer_extract_fi / transfer__insert_fi and

@@ -16,11 +16,12 @@ lbm_mod.VERBOSE = False
 SPLITS = {2: [(2, 1, 1), (1, 1, 2)], 4: [(2, 2, 1), (1, 4, 1)], 8: [(2, 2, 2), (4, 1, 2)]}
 ok_all = True
 for D in SPLITS[world]:
+  for overlap in (False, True):
     for (Q, coll, st, feat) in [(19, 0, 0, 0), (19, 0, 2, 0), (27, 1, 1, 3)]:
         dims, steps = (64, 32, 32), 9
         f = (1e-4, 0.0, -1e-4) if feat & 1 else (0.0, 0.0, 0.0)
         comm = fx.TorchComm()
-        sim = fx.LBM(*dims, 0.05, *f, Dx=D[0], Dy=D[1], Dz=D[2], velocity_set=Q, collision=coll, storage=st, features=feat, comm=comm)
+        sim = fx.LBM(*dims, 0.05, *f, Dx=D[0], Dy=D[1], Dz=D[2], velocity_set=Q, collision=coll, storage=st, features=feat, comm=comm, overlap=overlap)
         rho, u, flags = H.scenario(*dims, seed=12, eq_frac=0.03 if feat & 2 else 0.0)
         sim.rho.set_global(rho); [sim.u.set_global(u[a], a) for a in range(3)]; sim.flags.set_global(flags)
         sim.run(steps)
@@ -36,7 +37,7 @@ for D in SPLITS[world]:
             H.load_scenario(ref, rho, u, flags); ref.run(steps)
             ok = all(np.array_equal(t, w.view(np.uint32).ravel()) for t, w in zip(tot, ref.fields()[:4]))
             ok_all &= ok
-            print(f"dist_check world={world} D={D} Q={Q} coll={coll} storage={st} feat={feat}: {'OK' if ok else 'MISMATCH'}", flush=True)
+            print(f"dist_check world={world} D={D} overlap={int(overlap)} Q={Q} coll={coll} storage={st} feat={feat}: {'OK' if ok else 'MISMATCH'}", flush=True)
         sim.close()
         dist.barrier()
 if rank == 0:
