@@ -32,11 +32,31 @@ WORKLOADS = {
     "d3q19_srt_fp16s_256": (19, "srt", "fp16s", 0, (256, 256, 256), "D3Q19 SRT FP16S 256^3 periodic box"),
     "d3q19_srt_fp16c_1024": (19, "srt", "fp16c", 0, (1024, 1024, 1024), "D3Q19 SRT FP16C 1024^3 per GPU; with --gpus 8 --split 2,2,2 the 2048^3 domain of BASELINE configs[3] (run with --no-e2e: 18 GB of host fields per GPU)"),
     "d3q27_trt_fp32_windtunnel": (27, "trt", "fp32", 3, (256, 512, 256), "D3Q27 TRT FP32 wind tunnel with sphere, TYPE_E faces + VOLUME_FORCE (BASELINE configs[2], half size)"),
+    "d3q27_trt_fp32_windtunnel_full": (27, "trt", "fp32", 3, (512, 1024, 512), "D3Q27 TRT FP32 wind tunnel with sphere, TYPE_E faces + VOLUME_FORCE, 512x1024x512 (BASELINE configs[2], SURVEY 8d C3)"),
+    "d3q19_srt_fp32_256_cavity": (19, "srt", "fp32", 2, (256, 256, 256), "D3Q19 SRT FP32 256^3 lid-driven cavity inside the hot-path feature set: TYPE_S walls, TYPE_E lid u=(0,0.1,0), Re=1000 (SURVEY 8d C1w)"),
 }
 DEFAULT_OVERLAP = False  # multi-GPU step: overlap the halo exchange with the interior cells
 DEFAULT_WORKLOAD = "d3q19_srt_fp16s_512"
 # weak scaling: every GPU keeps the full per-GPU box; domains are stacked along z first, then y (faces that are contiguous in memory)
 SPLITS = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (1, 2, 4)}
+
+
+def make_scene(workload, fx, Nx, Ny, Nz):
+    """flags and u_y of the two scenes with boundaries (global arrays, shape (Nz,Ny,Nx))"""
+    import numpy as np
+    zz, yy, xx = np.meshgrid(np.arange(Nz), np.arange(Ny), np.arange(Nx), indexing="ij", sparse=True)
+    flags = np.zeros((Nz, Ny, Nx), np.uint8)
+    if "cavity" in workload:  # walls on five faces, equilibrium lid on z = Nz-1 moving along +y
+        for sl in [np.s_[0, :, :], np.s_[:, 0, :], np.s_[:, -1, :], np.s_[:, :, 0], np.s_[:, :, -1]]:
+            flags[sl] = fx.TYPE_S
+        flags[-1, :, :] = fx.TYPE_E
+        uy = np.zeros((Nz, Ny, Nx), np.float32); uy[-1, :, :] = 0.1
+        return flags, uy
+    # wind tunnel: sphere + TYPE_E faces (SURVEY section 8d, C3)
+    flags[(xx - Nx / 2) ** 2 + (yy - Ny / 4) ** 2 + (zz - Nz / 2) ** 2 <= (Nx / 8) ** 2] = fx.TYPE_S
+    for sl in [np.s_[0, :, :], np.s_[-1, :, :], np.s_[:, 0, :], np.s_[:, -1, :], np.s_[:, :, 0], np.s_[:, :, -1]]:
+        flags[sl] = fx.TYPE_E
+    return flags, np.where(flags == fx.TYPE_S, 0.0, 0.075).astype(np.float32)
 
 
 def measured_peaks():
@@ -138,6 +158,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--overlap", type=int, default=-1, help="multi-GPU: 1 = shell/exchange on one stream, interior on another; 0 = one stream; -1 = library default")
     ap.add_argument("--reserve", type=int, default=-1, help="resident-block slots the interior kernel leaves free for the exchange (with --overlap 1)")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the workload's box is the GLOBAL grid, divided among the GPUs")
     ap.add_argument("--split", default="", help="Dx,Dy,Dz domain grid for multi-GPU runs (default: z first, then y)")
     ap.add_argument("--variant", type=int, default=0, help="kernel choice: 0 default (pipelined), 1 general one-cell-per-thread, 2 or 4 cells per thread, 8 pipelined")
     args = ap.parse_args()
@@ -175,7 +196,7 @@ def main():
         if Dx * Dy * Dz != n_gpus: raise SystemExit("--split must multiply to the number of GPUs")
     if world == 1 and n_gpus > 1:
         raise SystemExit("launch multi-GPU runs with torchrun (one process per GPU)")
-    Nx, Ny, Nz = box[0] * Dx, box[1] * Dy, box[2] * Dz
+    Nx, Ny, Nz = (box[0], box[1], box[2]) if args.strong else (box[0] * Dx, box[1] * Dy, box[2] * Dz)
     device = local_rank if world > 1 else 0
     K, W = args.steps, args.warmup
 
@@ -187,16 +208,13 @@ def main():
     if args.reserve >= 0: lib.set_interior_reserve(args.reserve)
     # ---------------- device-resident arm: `value` ----------------
     force = (0.0, 1e-6, 0.0) if feat & 1 else (0.0, 0.0, 0.0)
-    sim = fx.LBM(Nx, Ny, Nz, 1.0, *force, Dx=Dx, Dy=Dy, Dz=Dz, velocity_set=Q, collision=collision, storage=storage, features=feat,
+    nu = 0.1 * (Nz - 2) / 1000.0 if "cavity" in args.workload else 1.0
+    sim = fx.LBM(Nx, Ny, Nz, nu, *force, Dx=Dx, Dy=Dy, Dz=Dz, velocity_set=Q, collision=collision, storage=storage, features=feat,
                  comm=comm, devices=None if comm else [device], host_fields=bool(feat & 2), benchmark=True, overlap=overlap)
-    if feat & 2:  # wind tunnel: sphere + TYPE_E faces
-        zz, yy, xx = np.meshgrid(np.arange(Nz), np.arange(Ny), np.arange(Nx), indexing="ij", sparse=True)
-        flags = np.zeros((Nz, Ny, Nx), np.uint8)
-        flags[(xx - Nx / 2) ** 2 + (yy - Ny / 4) ** 2 + (zz - Nz / 2) ** 2 <= (Nx / 8) ** 2] = fx.TYPE_S
-        for sl in [np.s_[0, :, :], np.s_[-1, :, :], np.s_[:, 0, :], np.s_[:, -1, :], np.s_[:, :, 0], np.s_[:, :, -1]]:
-            flags[sl] = fx.TYPE_E
-        sim.flags.set_global(flags)
-        sim.u.set_global(np.where(flags == fx.TYPE_S, 0.0, 0.075).astype(np.float32), 1)
+    scene_flags, scene_uy = None, None
+    if feat & 2:
+        scene_flags, scene_uy = make_scene(args.workload, fx, Nx, Ny, Nz)
+        sim.flags.set_global(scene_flags); sim.u.set_global(scene_uy, 1)
     (d0, dom), = sim.local_domains()
     sim.run(0)
     sim.run(W, sync=True)
@@ -241,10 +259,10 @@ def main():
     # ---------------- end-to-end arm through the host API with host buffers: `e2e` ----------------
     e2e = None
     if not args.no_e2e:
-        sim = fx.LBM(Nx, Ny, Nz, 1.0, *force, Dx=Dx, Dy=Dy, Dz=Dz, velocity_set=Q, collision=collision, storage=storage, features=feat,
+        sim = fx.LBM(Nx, Ny, Nz, nu, *force, Dx=Dx, Dy=Dy, Dz=Dz, velocity_set=Q, collision=collision, storage=storage, features=feat,
                      comm=comm, devices=None if comm else [device], host_fields=True, benchmark=True, overlap=overlap)
         if feat & 2:
-            sim.flags.set_global(flags); sim.u.set_global(np.where(flags == fx.TYPE_S, 0.0, 0.075).astype(np.float32), 1)
+            sim.flags.set_global(scene_flags); sim.u.set_global(scene_uy, 1)
         (d0, dom), = sim.local_domains()
         h2d = dom.rho.nbytes + dom.u.nbytes + dom.flags.nbytes
         d2h = dom.rho.nbytes + dom.u.nbytes
@@ -270,7 +288,7 @@ def main():
     if rank == 0:
         published = {"d3q19_srt_fp32_256": 42152.0, "d3q19_srt_fp16s_256": 55609.0}  # README.md:1147, 1x B200, 256^3
         line = {"metric": "MLUPs/s", "value": round(mlups, 1), "unit": "MLUPs/s", "n_gpus": n_gpus, "steps": K, "warmup": W,
-                "ms_per_step": round(ms_total / K, 5), "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": round(ms_total / K, 5), "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
                 "vs_baseline": round(mlups / published[args.workload], 4) if (args.workload in published and n_gpus == 1) else None,
                 "dtype": "f32 arithmetic, " + st + " DDF storage", "data": "synthetic",
                 "config": {"workload": args.workload, "description": desc, "global_grid": [Nx, Ny, Nz], "domains": [Dx, Dy, Dz], "overlap": bool(overlap and n_gpus > 1),
