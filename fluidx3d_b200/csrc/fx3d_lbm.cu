@@ -56,7 +56,7 @@ static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int re
 	const int want = g_variant.load();
 	uint32_t K = 1u;
 	bool pipelined = false;
-	if(want==8 || (want==0 && default_pipelined(region))) { // pipelined kernel: 4 cells per thread (2 for D3Q27 FP32)
+	if(want==8 || want==16 || (want==0 && default_pipelined(region))) { // pipelined kernel: 4 cells per thread (2 for D3Q27 FP32)
 		const uint32_t pk = pipe_cells_of(lat->velocity_set, lat->storage);
 		if(inner%pk==0u) { K = pk; pipelined = true; }
 	}
@@ -69,7 +69,7 @@ static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int re
 	const bool vf = (lat->features&FX3D_VOLUME_FORCE)!=0u;
 	for(const Region& R : regs) {
 		int rc;
-		FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, pipelined ? 0 : (int)K, (int)lat->collision, vf, stream, region==FX3D_REGION_INTERIOR ? g_interior_reserve.load() : 0); })
+		FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, pipelined ? (want==8 ? -1 : 0) : (int)K, (int)lat->collision, vf, stream, region==FX3D_REGION_INTERIOR ? g_interior_reserve.load() : 0); })
 		if(rc!=FX3D_OK) return rc;
 	}
 	return FX3D_OK;
@@ -81,7 +81,7 @@ using namespace fx3d;
 extern "C" {
 
 const char* fx3d_last_error(void) { return t_error.c_str(); }
-int fx3d_set_kernel_variant(int variant) { if(variant!=0&&variant!=1&&variant!=2&&variant!=4&&variant!=8) { set_error("variant must be 0 (auto), 1 (general), 2 or 4 (cells per thread), 8 (pipelined)"); return FX3D_ERR_INVALID; } g_variant = variant; return FX3D_OK; }
+int fx3d_set_kernel_variant(int variant) { if(variant!=0&&variant!=1&&variant!=2&&variant!=4&&variant!=8&&variant!=16) { set_error("variant must be 0 (auto), 1 (general), 2 or 4 (cells per thread), 8 (pipelined, cp.async), 16 (pipelined, bulk copies where eligible)"); return FX3D_ERR_INVALID; } g_variant = variant; return FX3D_OK; }
 int fx3d_set_interior_reserve(int blocks) { if(blocks<0||blocks>1024) { set_error("reserve must be 0..1024 blocks"); return FX3D_ERR_INVALID; } g_interior_reserve = blocks; return FX3D_OK; }
 int fx3d_launch_count(uint64_t* launches) { if(!launches) return FX3D_ERR_INVALID; *launches = g_launches.load(); return FX3D_OK; }
 

@@ -78,6 +78,9 @@ template<> struct Pack<ST_FP32, 4> {
 	FX3D_HD void store_head(float* q) const { *reinterpret_cast<unsigned long long*>(q) = bits64(p[0]); q[2] = f2_lo(p[1]); } // all but the last element
 	FX3D_HD uint32_t first_bits() const { return __float_as_uint(f2_lo(p[0])); }
 	FX3D_HD uint32_t last_bits() const { return __float_as_uint(f2_hi(p[1])); }
+	// my 4 elements belong at positions x+1..x+4 (up) / x-1..x+2 (down) of a periodic row of W elements (x a multiple of 4)
+	FX3D_HD void store_row_up(float* row, uint32_t x, uint32_t W) const { row[x+1u] = f2_lo(p[0]); *reinterpret_cast<unsigned long long*>(row+x+2u) = bits64(make_f2(f2_hi(p[0]), f2_lo(p[1]))); row[x+4u==W ? 0u : x+4u] = f2_hi(p[1]); }
+	FX3D_HD void store_row_down(float* row, uint32_t x, uint32_t W) const { row[x==0u ? W-1u : x-1u] = f2_lo(p[0]); *reinterpret_cast<unsigned long long*>(row+x) = bits64(make_f2(f2_hi(p[0]), f2_lo(p[1]))); row[x+2u] = f2_hi(p[1]); }
 	FX3D_HD void push_back(uint32_t b) { p[0] = make_f2(f2_hi(p[0]), f2_lo(p[1])); p[1] = make_f2(f2_hi(p[1]), __uint_as_float(b)); }  // {e1,e2,e3,b}
 	FX3D_HD void push_front(uint32_t b) { p[1] = make_f2(f2_hi(p[0]), f2_lo(p[1])); p[0] = make_f2(__uint_as_float(b), f2_lo(p[0])); } // {b,e0,e1,e2}
 	template<int k> FX3D_HD F2 get_pair() const { return p[k]; }
@@ -119,6 +122,8 @@ template<int ST> struct Pack<ST, 4> {
 	FX3D_HD void store_head(uint16_t* q) const { *reinterpret_cast<uint32_t*>(q) = r[0]; q[2] = (uint16_t)(r[1]&0xFFFFu); }
 	FX3D_HD uint32_t first_bits() const { return r[0]&0xFFFFu; }
 	FX3D_HD uint32_t last_bits() const { return r[1]>>16; }
+	FX3D_HD void store_row_up(uint16_t* row, uint32_t x, uint32_t W) const { row[x+1u] = (uint16_t)r[0]; *reinterpret_cast<uint32_t*>(row+x+2u) = (r[0]>>16)|(r[1]<<16); row[x+4u==W ? 0u : x+4u] = (uint16_t)(r[1]>>16); }
+	FX3D_HD void store_row_down(uint16_t* row, uint32_t x, uint32_t W) const { row[x==0u ? W-1u : x-1u] = (uint16_t)r[0]; *reinterpret_cast<uint32_t*>(row+x) = (r[0]>>16)|(r[1]<<16); row[x+2u] = (uint16_t)(r[1]>>16); }
 	FX3D_HD void push_back(uint32_t b) { r[0] = (r[0]>>16)|(r[1]<<16); r[1] = (r[1]>>16)|(b<<16); }
 	FX3D_HD void push_front(uint32_t b) { r[1] = (r[1]<<16)|(r[0]>>16); r[0] = (r[0]<<16)|(b&0xFFFFu); }
 	template<int k> FX3D_HD F2 get_pair() const { return decode_half_pair<ST>(r[k]); } // to the working scale of Codec<ST>
@@ -373,6 +378,64 @@ FX3D_HD unsigned char* dynamic_smem() {
 #endif
 }
 
+// ---- collision of the K cells a thread holds in A (raw storage vectors, stream-in order), pair by pair in packed arithmetic;
+// on return A holds what streams out through the same slots. flags4: the flag bytes of the cells (TYPE_S for cells to skip).
+template<int Q, int COLL, int ST, bool VF, int K> FX3D_HD void collide_tile(const Lattice& L, Pack<ST, K> (&A)[Q], const uint32_t flags4, const uint32_t x0, const uint32_t yc, const uint32_t z) {
+	typedef Codec<ST> C;
+	typedef typename C::elem_t E;
+	static_for<0, K/2, 1>([&](auto Pp) {
+		constexpr int p = Pp;
+		const uint32_t fb_lo = (flags4>>(16*p))&TYPE_BO, fb_hi = (flags4>>(16*p+8))&TYPE_BO;
+		const bool act_lo = fb_lo!=TYPE_S, act_hi = fb_hi!=TYPE_S;
+		if(act_lo || act_hi) {
+			const bool e_lo = L.eb!=0u && fb_lo==TYPE_E, e_hi = L.eb!=0u && fb_hi==TYPE_E;
+			const uint64_t n = lin(L, x0+2u*(uint32_t)p, yc, z), N = cells(L);
+			F2 rho_e = vsplat<F2>(1.0f), ux_e = vsplat<F2>(0.0f), uy_e = ux_e, uz_e = ux_e;
+			if(e_lo || e_hi) {
+				const uint64_t nl = e_lo ? n : n+1ull, nh = e_hi ? n+1ull : n;
+				rho_e = make_f2(L.rho[nl], L.rho[nh]); ux_e = make_f2(L.u[nl], L.u[nh]); uy_e = make_f2(L.u[N+nl], L.u[N+nh]); uz_e = make_f2(L.u[2ull*N+nl], L.u[2ull*N+nh]);
+			}
+			F2 rhon, uxn, uyn, uzn;
+			const bool both = act_lo && act_hi;
+			if constexpr(pipe_collide_mode<Q, ST>()==2) {
+			// populations are unpacked on demand and the results packed straight into the slot they stream out through:
+			// store_f() sends fhn[i] to the neighbour-side slot (A[i+1]) and fhn[i+1] to the local slot (A[i])
+			auto get = [&](auto I) { return A[I.value].template get_pair<p>(); };
+			const uint32_t am = (act_lo ? 0x0000FFFFu : 0u)|(act_hi ? 0xFFFF0000u : 0u), em = (e_lo ? 0x0000FFFFu : 0u)|(e_hi ? 0xFFFF0000u : 0u);
+			auto put = [&](auto I, F2 v) { // lanes that are not collided here keep what they streamed in
+				constexpr int i = I.value;
+				constexpr int dst = i==0 ? 0 : (i&1) ? i+1 : i-1;
+				if constexpr(sizeof(E)==2) A[dst].template set_masked<p>(v, am);
+				else { if(both) A[dst].template set_pair<p>(v); else A[dst].template set_lanes<p>(v, act_lo, act_hi); }
+			};
+			auto put_e = [&](auto I, F2 v) { // equilibrium-boundary lanes only
+				constexpr int i = I.value;
+				constexpr int dst = i==0 ? 0 : (i&1) ? i+1 : i-1;
+				A[dst].template set_masked<p>(v, em);
+			};
+			// within a direction pair both members are read before either is written, so the in-place swap is safe
+			collide_cell_stream<Q, COLL, VF, F2>(get, put, put_e, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+			} else {
+			F2 f[Q];
+			static_for<0, Q, 1>([&](auto I) { f[I] = A[I].template get_pair<p>(); });
+			if constexpr(pipe_collide_mode<Q, ST>()==1) collide_cell_fused<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+			else collide_cell<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+			if(both) {
+				A[0].template set_pair<p>(f[0]);
+				static_for<1, Q, 2>([&](auto I) { constexpr int i = I; A[i+1].template set_pair<p>(f[i]); A[i].template set_pair<p>(f[i+1]); });
+			} else {
+				A[0].template set_lanes<p>(f[0], act_lo, act_hi);
+				static_for<1, Q, 2>([&](auto I) { constexpr int i = I; A[i+1].template set_lanes<p>(f[i], act_lo, act_hi); A[i].template set_lanes<p>(f[i+1], act_lo, act_hi); });
+			}
+			}
+			if(L.upd!=0u) {
+				if(act_lo && !e_lo) { L.rho[n] = f2_lo(rhon); L.u[n] = f2_lo(uxn); L.u[N+n] = f2_lo(uyn); L.u[2ull*N+n] = f2_lo(uzn); }
+				if(act_hi && !e_hi) { L.rho[n+1ull] = f2_hi(rhon); L.u[n+1ull] = f2_hi(uxn); L.u[N+n+1ull] = f2_hi(uyn); L.u[2ull*N+n+1ull] = f2_hi(uzn); }
+			}
+		}
+	});
+}
+
 template<int Q, int COLL, int ST, bool VF, int ODD>
 __global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_collide_pipe(const Lattice L, const Region R, const uint32_t tiles_x, const uint32_t tiles_y) {
 	// Work unit = a run of z planes of one column of tiles (fixed x-group block and y rows); a block walks its units and, inside
@@ -473,58 +536,7 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_col
 				}
 			});
 
-			// ---- collide the cell pairs in packed arithmetic ----
-			static_for<0, K/2, 1>([&](auto Pp) {
-				constexpr int p = Pp;
-				const uint32_t fb_lo = (flags4>>(16*p))&TYPE_BO, fb_hi = (flags4>>(16*p+8))&TYPE_BO;
-				const bool act_lo = fb_lo!=TYPE_S, act_hi = fb_hi!=TYPE_S;
-				if(act_lo || act_hi) {
-					const bool e_lo = L.eb!=0u && fb_lo==TYPE_E, e_hi = L.eb!=0u && fb_hi==TYPE_E;
-					const uint64_t n = lin(L, x0+2u*(uint32_t)p, yc, z), N = cells(L);
-					F2 rho_e = vsplat<F2>(1.0f), ux_e = vsplat<F2>(0.0f), uy_e = ux_e, uz_e = ux_e;
-					if(e_lo || e_hi) {
-						const uint64_t nl = e_lo ? n : n+1ull, nh = e_hi ? n+1ull : n;
-						rho_e = make_f2(L.rho[nl], L.rho[nh]); ux_e = make_f2(L.u[nl], L.u[nh]); uy_e = make_f2(L.u[N+nl], L.u[N+nh]); uz_e = make_f2(L.u[2ull*N+nl], L.u[2ull*N+nh]);
-					}
-					F2 rhon, uxn, uyn, uzn;
-					const bool both = act_lo && act_hi;
-					if constexpr(pipe_collide_mode<Q, ST>()==2) {
-					// populations are unpacked on demand and the results packed straight into the slot they stream out through:
-					// store_f() sends fhn[i] to the neighbour-side slot (A[i+1]) and fhn[i+1] to the local slot (A[i])
-					auto get = [&](auto I) { return A[I.value].template get_pair<p>(); };
-					const uint32_t am = (act_lo ? 0x0000FFFFu : 0u)|(act_hi ? 0xFFFF0000u : 0u), em = (e_lo ? 0x0000FFFFu : 0u)|(e_hi ? 0xFFFF0000u : 0u);
-					auto put = [&](auto I, F2 v) { // lanes that are not collided here keep what they streamed in
-						constexpr int i = I.value;
-						constexpr int dst = i==0 ? 0 : (i&1) ? i+1 : i-1;
-						if constexpr(sizeof(E)==2) A[dst].template set_masked<p>(v, am);
-						else { if(both) A[dst].template set_pair<p>(v); else A[dst].template set_lanes<p>(v, act_lo, act_hi); }
-					};
-					auto put_e = [&](auto I, F2 v) { // equilibrium-boundary lanes only
-						constexpr int i = I.value;
-						constexpr int dst = i==0 ? 0 : (i&1) ? i+1 : i-1;
-						A[dst].template set_masked<p>(v, em);
-					};
-					// within a direction pair both members are read before either is written, so the in-place swap is safe
-					collide_cell_stream<Q, COLL, VF, F2>(get, put, put_e, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
-					} else {
-					F2 f[Q];
-					static_for<0, Q, 1>([&](auto I) { f[I] = A[I].template get_pair<p>(); });
-					if constexpr(pipe_collide_mode<Q, ST>()==1) collide_cell_fused<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
-					else collide_cell<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
-					if(both) {
-						A[0].template set_pair<p>(f[0]);
-						static_for<1, Q, 2>([&](auto I) { constexpr int i = I; A[i+1].template set_pair<p>(f[i]); A[i].template set_pair<p>(f[i+1]); });
-					} else {
-						A[0].template set_lanes<p>(f[0], act_lo, act_hi);
-						static_for<1, Q, 2>([&](auto I) { constexpr int i = I; A[i+1].template set_lanes<p>(f[i], act_lo, act_hi); A[i].template set_lanes<p>(f[i+1], act_lo, act_hi); });
-					}
-					}
-					if(L.upd!=0u) {
-						if(act_lo && !e_lo) { L.rho[n] = f2_lo(rhon); L.u[n] = f2_lo(uxn); L.u[N+n] = f2_lo(uyn); L.u[2ull*N+n] = f2_lo(uzn); }
-						if(act_hi && !e_hi) { L.rho[n+1ull] = f2_hi(rhon); L.u[n+1ull] = f2_hi(uxn); L.u[N+n+1ull] = f2_hi(uyn); L.u[2ull*N+n+1ull] = f2_hi(uzn); }
-					}
-				}
-			});
+			collide_tile<Q, COLL, ST, VF, K>(L, A, flags4, x0, yc, z);
 
 			// ---- stream out straight from registers (same addresses as stream in) ----
 			if(__any_sync(FULL, any_active)) {
@@ -561,6 +573,152 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_col
 		cp_async_wait<0>();
 #undef FX3D_AT
 	}
+}
+
+// ================================================================================================================
+// stream_collide, bulk-copy form: the same z-marching persistent blocks, but the DDF rows move between HBM and shared memory
+// with TMA bulk copies (cp.async.bulk, completion on an mbarrier) issued by the first warp, one lane per row buffer, and the
+// results go back the same way. Measured on B200 (tools/microbench/ubench3.cu): with 8-16 warps per SM, per-thread cp.async
+// loads + STG stores saturate at 5.2 TB/s however deep the ring is, bulk copies reach 6.4 TB/s. A tile row (all x of one (y,z))
+// is one contiguous segment per slot, so: one copy per (slot, tile row) in, one out; the x-shifted directions are read and
+// written at shifted positions of the periodic row buffer (no shuffles, no edge accesses). Requires the tile to span the
+// whole row: no x halo, Nx = 4*blockDim.x <= 512, 16-byte multiples (see tma_eligible()).
+// Per tile: wait(full[stage]) -> registers <- stage -> barrier -> collide -> stage <- registers -> proxy fence + barrier ->
+// bulk stores. A stage is refilled only after the bulk stores issued from it have finished reading it.
+// ================================================================================================================
+#ifndef FX3D_TMA_STAGES
+#define FX3D_TMA_STAGES 2
+#endif
+// direction components for a run-time direction index, from 2-bit fields of a constant (no table in memory)
+FX3D_HDC constexpr unsigned long long pack_dirs(int axis) { unsigned long long m = 0ull; for(int i=0; i<27; i++) m |= (unsigned long long)(dir_c(axis, i)+1)<<(2*i); return m; }
+FX3D_HD int dir_rt(int axis, uint32_t i) { constexpr unsigned long long my = pack_dirs(1), mz = pack_dirs(2); return (int)(((axis==1 ? my : mz)>>(2u*i))&3ull)-1; }
+template<int Q, int ST> FX3D_HDC constexpr uint32_t tma_stage_bytes() { return (uint32_t)Q*128u*4u*(ST==ST_FP32 ? 4u : 2u)+128u*4u; } // Q row-buffer sets + flag bytes
+template<int Q, int ST> FX3D_HDC constexpr int tma_blocks_per_sm() { return ST==ST_FP32 ? 2 : Q>19 ? 3 : 4; } // by shared memory; also the register cap
+template<int Q, int ST> FX3D_HDC constexpr uint32_t tma_smem_bytes() { return 128u+(uint32_t)FX3D_TMA_STAGES*tma_stage_bytes<Q, ST>(); }
+#if defined(FX3D_HOST_EMULATION)
+// emulation: copies happen at issue time; the barrier word counts completed phases (the issuing thread completes the phase itself)
+FX3D_HD void mbar_init(uint64_t* b) { __atomic_store_n(b, 0ull, __ATOMIC_SEQ_CST); }
+FX3D_HD void mbar_expect_tx(uint64_t*, uint32_t) {}
+FX3D_HD void mbar_phase_done_emulated(uint64_t* b) { __atomic_fetch_add(b, 1ull, __ATOMIC_SEQ_CST); }
+FX3D_HD void mbar_wait(uint64_t* b, uint32_t parity) { while((__atomic_load_n(b, __ATOMIC_SEQ_CST)&1ull)==(uint64_t)parity) std::this_thread::yield(); }
+FX3D_HD void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t*) { std::memcpy(smem_dst, gmem_src, bytes); }
+FX3D_HD void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) { std::memcpy(gmem_dst, smem_src, bytes); }
+FX3D_HD void bulk_commit() {}
+FX3D_HD void bulk_wait_read() {}
+FX3D_HD void bulk_wait_all() {}
+FX3D_HD void fence_async_smem() {}
+#else
+FX3D_HD uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+FX3D_HD void mbar_init(uint64_t* b) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_addr(b)) : "memory"); }
+FX3D_HD void mbar_expect_tx(uint64_t* b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(b)), "r"(bytes) : "memory"); }
+FX3D_HD void mbar_phase_done_emulated(uint64_t*) {}
+FX3D_HD void mbar_wait(uint64_t* b, uint32_t parity) {
+	asm volatile("{\n.reg .pred p;\nFX3D_WAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra FX3D_DONE_%=;\nbra FX3D_WAIT_%=;\nFX3D_DONE_%=:\n}" :: "r"(smem_addr(b)), "r"(parity) : "memory");
+}
+FX3D_HD void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* b) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(smem_addr(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_addr(b)) : "memory");
+}
+FX3D_HD void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) { asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gmem_dst), "r"(smem_addr(smem_src)), "r"(bytes) : "memory"); }
+FX3D_HD void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+FX3D_HD void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); } // my bulk stores have finished reading shared memory
+FX3D_HD void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+FX3D_HD void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); } // my shared-memory writes become visible to the bulk-copy engine
+#endif
+
+template<int Q, int COLL, int ST, bool VF, int ODD>
+__global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_collide_tma(const Lattice L, const Region R, const uint32_t tiles_y) {
+	constexpr int K = 4, S = FX3D_TMA_STAGES;
+	constexpr uint32_t odd = (uint32_t)ODD;
+	typedef Codec<ST> C;
+	typedef typename C::elem_t E;
+	typedef Pack<ST, K> P;
+	constexpr uint32_t VB = (uint32_t)(sizeof(E)*K), SET = 128u*VB, STAGE = tma_stage_bytes<Q, ST>(); // SET: one row-buffer set (all rows of the tile) of one slot
+	unsigned char* const smem = dynamic_smem();
+	uint64_t* const full = reinterpret_cast<uint64_t*>(smem); // full[stage]: the bulk loads of the tile in this stage have landed
+	unsigned char* const ring = smem+128;
+	const uint32_t tid = threadIdx.x+threadIdx.y*blockDim.x;
+	const uint32_t W = blockDim.x*(uint32_t)K, row_bytes = blockDim.x*VB; // W == L.Nx
+	const uint32_t ncopies = (uint32_t)(Q+1)*blockDim.y; // per tile: Q slot rows + one flag row for every tile row
+	if(tid==0u) { for(int s=0; s<S; s++) mbar_init(full+s); }
+	fence_async_smem();
+	__syncthreads();
+
+	// global address of copy c of the tile (rows R.y0+yb*by.., plane z): c = ty*(Q+1)+j; j<Q: slot buffer j, j==Q: flags
+	auto copy_src = [&](uint32_t c, uint32_t yb, uint32_t z, uint32_t& smem_off, uint32_t& bytes) -> char* {
+		const uint32_t ty = c/(uint32_t)(Q+1), j = c%(uint32_t)(Q+1), y = R.y0+yb*blockDim.y+ty;
+		if(j==(uint32_t)Q) { smem_off = (uint32_t)Q*SET+ty*W; bytes = W; return reinterpret_cast<char*>(L.flags)+((uint64_t)y+(uint64_t)z*L.Ny)*L.Nx; }
+		smem_off = j*SET+ty*row_bytes; bytes = row_bytes;
+		uint32_t slot = j, yr = y, zr = z;
+		if(j>0u) {
+			const uint32_t i = (j&1u) ? j : j-1u; // odd member of the direction pair
+			if(j&1u) slot = odd ? i : i+1u;
+			else { slot = odd ? i+1u : i; yr = step_rt(dir_rt(1, i), y, L.Ny); zr = step_rt(dir_rt(2, i), z, L.Nz); }
+		}
+		return reinterpret_cast<char*>(L.fi)+((uint64_t)slot*L.slot+row(L, yr, zr))*sizeof(E);
+	};
+	auto load_tile = [&](uint32_t yb, uint32_t z, uint32_t stage) { // first warp; lane c issues copies c, c+32, ..
+		if(tid==0u) mbar_expect_tx(full+stage, blockDim.y*((uint32_t)Q*row_bytes+W));
+		for(uint32_t c=tid; c<ncopies; c+=32u) { uint32_t off, bytes; char* src = copy_src(c, yb, z, off, bytes); bulk_load(ring+(size_t)stage*STAGE+off, src, bytes, full+stage); }
+#if defined(FX3D_HOST_EMULATION)
+		__shfl_down_sync(0xFFFFFFFFu, 0u, 1u); // (emulation: all lanes' copies are done before lane 0 completes the phase)
+		if(tid==0u) mbar_phase_done_emulated(full+stage);
+#endif
+	};
+	auto store_tile = [&](uint32_t yb, uint32_t z, uint32_t stage) {
+		for(uint32_t c=tid; c<ncopies; c+=32u) { uint32_t off, bytes; char* dst = copy_src(c, yb, z, off, bytes); if(c%(uint32_t)(Q+1)!=(uint32_t)Q) bulk_store(dst, ring+(size_t)stage*STAGE+off, bytes); }
+		bulk_commit();
+	};
+
+	const uint32_t nz = R.z1-R.z0;
+	const uint64_t ntiles = (uint64_t)tiles_y*nz;
+	uint64_t tile = ntiles*blockIdx.x/gridDim.x;
+	const uint64_t tile_end = ntiles*(blockIdx.x+1u)/gridDim.x;
+	uint32_t it = 0u; // tiles this block has consumed: stage = it%S, barrier parity = (it/S)&1
+	const uint32_t x0 = (uint32_t)K*threadIdx.x;
+	while(tile<tile_end) {
+		const uint32_t yb = (uint32_t)(tile/nz), zoff = (uint32_t)(tile%nz);
+		const uint32_t zs = R.z0+zoff, ze = (uint64_t)(nz-zoff)<=tile_end-tile ? R.z1 : zs+(uint32_t)(tile_end-tile);
+		tile += ze-zs;
+		const uint32_t y = R.y0+yb*blockDim.y+threadIdx.y;
+		if(tid<32u) { // prologue: the first S-1 planes of this run
+			bulk_wait_read();
+			for(uint32_t k=0u; k<(uint32_t)(S-1); k++) if(zs+k<ze) load_tile(yb, zs+k, (it+k)%(uint32_t)S);
+		}
+		for(uint32_t z=zs; z<ze; z++, it++) {
+			const uint32_t stage = it%(uint32_t)S;
+			mbar_wait(full+stage, (it/(uint32_t)S)&1u);
+			unsigned char* const sb = ring+(size_t)stage*STAGE;
+			const uint32_t flags4 = *reinterpret_cast<const uint32_t*>(sb+(size_t)Q*SET+tid*(uint32_t)K);
+			// ---- stream in from the stage: my vectors, and for the x-shifted directions the element beyond them in the periodic row ----
+			P A[Q];
+			static_for<0, Q, 1>([&](auto I) { A[I].load(reinterpret_cast<const E*>(sb+(size_t)I.value*SET+tid*VB)); });
+			static_for<1, Q, 2>([&](auto I) {
+				constexpr int i = I;
+				const E* rowp = reinterpret_cast<const E*>(sb+(size_t)(i+1)*SET+threadIdx.y*row_bytes);
+				if constexpr(dir_x(i)>0) A[i+1].push_back(P::bits(rowp[x0+(uint32_t)K==W ? 0u : x0+(uint32_t)K]));
+				else if constexpr(dir_x(i)<0) A[i+1].push_front(P::bits(rowp[x0==0u ? W-1u : x0-1u]));
+			});
+			__syncthreads(); // everybody has read the stage before anybody writes results into it
+			// refill the other stage(s) now rather than at the top of the iteration: the bulk stores issued from it at the end of the
+			// previous iteration have had the stream-in to finish reading it, so the first warp rarely waits here
+			if(tid<32u && z+(uint32_t)(S-1)<ze) { bulk_wait_read(); load_tile(yb, z+(uint32_t)(S-1), (it+(uint32_t)(S-1))%(uint32_t)S); }
+			collide_tile<Q, COLL, ST, VF, K>(L, A, flags4, x0, y, z);
+			// ---- stream out into the same row buffers ----
+			A[0].store(reinterpret_cast<E*>(sb+tid*VB));
+			static_for<1, Q, 2>([&](auto I) {
+				constexpr int i = I;
+				A[i].store(reinterpret_cast<E*>(sb+(size_t)i*SET+tid*VB));
+				E* rowp = reinterpret_cast<E*>(sb+(size_t)(i+1)*SET+threadIdx.y*row_bytes);
+				if constexpr(dir_x(i)==0) A[i+1].store(rowp+x0);
+				else if constexpr(dir_x(i)>0) A[i+1].store_row_up(rowp, x0, W);
+				else A[i+1].store_row_down(rowp, x0, W);
+			});
+			fence_async_smem();
+			__syncthreads();
+			if(tid<32u) store_tile(yb, z, stage);
+		}
+	}
+	if(tid<32u) bulk_wait_all();
 }
 
 // ================================================================================================================

@@ -41,10 +41,44 @@ template<int Q, int COLL, int ST, bool VF> static int launch_pipe(const Lattice&
 	return L.odd ? launch_pipe_parity<Q, COLL, ST, VF, 1>(L, R, block, stream, reserve) : launch_pipe_parity<Q, COLL, ST, VF, 0>(L, R, block, stream, reserve);
 }
 
+// bulk-copy (TMA) kernel: the tile must span whole rows -- see the kernel's header comment
+static bool tma_eligible(const Lattice& L, const Region& R, const dim3& block) {
+	return L.Hx==0u && L.xo==0u && R.g0==0u && R.g1*4u==L.Nx && block.x*4u==L.Nx && L.Nx%16u==0u && block.x*block.y==128u && (R.y1-R.y0)%block.y==0u;
+}
+template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_tma_parity(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
+	const uint32_t tiles_y = (R.y1-R.y0)/block.y, nz = R.z1-R.z0;
+	constexpr uint32_t smem = tma_smem_bytes<Q, ST>();
+	int sms = 148, per_sm = tma_blocks_per_sm<Q, ST>();
+#if !defined(FX3D_HOST_EMULATION)
+	static std::atomic<uint64_t> configured{0ull};
+	int dev = 0; cudaGetDevice(&dev);
+	if(dev>=64 || !((configured.load()>>dev)&1ull)) {
+		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_tma<Q, COLL, ST, VF, ODD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if(e!=cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stream_collide_tma)");
+		if(dev<64) configured.fetch_or(1ull<<dev);
+	}
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#else
+	sms = 2; per_sm = 1;
+#endif
+	const uint64_t all_blocks = (uint64_t)sms*(uint64_t)per_sm, blocks = all_blocks>2ull*(uint64_t)std::max(reserve, 0) ? all_blocks-(uint64_t)std::max(reserve, 0) : all_blocks, ntiles = (uint64_t)tiles_y*nz;
+	if(ntiles==0ull) return FX3D_OK;
+	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, blocks), 1u, 1u);
+	FX3D_LAUNCH_SMEM((k_stream_collide_tma<Q, COLL, ST, VF, ODD>), grid, block, smem, stream, L, R, tiles_y);
+	return check_launch("stream_collide (bulk copies)");
+}
+template<int Q, int COLL, int ST, bool VF> static int launch_tma(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
+	return L.odd ? launch_tma_parity<Q, COLL, ST, VF, 1>(L, R, block, stream, reserve) : launch_tma_parity<Q, COLL, ST, VF, 0>(L, R, block, stream, reserve);
+}
+
 template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, int cells_per_thread, int collision, bool volume_force, void* stream, int reserve) {
 	if(R.g1<=R.g0||R.y1<=R.y0||R.z1<=R.z0) return FX3D_OK;
-	if(cells_per_thread==0) { // pipelined kernel; R.g0/g1 are in groups of 4 cells
+	if(cells_per_thread<=0) { // persistent kernels; R.g0/g1 are in groups of pipe_cells<Q,ST>() cells. 0: bulk copies where the tile spans the row, else cp.async; -1: cp.async
 		const dim3 block = block_shape(R.g1-R.g0);
+		if(cells_per_thread==0 && pipe_cells<Q, ST>()==4 && tma_eligible(L, R, block)) {
+			if(collision==COLL_SRT) return volume_force ? launch_tma<Q, COLL_SRT, ST, true>(L, R, block, stream, reserve) : launch_tma<Q, COLL_SRT, ST, false>(L, R, block, stream, reserve);
+			return volume_force ? launch_tma<Q, COLL_TRT, ST, true>(L, R, block, stream, reserve) : launch_tma<Q, COLL_TRT, ST, false>(L, R, block, stream, reserve);
+		}
 		if(collision==COLL_SRT) return volume_force ? launch_pipe<Q, COLL_SRT, ST, true>(L, R, block, stream, reserve) : launch_pipe<Q, COLL_SRT, ST, false>(L, R, block, stream, reserve);
 		return volume_force ? launch_pipe<Q, COLL_TRT, ST, true>(L, R, block, stream, reserve) : launch_pipe<Q, COLL_TRT, ST, false>(L, R, block, stream, reserve);
 	}

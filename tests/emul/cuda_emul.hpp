@@ -44,7 +44,7 @@ struct WarpCtx {
 	int pred[32];
 	unsigned lanes;
 };
-struct ThreadCtx { WarpCtx* warp; unsigned lane; unsigned char* smem; };
+struct ThreadCtx { WarpCtx* warp; unsigned lane; unsigned char* smem; std::barrier<>* block_bar; };
 inline thread_local ThreadCtx tctx;
 }
 inline thread_local uint3_ threadIdx, blockIdx;
@@ -77,22 +77,26 @@ template<class F> void launch(dim3 grid, dim3 block, F&& body, size_t smem_bytes
 			warps[wi].lanes = std::min(32u, nthreads-32u*wi);
 			warps[wi].bar = std::make_unique<std::barrier<>>((std::ptrdiff_t)warps[wi].lanes);
 		}
-		std::vector<unsigned char> smem(smem_bytes+16);
+		std::vector<unsigned char> smem(smem_bytes+128);
+		std::barrier<> block_bar((std::ptrdiff_t)nthreads);
 		std::vector<std::thread> th;
 		th.reserve(nthreads);
 		for(unsigned tid=0u; tid<nthreads; tid++) th.emplace_back([&, tid]() {
 			threadIdx = uint3_{ tid%block.x, (tid/block.x)%block.y, tid/(block.x*block.y) };
 			blockIdx = uint3_{ bx, by, bz };
 			blockDim = block; gridDim = grid;
-			tctx.warp = &warps[tid/32u]; tctx.lane = tid%32u; tctx.smem = smem.data()+((16-reinterpret_cast<uintptr_t>(smem.data())%16)%16);
+			tctx.warp = &warps[tid/32u]; tctx.lane = tid%32u; tctx.smem = smem.data()+((128-reinterpret_cast<uintptr_t>(smem.data())%128)%128);
+			tctx.block_bar = &block_bar;
 			body();
 			tctx.warp->bar->arrive_and_drop(); // a thread that has returned no longer takes part in warp collectives
+			block_bar.arrive_and_drop();       // ... nor in block barriers
 		});
 		for(auto& t : th) t.join();
 	}
 }
 }
 
+static inline void __syncthreads() { emul::tctx.block_bar->arrive_and_wait(); }
 static inline uint32_t __float_as_uint(float x) { uint32_t u; std::memcpy(&u, &x, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float x; std::memcpy(&x, &u, 4); return x; }
 static inline uint32_t __shfl_down_sync(unsigned, uint32_t v, unsigned d) { return emul::exchange(v, (int)emul::tctx.lane+(int)d, emul::tctx.lane+d<32u); }

@@ -57,16 +57,17 @@ VID = [f"q{v[0]}c{v[1]}s{v[2]}f{v[3]}" for v in VARIANTS]
 
 
 @pytest.mark.parametrize("v", VARIANTS, ids=VID)
-@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8], ids=["default", "general", "vector2", "vector4", "pipelined"])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 8, 16], ids=["default", "general", "vector2", "vector4", "pipelined", "bulkcopy"])
 def test_fields_bit_exact_small(fx, v, variant):
     f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
-    for dims, steps in [((32, 12, 10), 1), ((32, 12, 10), 2), ((32, 12, 10), 3), ((64, 9, 7), 10), ((20, 6, 5), 5), ((7, 5, 3), 4), ((132, 4, 3), 3)]:
+    # (32,16,10), (64,8,7), (128,4,5): whole-row tiles, where the default / bulk-copy variants take the TMA kernel
+    for dims, steps in [((32, 12, 10), 1), ((32, 12, 10), 2), ((32, 16, 10), 3), ((64, 9, 7), 10), ((64, 8, 7), 4), ((128, 4, 5), 3), ((20, 6, 5), 5), ((7, 5, 3), 4), ((132, 4, 3), 3)]:
         got, want = product(fx, v, dims, (1, 1, 1), steps, f, variant), oracle(v, dims, (1, 1, 1), steps, f)
         for a, b in zip(got, want):
             assert np.array_equal(bits(a), bits(b)), (dims, steps)
 
 
-@pytest.mark.parametrize("variant", [4, 8], ids=["vector4", "pipelined"])
+@pytest.mark.parametrize("variant", [4, 8, 16], ids=["vector4", "pipelined", "bulkcopy"])
 @pytest.mark.parametrize("v", [(19, SRT, FP32, 0), (19, SRT, FP16S, 0), (19, SRT, FP16C, 0), (27, TRT, FP32, 3)], ids=["fp32", "fp16s", "fp16c", "q27trt"])
 def test_fields_bit_exact_medium_100_steps(fx, v, variant):
     # SURVEY 8d parity fixtures: 64^3 and the non-cubic 96x64x48, perturbed IC, 100 steps

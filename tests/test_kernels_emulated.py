@@ -61,6 +61,21 @@ def test_emulated_kernels_match_oracle(emul, v, dims, D, variant):
             assert np.array_equal(bits(a), bits(b))
 
 
+TMA_CASES = [((19, SRT, FP16S, 0), (32, 16, 4), (1, 1, 1)), ((19, SRT, FP32, 0), (64, 8, 3), (1, 1, 1)), ((19, TRT, FP16C, 3), (16, 32, 3), (1, 1, 1)),
+             ((27, TRT, FP32, 3), (32, 16, 3), (1, 1, 1)), ((27, SRT, FP16S, 1), (32, 32, 4), (1, 2, 2)), ((19, SRT, FP16S, 2), (64, 16, 6), (1, 2, 1))]
+
+
+@pytest.mark.parametrize("v,dims,D", TMA_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in TMA_CASES])
+def test_emulated_bulk_copy_kernel_matches_oracle(emul, v, dims, D):
+    """the bulk-copy (TMA) form of stream_collide on grids where it is eligible (tile = whole rows): row buffers in shared
+    memory, shifted reads/writes of the periodic row, stage recycling, two block barriers per tile"""
+    f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
+    for steps in (1, 2, 5):
+        got, want = product(emul, v, dims, D, steps, f, 16), oracle(v, dims, D, steps, f)
+        for a, b in zip(got, want):
+            assert np.array_equal(bits(a), bits(b))
+
+
 @pytest.mark.parametrize("variant", [1, 4, 8], ids=["general", "vector4", "pipelined"])
 def test_shell_plus_interior_equals_all(emul, variant):
     # FX3D_REGION_SHELL followed by FX3D_REGION_INTERIOR must cover every non-halo cell exactly once

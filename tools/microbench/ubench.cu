@@ -66,6 +66,18 @@ int main(){
   { size_t n=cells*4/4;  float t = timeit([&]{ k_rmw<unsigned,19><<<(unsigned)((n+127)/128),128>>>((unsigned*)buf, n, n); }); printf("RMW fp32 19 slots,  4 B/thread/slot: %.3f ms  %.0f GB/s\n", t, cells*19*4*2/t*1e-6); }
   { size_t n=cells*4/8;  float t = timeit([&]{ k_rmw<uint2,19><<<(unsigned)((n+127)/128),128>>>((uint2*)buf, n, n); }); printf("RMW fp32 19 slots,  8 B/thread/slot: %.3f ms  %.0f GB/s\n", t, cells*19*4*2/t*1e-6); }
   { size_t n=cells*4/16; float t = timeit([&]{ k_rmw<uint4,19><<<(unsigned)((n+127)/128),128>>>((uint4*)buf, n, n); }); printf("RMW fp32 19 slots, 16 B/thread/slot: %.3f ms  %.0f GB/s\n", t, cells*19*4*2/t*1e-6); }
+  // the same sweep with occupancy capped through dynamic shared memory: bandwidth as a function of the bytes in flight per SM
+  // (blocks/SM x 128 threads x 19 slots x V bytes) -- tells how deep the stream_collide pipeline has to be
+  for(int bps : {1, 2, 3, 4, 6, 8, 12, 16}) {
+    const int smem = (int)(227*1024/bps) - 1024;
+    CK(cudaFuncSetAttribute(k_rmw<uint2,19>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_rmw<uint4,19>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    size_t n8=cells*2/8, n16=cells*4/16;
+    float t8 = timeit([&]{ k_rmw<uint2,19><<<(unsigned)((n8+127)/128),128,smem>>>((uint2*)buf, n8, n8); });
+    float t16 = timeit([&]{ k_rmw<uint4,19><<<(unsigned)((n16+127)/128),128,smem>>>((uint4*)buf, n16, n16); });
+    printf("blocks/SM=%2d  fp16 8 B/thread: %5.0f GB/s (%3d KB in flight/SM)   fp32 16 B/thread: %5.0f GB/s (%3d KB in flight/SM)\n", bps,
+      cells*19*2*2/t8*1e-6, bps*128*19*8/1024, cells*19*4*2/t16*1e-6, bps*128*19*16/1024);
+  }
   // plain copy for reference
   { size_t n=cells*19*2/16/2; uint4* a=(uint4*)buf; uint4* b=a+n; float t = timeit([&]{ cudaMemcpyAsync(b,a,n*16,cudaMemcpyDeviceToDevice); }); printf("cudaMemcpy D2D %.1f GB: %.0f GB/s (read+write)\n", n*16e-9, n*16*2/t*1e-6); }
   return 0;

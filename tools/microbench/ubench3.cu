@@ -1,0 +1,98 @@
+// Can a low-occupancy persistent kernel (the stream_collide shape: 8-16 heavy warps per SM) reach the HBM peak if the bytes move
+// by (a) per-thread cp.async (LDGSTS) + STG, or (b) TMA bulk copies (cp.async.bulk global<->shared, mbarrier completion) issued by
+// one thread per block? In-place 19-slot RMW sweep, tile = 128 threads x 8 B per slot, S-stage ring, tiles strided over the grid.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+#define CK(x) do{cudaError_t e=(x); if(e!=cudaSuccess){printf("err %s line %d\n", cudaGetErrorString(e), __LINE__); exit(1);} }while(0)
+constexpr int Q = 19, TPB = 128, VB = 8, ROW = TPB*VB; // bytes per slot per tile
+__device__ __forceinline__ uint32_t saddr(const void* p){ return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int n){ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(saddr(b)), "r"(n)); }
+__device__ __forceinline__ void mbar_expect(uint64_t* b, uint32_t bytes){ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(saddr(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity){
+  asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(saddr(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b){
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(saddr(dst)), "l"(src), "r"(bytes), "r"(saddr(b)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes){
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(saddr(src)), "r"(bytes) : "memory");
+}
+template<int S> __global__ void __launch_bounds__(TPB) k_tma(char* base, size_t slot_bytes, size_t ntiles){
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem); // S barriers
+  unsigned char* ring = smem+128;
+  const int tid = threadIdx.x;
+  if(tid==0) { for(int s=0;s<S;s++) mbar_init(bars+s, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  const size_t stride = gridDim.x;
+  auto load = [&](size_t tile, int stage) {
+    mbar_expect(bars+stage, Q*ROW);
+    for(int q=0;q<Q;q++) bulk_g2s(ring+(size_t)(stage*Q+q)*ROW, base+q*slot_bytes+tile*ROW, ROW, bars+stage);
+  };
+  size_t t = blockIdx.x; int k = 0;
+  if(tid==0) for(int s=0;s<S-1;s++) if(t+s*stride<ntiles) load(t+s*stride, s);
+  for(; t<ntiles; t+=stride, k++) {
+    const int stage = k%S;
+    if(tid==0 && t+(S-1)*stride<ntiles) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the stores that still read the stage to be refilled are done with it
+      load(t+(S-1)*stride, (k+S-1)%S);
+    }
+    mbar_wait(bars+stage, (k/S)&1);
+    uint2* mine = reinterpret_cast<uint2*>(ring+(size_t)stage*Q*ROW)+tid;
+    #pragma unroll
+    for(int q=0;q<Q;q++) { uint2 v = mine[q*TPB]; v.x += 1u; mine[q*TPB] = v; }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if(tid==0) {
+      for(int q=0;q<Q;q++) bulk_s2g(base+q*slot_bytes+t*ROW, ring+(size_t)(stage*Q+q)*ROW, ROW);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  if(tid==0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// (a) per-thread cp.async ring + direct STG
+template<int S> __global__ void __launch_bounds__(TPB) k_ldgsts(char* base, size_t slot_bytes, size_t ntiles){
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x;
+  const size_t stride = gridDim.x;
+  auto load = [&](size_t tile, int stage) {
+    #pragma unroll
+    for(int q=0;q<Q;q++) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(saddr(smem+(size_t)((stage*Q+q)*TPB+tid)*VB)), "l"(base+q*slot_bytes+tile*ROW+tid*VB) : "memory");
+  };
+  size_t t = blockIdx.x; int k = 0;
+  for(int s=0;s<S-1;s++) { if(t+s*stride<ntiles) load(t+s*stride, s); asm volatile("cp.async.commit_group;" ::: "memory"); }
+  for(; t<ntiles; t+=stride, k++) {
+    const int stage = k%S;
+    if(t+(S-1)*stride<ntiles) load(t+(S-1)*stride, (k+S-1)%S);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" :: "n"(S-1) : "memory");
+    uint2 v[Q];
+    #pragma unroll
+    for(int q=0;q<Q;q++) { v[q] = *reinterpret_cast<uint2*>(smem+(size_t)((stage*Q+q)*TPB+tid)*VB); v[q].x += 1u; }
+    #pragma unroll
+    for(int q=0;q<Q;q++) *reinterpret_cast<uint2*>(base+q*slot_bytes+t*ROW+tid*VB) = v[q];
+  }
+}
+template<class F> float timeit(F f, int reps=4){ cudaEvent_t e0,e1; cudaEventCreate(&e0); cudaEventCreate(&e1); f(); CK(cudaDeviceSynchronize()); float best=1e30f; for(int r=0;r<reps;r++){ cudaEventRecord(e0); f(); cudaEventRecord(e1); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms,e0,e1); if(ms<best) best=ms; } CK(cudaGetLastError()); return best; }
+template<int S> void run(char* buf, size_t slot_bytes, size_t ntiles, double bytes){
+  for(int bps : {1, 2, 4, 6, 8}) {
+    const int need = 128+S*Q*ROW; if(need*bps>227*1024) continue;
+    const int smem = 227*1024/bps-1024 < need ? need : 227*1024/bps-1024; // pads the request so that exactly bps blocks fit
+    CK(cudaFuncSetAttribute(k_tma<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(k_ldgsts<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    float t1 = timeit([&]{ k_tma<S><<<148*bps, TPB, smem>>>(buf, slot_bytes, ntiles); });
+    float t2 = timeit([&]{ k_ldgsts<S><<<148*bps, TPB, smem>>>(buf, slot_bytes, ntiles); });
+    printf("stages %d, %d blocks/SM (%2d warps, %3d KB ring/SM): TMA bulk %5.0f GB/s | cp.async+STG %5.0f GB/s\n", S, bps, bps*4, bps*S*Q*ROW/1024, bytes/t1*1e-6, bytes/t2*1e-6);
+  }
+}
+int main(){
+  const size_t cells = 512ull*512*512, slot_bytes = cells*2, ntiles = slot_bytes/ROW;
+  char* buf; CK(cudaMalloc(&buf, slot_bytes*Q)); CK(cudaMemset(buf, 0, slot_bytes*Q));
+  const double bytes = (double)slot_bytes*Q*2;
+  run<2>(buf, slot_bytes, ntiles, bytes); run<3>(buf, slot_bytes, ntiles, bytes); run<4>(buf, slot_bytes, ntiles, bytes);
+  // correctness of the in-place update: every first word was incremented once per launch, identically by both kernels
+  unsigned h[4]; CK(cudaMemcpy(h, buf, 16, cudaMemcpyDeviceToHost)); printf("check: word0=%u word1=%u (word0 = number of launches, word1 = 0)\n", h[0], h[1]);
+  return 0;
+}
