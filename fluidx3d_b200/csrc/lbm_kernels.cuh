@@ -577,8 +577,8 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_col
 
 // ================================================================================================================
 // stream_collide, bulk-copy form: the same z-marching persistent blocks, but the DDF rows move between HBM and shared memory
-// with TMA bulk copies (cp.async.bulk, completion on an mbarrier) issued by the first warp, one lane per row buffer, and the
-// results go back the same way. Measured on B200 (tools/microbench/ubench3.cu): with 8-16 warps per SM, per-thread cp.async
+// with TMA bulk copies (cp.async.bulk, completion on an mbarrier), one thread per row buffer, dealt evenly to the warps, and
+// the results go back the same way. Measured on B200 (tools/microbench/ubench3.cu): with 8-16 warps per SM, per-thread cp.async
 // loads + STG stores saturate at 5.2 TB/s however deep the ring is, bulk copies reach 6.4 TB/s. A tile row (all x of one (y,z))
 // is one contiguous segment per slot, so: one copy per (slot, tile row) in, one out; the x-shifted directions are read and
 // written at shifted positions of the periodic row buffer (no shuffles, no edge accesses). Requires the tile to span the
@@ -656,18 +656,24 @@ __global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_coll
 		}
 		return reinterpret_cast<char*>(L.fi)+((uint64_t)slot*L.slot+row(L, yr, zr))*sizeof(E);
 	};
-	auto load_tile = [&](uint32_t yb, uint32_t z, uint32_t stage) { // first warp; lane c issues copies c, c+32, ..
+	// The copies of a tile are dealt round-robin to the warps (copy c belongs to lane c/4 of warp c%4), so that no warp arrives
+	// late at the block barriers because it alone feeds the copy engine; a thread waits only for the bulk stores it issued itself,
+	// and buffer c is always loaded and stored by the same thread.
+	const uint32_t first_copy = (tid>>5)+4u*(tid&31u);
+	auto load_tile = [&](uint32_t yb, uint32_t z, uint32_t stage) { // every thread calls it
 		if(tid==0u) mbar_expect_tx(full+stage, blockDim.y*((uint32_t)Q*row_bytes+W));
-		for(uint32_t c=tid; c<ncopies; c+=32u) { uint32_t off, bytes; char* src = copy_src(c, yb, z, off, bytes); bulk_load(ring+(size_t)stage*STAGE+off, src, bytes, full+stage); }
+		for(uint32_t c=first_copy; c<ncopies; c+=128u) { uint32_t off, bytes; char* src = copy_src(c, yb, z, off, bytes); bulk_load(ring+(size_t)stage*STAGE+off, src, bytes, full+stage); }
 #if defined(FX3D_HOST_EMULATION)
-		__shfl_down_sync(0xFFFFFFFFu, 0u, 1u); // (emulation: all lanes' copies are done before lane 0 completes the phase)
+		__syncthreads(); // (emulation: copies happen at issue; the phase completes once every thread has made its copies)
 		if(tid==0u) mbar_phase_done_emulated(full+stage);
 #endif
 	};
 	auto store_tile = [&](uint32_t yb, uint32_t z, uint32_t stage) {
-		for(uint32_t c=tid; c<ncopies; c+=32u) { uint32_t off, bytes; char* dst = copy_src(c, yb, z, off, bytes); if(c%(uint32_t)(Q+1)!=(uint32_t)Q) bulk_store(dst, ring+(size_t)stage*STAGE+off, bytes); }
-		bulk_commit();
+		bool any = false;
+		for(uint32_t c=first_copy; c<ncopies; c+=128u) { uint32_t off, bytes; char* dst = copy_src(c, yb, z, off, bytes); if(c%(uint32_t)(Q+1)!=(uint32_t)Q) { bulk_store(dst, ring+(size_t)stage*STAGE+off, bytes); any = true; } }
+		if(any) bulk_commit();
 	};
+	const bool copier = first_copy<ncopies;
 
 	const uint32_t nz = R.z1-R.z0;
 	const uint64_t ntiles = (uint64_t)tiles_y*nz;
@@ -680,10 +686,8 @@ __global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_coll
 		const uint32_t zs = R.z0+zoff, ze = (uint64_t)(nz-zoff)<=tile_end-tile ? R.z1 : zs+(uint32_t)(tile_end-tile);
 		tile += ze-zs;
 		const uint32_t y = R.y0+yb*blockDim.y+threadIdx.y;
-		if(tid<32u) { // prologue: the first S-1 planes of this run
-			bulk_wait_read();
-			for(uint32_t k=0u; k<(uint32_t)(S-1); k++) if(zs+k<ze) load_tile(yb, zs+k, (it+k)%(uint32_t)S);
-		}
+		if(copier) bulk_wait_read(); // prologue: the first S-1 planes of this run
+		for(uint32_t k=0u; k<(uint32_t)(S-1); k++) if(zs+k<ze) load_tile(yb, zs+k, (it+k)%(uint32_t)S);
 		for(uint32_t z=zs; z<ze; z++, it++) {
 			const uint32_t stage = it%(uint32_t)S;
 			mbar_wait(full+stage, (it/(uint32_t)S)&1u);
@@ -700,8 +704,8 @@ __global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_coll
 			});
 			__syncthreads(); // everybody has read the stage before anybody writes results into it
 			// refill the other stage(s) now rather than at the top of the iteration: the bulk stores issued from it at the end of the
-			// previous iteration have had the stream-in to finish reading it, so the first warp rarely waits here
-			if(tid<32u && z+(uint32_t)(S-1)<ze) { bulk_wait_read(); load_tile(yb, z+(uint32_t)(S-1), (it+(uint32_t)(S-1))%(uint32_t)S); }
+			// previous iteration have had the stream-in to finish reading it, so the copying threads rarely wait here
+			if(z+(uint32_t)(S-1)<ze) { if(copier) bulk_wait_read(); load_tile(yb, z+(uint32_t)(S-1), (it+(uint32_t)(S-1))%(uint32_t)S); }
 			collide_tile<Q, COLL, ST, VF, K>(L, A, flags4, x0, y, z);
 			// ---- stream out into the same row buffers ----
 			A[0].store(reinterpret_cast<E*>(sb+tid*VB));
@@ -715,10 +719,10 @@ __global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_coll
 			});
 			fence_async_smem();
 			__syncthreads();
-			if(tid<32u) store_tile(yb, z, stage);
+			store_tile(yb, z, stage);
 		}
 	}
-	if(tid<32u) bulk_wait_all();
+	if(copier) bulk_wait_all();
 }
 
 // ================================================================================================================
