@@ -660,20 +660,44 @@ __global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_coll
 	// late at the block barriers because it alone feeds the copy engine; a thread waits only for the bulk stores it issued itself,
 	// and buffer c is always loaded and stored by the same thread.
 	const uint32_t first_copy = (tid>>5)+4u*(tid&31u);
+	// One-row tiles (blockDim.y==1, e.g. Nx=512): everything about a copy but y and z is known at compile time once the warp is
+	// known, so lane 0 of warp w issues buffers w, w+4, .. from an unrolled list with warp-uniform address arithmetic.
+	const bool one_row = blockDim.y==1u;
+	const uint32_t warp = __shfl_sync(0xFFFFFFFFu, tid>>5, 0);
+	auto copy_rows = [&](auto LOAD, uint32_t yb, uint32_t z, uint32_t stage) {
+		constexpr bool load = decltype(LOAD)::value;
+		const uint32_t y = R.y0+yb;
+		const uint32_t yv[3] = { dec(y, L.Ny), y, inc(y, L.Ny) }, zv[3] = { dec(z, L.Nz), z, inc(z, L.Nz) };
+		unsigned char* const sb = ring+(size_t)stage*STAGE;
+		auto one = [&](auto J) {
+			constexpr int j = J;
+			if constexpr(j==Q) { if constexpr(load) bulk_load(sb+(size_t)Q*SET, reinterpret_cast<char*>(L.flags)+((uint64_t)y+(uint64_t)z*L.Ny)*L.Nx, W, full+stage); }
+			else {
+				constexpr int i = j==0 ? 0 : (j&1) ? j : j-1; // odd member of the direction pair
+				constexpr uint32_t slot = j==0 ? 0u : (j&1) ? (ODD ? (uint32_t)i : (uint32_t)i+1u) : (ODD ? (uint32_t)i+1u : (uint32_t)i);
+				constexpr int ey = (j==0 || (j&1)) ? 0 : dir_y(i), ez = (j==0 || (j&1)) ? 0 : dir_z(i);
+				char* g = reinterpret_cast<char*>(L.fi)+((uint64_t)slot*L.slot+row(L, yv[ey+1], zv[ez+1]))*sizeof(E);
+				if constexpr(load) bulk_load(sb+(size_t)j*SET, g, row_bytes, full+stage); else bulk_store(g, sb+(size_t)j*SET, row_bytes);
+			}
+		};
+		if(warp==0u) static_for<0, Q+1, 4>(one); else if(warp==1u) static_for<1, Q+1, 4>(one); else if(warp==2u) static_for<2, Q+1, 4>(one); else static_for<3, Q+1, 4>(one);
+	};
 	auto load_tile = [&](uint32_t yb, uint32_t z, uint32_t stage) { // every thread calls it
 		if(tid==0u) mbar_expect_tx(full+stage, blockDim.y*((uint32_t)Q*row_bytes+W));
-		for(uint32_t c=first_copy; c<ncopies; c+=128u) { uint32_t off, bytes; char* src = copy_src(c, yb, z, off, bytes); bulk_load(ring+(size_t)stage*STAGE+off, src, bytes, full+stage); }
+		if(one_row) { if((tid&31u)==0u) copy_rows(std::true_type{}, yb, z, stage); }
+		else for(uint32_t c=first_copy; c<ncopies; c+=128u) { uint32_t off, bytes; char* src = copy_src(c, yb, z, off, bytes); bulk_load(ring+(size_t)stage*STAGE+off, src, bytes, full+stage); }
 #if defined(FX3D_HOST_EMULATION)
 		__syncthreads(); // (emulation: copies happen at issue; the phase completes once every thread has made its copies)
 		if(tid==0u) mbar_phase_done_emulated(full+stage);
 #endif
 	};
 	auto store_tile = [&](uint32_t yb, uint32_t z, uint32_t stage) {
+		if(one_row) { if((tid&31u)==0u) { copy_rows(std::false_type{}, yb, z, stage); bulk_commit(); } return; }
 		bool any = false;
 		for(uint32_t c=first_copy; c<ncopies; c+=128u) { uint32_t off, bytes; char* dst = copy_src(c, yb, z, off, bytes); if(c%(uint32_t)(Q+1)!=(uint32_t)Q) { bulk_store(dst, ring+(size_t)stage*STAGE+off, bytes); any = true; } }
 		if(any) bulk_commit();
 	};
-	const bool copier = first_copy<ncopies;
+	const bool copier = one_row ? (tid&31u)==0u : first_copy<ncopies;
 
 	const uint32_t nz = R.z1-R.z0;
 	const uint64_t ntiles = (uint64_t)tiles_y*nz;

@@ -103,6 +103,7 @@ static inline uint32_t __shfl_down_sync(unsigned, uint32_t v, unsigned d) { retu
 static inline uint32_t __shfl_up_sync(unsigned, uint32_t v, unsigned d) { return emul::exchange(v, (int)emul::tctx.lane-(int)d, emul::tctx.lane>=d); }
 static inline float __shfl_down_sync(unsigned m, float v, unsigned d) { return __uint_as_float(__shfl_down_sync(m, __float_as_uint(v), d)); }
 static inline float __shfl_up_sync(unsigned m, float v, unsigned d) { return __uint_as_float(__shfl_up_sync(m, __float_as_uint(v), d)); }
+static inline uint32_t __shfl_sync(unsigned, uint32_t v, int src) { return emul::exchange(v, src, true); }
 static inline unsigned __ballot_sync(unsigned, int p) { return emul::ballot(p); }
 static inline int __any_sync(unsigned, int p) { return emul::ballot(p)!=0u; }
 
