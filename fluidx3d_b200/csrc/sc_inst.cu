@@ -75,7 +75,8 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 	if(R.g1<=R.g0||R.y1<=R.y0||R.z1<=R.z0) return FX3D_OK;
 	if(cells_per_thread<=0) { // persistent kernels; R.g0/g1 are in groups of pipe_cells<Q,ST>() cells. 0: bulk copies where the tile spans the row, else cp.async; -1: cp.async
 		const dim3 block = block_shape(R.g1-R.g0);
-		if(cells_per_thread==0 && pipe_cells<Q, ST>()==4 && tma_eligible(L, R, block)) {
+		if(cells_per_thread==-2 && !tma_eligible(L, R, block)) return 1; // -2: bulk copies or nothing (regions in groups of 4 cells); 1 = "not eligible", no launch
+		if((cells_per_thread==-2 || (cells_per_thread==0 && pipe_cells<Q, ST>()==4)) && tma_eligible(L, R, block)) {
 			if(collision==COLL_SRT) return volume_force ? launch_tma<Q, COLL_SRT, ST, true>(L, R, block, stream, reserve) : launch_tma<Q, COLL_SRT, ST, false>(L, R, block, stream, reserve);
 			return volume_force ? launch_tma<Q, COLL_TRT, ST, true>(L, R, block, stream, reserve) : launch_tma<Q, COLL_TRT, ST, false>(L, R, block, stream, reserve);
 		}
