@@ -65,6 +65,7 @@ _SIGS = {
     "fx3d_relaxation_rate": (_F, [_F], False),
     "fx3d_bytes_per_cell_per_step": (_U32, [_LP], False),
     "fx3d_initialize": (_I, [_LP, _VP], True),
+    "fx3d_stream_collide_launches": (_I, [_I, C.POINTER(_U64)], True),
     "fx3d_set_interior_reserve": (_I, [_I], True),
     "fx3d_stream_collide": (_I, [_LP, _U64, _F, _F, _F, _I, _VP], True),
     "fx3d_update_fields": (_I, [_LP, _U64, _F, _F, _F, _VP], True),
@@ -131,6 +132,17 @@ class Lib:
         v = C.c_uint64(0)
         self.launch_count(C.byref(v))
         return v.value
+
+    KERNEL_KINDS = ("k_stream_collide_v1", "k_stream_collide_vec", "k_stream_collide_pipe", "k_stream_collide_tma", "k_stream_collide_tma_seg")
+
+    def kernel_kind_counts(self):
+        """stream_collide launches so far per kernel kind (same order as KERNEL_KINDS)"""
+        out = []
+        for k in range(5):
+            v = C.c_uint64(0)
+            self.stream_collide_launches(k, C.byref(v))
+            out.append(v.value)
+        return out
 
 
 _default = None

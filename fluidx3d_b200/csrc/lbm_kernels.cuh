@@ -79,6 +79,8 @@ template<> struct Pack<ST_FP32, 4> {
 	FX3D_HD uint32_t first_bits() const { return __float_as_uint(f2_lo(p[0])); }
 	FX3D_HD uint32_t last_bits() const { return __float_as_uint(f2_hi(p[1])); }
 	// my 4 elements belong at positions x+1..x+4 (up) / x-1..x+2 (down) of a periodic row of W elements (x a multiple of 4)
+	FX3D_HD void store_seg_up(float* row, uint32_t x) const { row[x+1u] = f2_lo(p[0]); *reinterpret_cast<unsigned long long*>(row+x+2u) = bits64(make_f2(f2_hi(p[0]), f2_lo(p[1]))); row[x+4u] = f2_hi(p[1]); } // positions x+1..x+4 of a padded segment buffer
+	FX3D_HD void store_seg_down(float* row, uint32_t x) const { *(row+x-1) = f2_lo(p[0]); *reinterpret_cast<unsigned long long*>(row+x) = bits64(make_f2(f2_hi(p[0]), f2_lo(p[1]))); row[x+2u] = f2_hi(p[1]); } // positions x-1..x+2
 	FX3D_HD void store_row_up(float* row, uint32_t x, uint32_t W) const { row[x+1u] = f2_lo(p[0]); *reinterpret_cast<unsigned long long*>(row+x+2u) = bits64(make_f2(f2_hi(p[0]), f2_lo(p[1]))); row[x+4u==W ? 0u : x+4u] = f2_hi(p[1]); }
 	FX3D_HD void store_row_down(float* row, uint32_t x, uint32_t W) const { row[x==0u ? W-1u : x-1u] = f2_lo(p[0]); *reinterpret_cast<unsigned long long*>(row+x) = bits64(make_f2(f2_hi(p[0]), f2_lo(p[1]))); row[x+2u] = f2_hi(p[1]); }
 	FX3D_HD void push_back(uint32_t b) { p[0] = make_f2(f2_hi(p[0]), f2_lo(p[1])); p[1] = make_f2(f2_hi(p[1]), __uint_as_float(b)); }  // {e1,e2,e3,b}
@@ -122,6 +124,8 @@ template<int ST> struct Pack<ST, 4> {
 	FX3D_HD void store_head(uint16_t* q) const { *reinterpret_cast<uint32_t*>(q) = r[0]; q[2] = (uint16_t)(r[1]&0xFFFFu); }
 	FX3D_HD uint32_t first_bits() const { return r[0]&0xFFFFu; }
 	FX3D_HD uint32_t last_bits() const { return r[1]>>16; }
+	FX3D_HD void store_seg_up(uint16_t* row, uint32_t x) const { row[x+1u] = (uint16_t)r[0]; *reinterpret_cast<uint32_t*>(row+x+2u) = (r[0]>>16)|(r[1]<<16); row[x+4u] = (uint16_t)(r[1]>>16); }
+	FX3D_HD void store_seg_down(uint16_t* row, uint32_t x) const { *(row+x-1) = (uint16_t)r[0]; *reinterpret_cast<uint32_t*>(row+x) = (r[0]>>16)|(r[1]<<16); row[x+2u] = (uint16_t)(r[1]>>16); }
 	FX3D_HD void store_row_up(uint16_t* row, uint32_t x, uint32_t W) const { row[x+1u] = (uint16_t)r[0]; *reinterpret_cast<uint32_t*>(row+x+2u) = (r[0]>>16)|(r[1]<<16); row[x+4u==W ? 0u : x+4u] = (uint16_t)(r[1]>>16); }
 	FX3D_HD void store_row_down(uint16_t* row, uint32_t x, uint32_t W) const { row[x==0u ? W-1u : x-1u] = (uint16_t)r[0]; *reinterpret_cast<uint32_t*>(row+x) = (r[0]>>16)|(r[1]<<16); row[x+2u] = (uint16_t)(r[1]>>16); }
 	FX3D_HD void push_back(uint32_t b) { r[0] = (r[0]>>16)|(r[1]<<16); r[1] = (r[1]>>16)|(b<<16); }
@@ -591,7 +595,7 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_col
 #endif
 // direction components for a run-time direction index, from 2-bit fields of a constant (no table in memory)
 FX3D_HDC constexpr unsigned long long pack_dirs(int axis) { unsigned long long m = 0ull; for(int i=0; i<27; i++) m |= (unsigned long long)(dir_c(axis, i)+1)<<(2*i); return m; }
-FX3D_HD int dir_rt(int axis, uint32_t i) { constexpr unsigned long long my = pack_dirs(1), mz = pack_dirs(2); return (int)(((axis==1 ? my : mz)>>(2u*i))&3ull)-1; }
+FX3D_HD int dir_rt(int axis, uint32_t i) { constexpr unsigned long long mx = pack_dirs(0), my = pack_dirs(1), mz = pack_dirs(2); return (int)(((axis==0 ? mx : axis==1 ? my : mz)>>(2u*i))&3ull)-1; }
 template<int Q, int ST> FX3D_HDC constexpr uint32_t tma_stage_bytes() { return (uint32_t)Q*128u*4u*(ST==ST_FP32 ? 4u : 2u)+128u*4u; } // Q row-buffer sets + flag bytes
 template<int Q, int ST> FX3D_HDC constexpr int tma_blocks_per_sm() { return ST==ST_FP32 ? 2 : Q>19 ? 3 : 4; } // by shared memory; also the register cap
 template<int Q, int ST> FX3D_HDC constexpr uint32_t tma_smem_bytes() { return 128u+(uint32_t)FX3D_TMA_STAGES*tma_stage_bytes<Q, ST>(); }
@@ -744,6 +748,212 @@ __global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_coll
 			fence_async_smem();
 			__syncthreads();
 			store_tile(yb, z, stage);
+		}
+	}
+	if(copier) bulk_wait_all();
+}
+
+// ---- bulk-copy form for tiles that are a segment of a longer row, and for rows with x halos ----
+// Same pipeline as k_stream_collide_tma; what changes is the row ends. A slot buffer whose direction has an x component holds
+// elements that other tiles own: of the positions a tile writes for ex>0 (x+1 .. x+W) the first 16-byte chunk of its segment
+// contains the left neighbour's element, and its own last element lies one past the segment (mirrored for ex<0). So every row
+// buffer has a 16-byte pad on either side: the pad on the side the direction reaches into is loaded along with the segment
+// (one longer copy; a separate 16-byte copy where the row wraps periodically), threads read and write at shifted positions
+// without any wrap logic, the bulk store covers the fully owned chunks only, and the remaining <= 16/sizeof(E) owned elements per
+// shifted buffer are written by single threads with plain stores. Flags are read per thread (their rows are not 16-byte aligned).
+template<int Q, int ST> FX3D_HDC constexpr uint32_t tmaseg_set_bytes() { return 128u*4u*(ST==ST_FP32 ? 4u : 2u)+4u*32u; } // up to 4 tile rows, each padded by 2x16 bytes
+template<int Q, int ST> FX3D_HDC constexpr uint32_t tmaseg_smem_bytes() { return 128u+(uint32_t)FX3D_TMA_STAGES*(uint32_t)Q*tmaseg_set_bytes<Q, ST>(); }
+template<int Q> FX3D_HDC constexpr unsigned long long pack_x_dirs() { unsigned long long m = 0ull; int n = 0; for(int i=1; i<Q; i+=2) if(dir_x(i)!=0) { m |= (unsigned long long)i<<(5*n); n++; } return m; } // the odd directions with an x component, 5 bits each
+
+template<int Q, int COLL, int ST, bool VF, int ODD>
+__global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_collide_tma_seg(const Lattice L, const Region R, const uint32_t tiles_x, const uint32_t tiles_y) {
+	constexpr int K = 4, S = FX3D_TMA_STAGES, NXD = x_dirs<Q>();
+	constexpr uint32_t odd = (uint32_t)ODD;
+	typedef Codec<ST> C;
+	typedef typename C::elem_t E;
+	typedef Pack<ST, K> P;
+	constexpr uint32_t VB = (uint32_t)(sizeof(E)*K), PAD = 16u, CH = PAD/(uint32_t)sizeof(E), SET = tmaseg_set_bytes<Q, ST>(), STAGE = (uint32_t)Q*SET;
+	unsigned char* const smem = dynamic_smem();
+	uint64_t* const full = reinterpret_cast<uint64_t*>(smem);
+	unsigned char* const ring = smem+128;
+	const uint32_t tid = threadIdx.x+threadIdx.y*blockDim.x;
+	const uint32_t W = blockDim.x*(uint32_t)K, row_bytes = blockDim.x*VB, ROWB = row_bytes+2u*PAD; // a row buffer: [pad | W elements | pad]
+	const uint32_t nbuf = (uint32_t)Q*blockDim.y, nfix = (uint32_t)NXD*blockDim.y*CH;
+	if(tid==0u) { for(int s=0; s<S; s++) mbar_init(full+s); }
+	fence_async_smem();
+	__syncthreads();
+
+	// buffer c = ty*Q+j of the tile at (X0, rows R.y0+yb*by.., plane z): global address of the segment start, x shift of its direction
+	auto buffer_row = [&](uint32_t c, uint32_t X0, uint32_t yb, uint32_t z, uint32_t& smem_off, int& ex) -> char* {
+		const uint32_t ty = c/(uint32_t)Q, j = c%(uint32_t)Q, y = R.y0+yb*blockDim.y+ty;
+		smem_off = j*SET+ty*ROWB;
+		uint32_t slot = j, yr = y, zr = z;
+		ex = 0;
+		if(j>0u) {
+			const uint32_t i = (j&1u) ? j : j-1u;
+			if(j&1u) slot = odd ? i : i+1u;
+			else { slot = odd ? i+1u : i; yr = step_rt(dir_rt(1, i), y, L.Ny); zr = step_rt(dir_rt(2, i), z, L.Nz); ex = dir_rt(0, i); }
+		}
+		return reinterpret_cast<char*>(L.fi)+((uint64_t)slot*L.slot+row(L, yr, zr)+(uint64_t)(X0+L.xo))*sizeof(E);
+	};
+	const uint32_t first_copy = (tid>>5)+4u*(tid&31u);
+	// One-row tiles (blockDim.y==1, i.e. segments of 512 cells): lane 0 of warp w issues buffers w, w+4, .. from an unrolled list
+	// in which everything but X0, y and z is a compile-time constant; the end-chunk elements are stored by threads n*CH+k.
+	const bool one_row = blockDim.y==1u;
+	const uint32_t warp = __shfl_sync(0xFFFFFFFFu, tid>>5, 0);
+	const bool copier = one_row ? (tid&31u)==0u : first_copy<nbuf;
+	auto row_ptr = [&](auto J, uint32_t X0, uint32_t y, uint32_t z) -> char* { // segment start of buffer J (compile time) in row y of plane z
+		constexpr int j = decltype(J)::value;
+		constexpr int i = j==0 ? 0 : (j&1) ? j : j-1;
+		constexpr uint32_t slot = j==0 ? 0u : (j&1) ? (ODD ? (uint32_t)i : (uint32_t)i+1u) : (ODD ? (uint32_t)i+1u : (uint32_t)i);
+		constexpr int ey = (j==0 || (j&1)) ? 0 : dir_y(i), ez = (j==0 || (j&1)) ? 0 : dir_z(i);
+		return reinterpret_cast<char*>(L.fi)+((uint64_t)slot*L.slot+row(L, step<ey>(y, L.Ny), step<ez>(z, L.Nz))+(uint64_t)(X0+L.xo))*sizeof(E);
+	};
+	auto copy_rows = [&](auto LOAD, uint32_t X0, uint32_t yb, uint32_t z, uint32_t stage) {
+		constexpr bool load = decltype(LOAD)::value;
+		const uint32_t y = R.y0+yb;
+		unsigned char* const sb = ring+(size_t)stage*STAGE;
+		auto one = [&](auto J) {
+			constexpr int j = J;
+			constexpr int ex = (j==0 || (j&1)) ? 0 : dir_x(j-1);
+			char* g = row_ptr(J, X0, y, z);
+			unsigned char* b = sb+(size_t)j*SET;
+			if constexpr(load) {
+				if constexpr(ex>0) {
+					if(X0+W<L.Nx) bulk_load(b+PAD, g, row_bytes+PAD, full+stage);
+					else { bulk_load(b+PAD, g, row_bytes, full+stage); bulk_load(b+PAD+row_bytes, g-(size_t)X0*sizeof(E), PAD, full+stage); }
+				} else if constexpr(ex<0) {
+					if(X0>0u) bulk_load(b, g-PAD, row_bytes+PAD, full+stage);
+					else { bulk_load(b+PAD, g, row_bytes, full+stage); bulk_load(b, g+(size_t)(L.Nx-CH)*sizeof(E), PAD, full+stage); }
+				} else bulk_load(b+PAD, g, row_bytes, full+stage);
+			} else {
+				if constexpr(ex>0) bulk_store(g+PAD, b+2u*PAD, row_bytes-PAD); else if constexpr(ex<0) bulk_store(g, b+PAD, row_bytes-PAD); else bulk_store(g, b+PAD, row_bytes);
+			}
+		};
+		if(warp==0u) static_for<0, Q, 4>(one); else if(warp==1u) static_for<1, Q, 4>(one); else if(warp==2u) static_for<2, Q, 4>(one); else static_for<3, Q, 4>(one);
+	};
+	auto fix_rows = [&](uint32_t X0, uint32_t yb, uint32_t z, uint32_t stage) { // one-row tiles: thread n*CH+k stores end-chunk element k of the n-th shifted buffer
+		const uint32_t y = R.y0+yb, k = tid%CH;
+		int n = 0;
+		static_for<1, Q, 2>([&](auto I) {
+			constexpr int i = I;
+			if constexpr(dir_x(i)!=0) {
+				if(tid/CH==(uint32_t)n) {
+					char* g = row_ptr(std::integral_constant<int, i+1>{}, X0, y, z);
+					const E* seg = reinterpret_cast<const E*>(ring+(size_t)stage*STAGE+(size_t)(i+1)*SET+PAD);
+					const int pos = dir_x(i)>0 ? (k+1u<CH ? (int)k+1 : (int)W) : (k==0u ? -1 : (int)(W-CH+k-1u));
+					int64_t gp = pos;
+					if(pos<0 && X0==0u) gp = (int64_t)L.Nx-1; else if(pos>=(int)W && X0+W>=L.Nx) gp = -(int64_t)X0;
+					reinterpret_cast<E*>(g)[gp] = seg[pos];
+				}
+				n++;
+			}
+		});
+	};
+	auto load_tile = [&](uint32_t X0, uint32_t yb, uint32_t z, uint32_t stage) {
+		if(tid==0u) mbar_expect_tx(full+stage, blockDim.y*((uint32_t)Q*row_bytes+(uint32_t)NXD*PAD));
+		if(one_row) { if((tid&31u)==0u) copy_rows(std::true_type{}, X0, yb, z, stage); }
+		else for(uint32_t c=first_copy; c<nbuf; c+=128u) {
+			uint32_t off; int ex;
+			char* g = buffer_row(c, X0, yb, z, off, ex);
+			unsigned char* b = ring+(size_t)stage*STAGE+off;
+			if(ex>0) { // segment + the element one past it
+				if(X0+W<L.Nx) bulk_load(b+PAD, g, row_bytes+PAD, full+stage);
+				else { bulk_load(b+PAD, g, row_bytes, full+stage); bulk_load(b+PAD+row_bytes, g-(size_t)X0*sizeof(E), PAD, full+stage); } // periodic: the row's first chunk
+			} else if(ex<0) { // the element before the segment + segment
+				if(X0>0u) bulk_load(b, g-PAD, row_bytes+PAD, full+stage);
+				else { bulk_load(b+PAD, g, row_bytes, full+stage); bulk_load(b, g+(size_t)(L.Nx-CH)*sizeof(E), PAD, full+stage); } // periodic: the row's last chunk
+			} else bulk_load(b+PAD, g, row_bytes, full+stage);
+		}
+#if defined(FX3D_HOST_EMULATION)
+		__syncthreads();
+		if(tid==0u) mbar_phase_done_emulated(full+stage);
+#endif
+	};
+	auto store_tile = [&](uint32_t X0, uint32_t yb, uint32_t z, uint32_t stage) {
+		if(one_row) {
+			if((tid&31u)==0u) { copy_rows(std::false_type{}, X0, yb, z, stage); bulk_commit(); }
+			if(tid<(uint32_t)NXD*CH) fix_rows(X0, yb, z, stage);
+			return;
+		}
+		for(uint32_t c=first_copy; c<nbuf; c+=128u) { // the fully owned 16-byte chunks, in bulk
+			uint32_t off; int ex;
+			char* g = buffer_row(c, X0, yb, z, off, ex);
+			unsigned char* b = ring+(size_t)stage*STAGE+off+PAD;
+			if(ex>0) bulk_store(g+PAD, b+PAD, row_bytes-PAD); else if(ex<0) bulk_store(g, b, row_bytes-PAD); else bulk_store(g, b, row_bytes);
+		}
+		if(copier) bulk_commit();
+		for(uint32_t f=tid; f<nfix; f+=128u) { // the owned elements of the two end chunks, one by one
+			const uint32_t k = f%CH, ty = (f/CH)%blockDim.y, n = f/(CH*blockDim.y);
+			const uint32_t i = (uint32_t)((pack_x_dirs<Q>()>>(5u*n))&31ull);
+			uint32_t off; int ex;
+			char* g = buffer_row(ty*(uint32_t)Q+i+1u, X0, yb, z, off, ex);
+			const E* seg = reinterpret_cast<const E*>(ring+(size_t)stage*STAGE+off+PAD);
+			// ex>0: positions 1..CH-1 and W; ex<0: positions -1 and W-CH..W-2 (position p of the segment is cell X0+p)
+			const int pos = ex>0 ? (k+1u<CH ? (int)k+1 : (int)W) : (k==0u ? -1 : (int)(W-CH+k-1u));
+			int64_t gp = pos;
+			if(pos<0 && X0==0u) gp = (int64_t)L.Nx-1; else if(pos>=(int)W && X0+W>=L.Nx) gp = -(int64_t)X0; // periodic wrap inside the row
+			reinterpret_cast<E*>(g)[gp] = seg[pos];
+		}
+	};
+
+	const uint32_t nz = R.z1-R.z0;
+	const uint64_t ntiles = (uint64_t)tiles_x*tiles_y*nz;
+	uint64_t tile = ntiles*blockIdx.x/gridDim.x;
+	const uint64_t tile_end = ntiles*(blockIdx.x+1u)/gridDim.x;
+	uint32_t it = 0u;
+	const uint32_t x0 = (uint32_t)K*threadIdx.x; // my first cell within the segment
+	while(tile<tile_end) {
+		const uint32_t col = (uint32_t)(tile/nz), zoff = (uint32_t)(tile%nz), xb = col%tiles_x, yb = col/tiles_x;
+		const uint32_t zs = R.z0+zoff, ze = (uint64_t)(nz-zoff)<=tile_end-tile ? R.z1 : zs+(uint32_t)(tile_end-tile);
+		tile += ze-zs;
+		const uint32_t X0 = L.Hx+(R.g0+xb*blockDim.x)*(uint32_t)K, y = R.y0+yb*blockDim.y+threadIdx.y;
+		const uint8_t* const my_flags = L.flags+((uint64_t)(X0+x0)+(uint64_t)y*L.Nx);
+		const uint64_t flag_plane = (uint64_t)L.Nx*L.Ny;
+		// my 4 flag bytes come from two aligned words; the words of the next plane are requested a whole tile ahead and only
+		// combined when they are needed (combining at the load would wait for them on the spot)
+		uint32_t fw0, fw1;
+		auto request_flags = [&](uint32_t z) {
+			const uintptr_t a = reinterpret_cast<uintptr_t>(my_flags+(uint64_t)z*flag_plane);
+			fw0 = *reinterpret_cast<const uint32_t*>(a&~(uintptr_t)3u);
+			fw1 = (a&3u) ? *reinterpret_cast<const uint32_t*>((a&~(uintptr_t)3u)+4u) : 0u;
+		};
+		auto combine_flags = [&](uint32_t z) -> uint32_t {
+			const uint32_t sh = 8u*(uint32_t)(reinterpret_cast<uintptr_t>(my_flags+(uint64_t)z*flag_plane)&3u);
+			return sh==0u ? fw0 : (fw0>>sh)|(fw1<<(32u-sh));
+		};
+		if(copier) bulk_wait_read();
+		for(uint32_t k=0u; k<(uint32_t)(S-1); k++) if(zs+k<ze) load_tile(X0, yb, zs+k, (it+k)%(uint32_t)S);
+		request_flags(zs);
+		for(uint32_t z=zs; z<ze; z++, it++) {
+			const uint32_t stage = it%(uint32_t)S;
+			const uint32_t flags4 = combine_flags(z);
+			mbar_wait(full+stage, (it/(uint32_t)S)&1u);
+			unsigned char* const sb = ring+(size_t)stage*STAGE+threadIdx.y*ROWB+PAD;
+			P A[Q];
+			static_for<0, Q, 1>([&](auto I) { A[I].load(reinterpret_cast<const E*>(sb+(size_t)I.value*SET)+x0); });
+			static_for<1, Q, 2>([&](auto I) {
+				constexpr int i = I;
+				const E* rowp = reinterpret_cast<const E*>(sb+(size_t)(i+1)*SET);
+				if constexpr(dir_x(i)>0) A[i+1].push_back(P::bits(rowp[x0+(uint32_t)K]));
+				else if constexpr(dir_x(i)<0) A[i+1].push_front(P::bits(*(rowp+x0-1)));
+			});
+			__syncthreads();
+			if(z+(uint32_t)(S-1)<ze) { if(copier) bulk_wait_read(); load_tile(X0, yb, z+(uint32_t)(S-1), (it+(uint32_t)(S-1))%(uint32_t)S); }
+			if(z+1u<ze) request_flags(z+1u);
+			collide_tile<Q, COLL, ST, VF, K>(L, A, flags4, X0+x0, y, z);
+			A[0].store(reinterpret_cast<E*>(sb)+x0);
+			static_for<1, Q, 2>([&](auto I) {
+				constexpr int i = I;
+				A[i].store(reinterpret_cast<E*>(sb+(size_t)i*SET)+x0);
+				E* rowp = reinterpret_cast<E*>(sb+(size_t)(i+1)*SET);
+				if constexpr(dir_x(i)==0) A[i+1].store(rowp+x0);
+				else if constexpr(dir_x(i)>0) A[i+1].store_seg_up(rowp, x0);
+				else A[i+1].store_seg_down(rowp, x0);
+			});
+			fence_async_smem();
+			__syncthreads();
+			store_tile(X0, yb, z, stage);
 		}
 	}
 	if(copier) bulk_wait_all();

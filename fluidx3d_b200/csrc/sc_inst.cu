@@ -33,6 +33,7 @@ template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_pipe_parit
 	if((uint64_t)tiles_x*tiles_y>0xFFFFFFFFull) { set_error("region has too many tile columns"); return FX3D_ERR_INVALID; }
 	if(ntiles==0ull) return FX3D_OK;
 	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, blocks), 1u, 1u); // every block takes an equal contiguous share of the tiles
+	g_kind_launches[2]++;
 	FX3D_LAUNCH_SMEM((k_stream_collide_pipe<Q, COLL, ST, VF, ODD>), grid, block, smem, stream, L, R, tiles_x, tiles_y);
 	return check_launch("stream_collide (pipelined)");
 }
@@ -64,8 +65,45 @@ template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_tma_parity
 	const uint64_t all_blocks = (uint64_t)sms*(uint64_t)per_sm, blocks = all_blocks>2ull*(uint64_t)std::max(reserve, 0) ? all_blocks-(uint64_t)std::max(reserve, 0) : all_blocks, ntiles = (uint64_t)tiles_y*nz;
 	if(ntiles==0ull) return FX3D_OK;
 	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, blocks), 1u, 1u);
+	g_kind_launches[3]++;
 	FX3D_LAUNCH_SMEM((k_stream_collide_tma<Q, COLL, ST, VF, ODD>), grid, block, smem, stream, L, R, tiles_y);
 	return check_launch("stream_collide (bulk copies)");
+}
+// segment form: tiles are full 4*block.x-cell segments of longer rows, or rows with x halos
+template<int Q, int ST> static bool tmaseg_eligible(const Lattice& L, const Region& R, const dim3& block) {
+	const uint32_t esz = ST==ST_FP32 ? 4u : 2u, groups = R.g1-R.g0;
+	if((uint64_t)tmaseg_smem_bytes<Q, ST>()*tma_blocks_per_sm<Q, ST>()+2048u>227u*1024u) return false; // D3Q27 FP32
+	if(block.x*block.y!=128u || block.y>4u || groups%block.x!=0u || (R.y1-R.y0)%block.y!=0u || block.x*4u*esz<32u) return false;
+	if(((uint64_t)(L.Hx+R.g0*4u+L.xo)*esz)%16u!=0u) return false; // segment starts on a 16-byte boundary of its row
+	if(L.Hx==0u && (L.Nx*esz)%16u!=0u) return false;               // so does the periodic wrap chunk
+	return true;
+}
+template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_tmaseg_parity(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
+	const uint32_t tiles_x = (R.g1-R.g0)/block.x, tiles_y = (R.y1-R.y0)/block.y, nz = R.z1-R.z0;
+	constexpr uint32_t smem = tmaseg_smem_bytes<Q, ST>();
+	int sms = 148, per_sm = tma_blocks_per_sm<Q, ST>();
+#if !defined(FX3D_HOST_EMULATION)
+	static std::atomic<uint64_t> configured{0ull};
+	int dev = 0; cudaGetDevice(&dev);
+	if(dev>=64 || !((configured.load()>>dev)&1ull)) {
+		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_tma_seg<Q, COLL, ST, VF, ODD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if(e!=cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stream_collide_tma_seg)");
+		if(dev<64) configured.fetch_or(1ull<<dev);
+	}
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#else
+	sms = 2; per_sm = 1;
+#endif
+	const uint64_t all_blocks = (uint64_t)sms*(uint64_t)per_sm, blocks = all_blocks>2ull*(uint64_t)std::max(reserve, 0) ? all_blocks-(uint64_t)std::max(reserve, 0) : all_blocks, ntiles = (uint64_t)tiles_x*tiles_y*nz;
+	if(ntiles==0ull) return FX3D_OK;
+	if((uint64_t)tiles_x*tiles_y>0xFFFFFFFFull) { set_error("region has too many tile columns"); return FX3D_ERR_INVALID; }
+	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, blocks), 1u, 1u);
+	g_kind_launches[4]++;
+	FX3D_LAUNCH_SMEM((k_stream_collide_tma_seg<Q, COLL, ST, VF, ODD>), grid, block, smem, stream, L, R, tiles_x, tiles_y);
+	return check_launch("stream_collide (bulk copies, row segments)");
+}
+template<int Q, int COLL, int ST, bool VF> static int launch_tmaseg(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
+	return L.odd ? launch_tmaseg_parity<Q, COLL, ST, VF, 1>(L, R, block, stream, reserve) : launch_tmaseg_parity<Q, COLL, ST, VF, 0>(L, R, block, stream, reserve);
 }
 template<int Q, int COLL, int ST, bool VF> static int launch_tma(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
 	return L.odd ? launch_tma_parity<Q, COLL, ST, VF, 1>(L, R, block, stream, reserve) : launch_tma_parity<Q, COLL, ST, VF, 0>(L, R, block, stream, reserve);
@@ -75,8 +113,14 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 	if(R.g1<=R.g0||R.y1<=R.y0||R.z1<=R.z0) return FX3D_OK;
 	if(cells_per_thread<=0) { // persistent kernels; R.g0/g1 are in groups of pipe_cells<Q,ST>() cells. 0: bulk copies where the tile spans the row, else cp.async; -1: cp.async
 		const dim3 block = block_shape(R.g1-R.g0);
+		// row segments / x halos: measured on B200 the bulk-copy form wins for FP32 (+8 %) but not for 16-bit storage (issue-bound: -3 %), so
+		// the automatic choice takes it for FP32 only; variant 16 (-3) takes it wherever it is eligible
+		if((cells_per_thread==-3 || (cells_per_thread==0 && ST==ST_FP32)) && pipe_cells<Q, ST>()==4 && !tma_eligible(L, R, block) && tmaseg_eligible<Q, ST>(L, R, block)) {
+			if(collision==COLL_SRT) return volume_force ? launch_tmaseg<Q, COLL_SRT, ST, true>(L, R, block, stream, reserve) : launch_tmaseg<Q, COLL_SRT, ST, false>(L, R, block, stream, reserve);
+			return volume_force ? launch_tmaseg<Q, COLL_TRT, ST, true>(L, R, block, stream, reserve) : launch_tmaseg<Q, COLL_TRT, ST, false>(L, R, block, stream, reserve);
+		}
 		if(cells_per_thread==-2 && !tma_eligible(L, R, block)) return 1; // -2: bulk copies or nothing (regions in groups of 4 cells); 1 = "not eligible", no launch
-		if((cells_per_thread==-2 || (cells_per_thread==0 && pipe_cells<Q, ST>()==4)) && tma_eligible(L, R, block)) {
+		if((cells_per_thread==-2 || ((cells_per_thread==0 || cells_per_thread==-3) && pipe_cells<Q, ST>()==4)) && tma_eligible(L, R, block)) {
 			if(collision==COLL_SRT) return volume_force ? launch_tma<Q, COLL_SRT, ST, true>(L, R, block, stream, reserve) : launch_tma<Q, COLL_SRT, ST, false>(L, R, block, stream, reserve);
 			return volume_force ? launch_tma<Q, COLL_TRT, ST, true>(L, R, block, stream, reserve) : launch_tma<Q, COLL_TRT, ST, false>(L, R, block, stream, reserve);
 		}
@@ -90,6 +134,7 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 #define FX3D_SC_ALL(MACRO, ARG) \
 	if(collision==COLL_SRT) { if(volume_force) MACRO(ARG, COLL_SRT, true); else MACRO(ARG, COLL_SRT, false); } \
 	else                    { if(volume_force) MACRO(ARG, COLL_TRT, true); else MACRO(ARG, COLL_TRT, false); }
+	g_kind_launches[cells_per_thread>1 ? 1 : 0]++;
 	if(cells_per_thread==4) { FX3D_SC_ALL(FX3D_SCV, 4) }
 	else if(cells_per_thread==2) { FX3D_SC_ALL(FX3D_SCV, 2) }
 	else { FX3D_SC_ALL(FX3D_SC, k_stream_collide_v1) }

@@ -111,6 +111,9 @@ int fx3d_set_kernel_variant(int variant);
 /* FX3D_REGION_INTERIOR launches of the persistent kernel leave this many resident-block slots free, so that the halo exchange
  * kernels enqueued on another stream find room beside it (default 8; 0 = occupy every slot) */
 int fx3d_set_interior_reserve(int blocks);
+/* stream_collide launches so far by kernel kind: 0 general (1 cell/thread), 1 vector (2/4 cells/thread), 2 persistent with a
+ * cp.async ring, 3 persistent with bulk copies of whole rows, 4 persistent with bulk copies of row segments */
+int fx3d_stream_collide_launches(int kind, uint64_t* launches);
 int fx3d_launch_count(uint64_t* launches);                            /* kernels launched by this library so far */
 
 /* halo transfer through linear buffers, layout and semantics of transfer_extract_fi / transfer__insert_fi and

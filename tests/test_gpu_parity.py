@@ -78,6 +78,26 @@ def test_fields_bit_exact_medium_100_steps(fx, v, variant):
             assert np.array_equal(bits(a), bits(b)), dims
 
 
+SEG_CASES = [((19, SRT, FP16S, 0), (1024, 4, 3), (1, 1, 1)), ((19, SRT, FP16S, 0), (256, 8, 6), (2, 1, 1)), ((19, TRT, FP32, 3), (256, 8, 4), (2, 2, 1)),
+             ((27, SRT, FP16C, 2), (1024, 2, 2), (1, 1, 1)), ((19, SRT, FP32, 1), (2048, 3, 2), (1, 1, 2)), ((27, TRT, FP16S, 3), (512, 8, 2), (4, 2, 1)),
+             ((19, SRT, FP16C, 0), (1024, 8, 8), (2, 2, 2))]
+
+
+@pytest.mark.parametrize("v,dims,D", SEG_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in SEG_CASES])
+def test_bulk_copy_segment_kernel_bit_exact(fx, v, dims, D):
+    """rows longer than one tile (periodic wrap across tiles) and x-decomposed domains (halo cells at the row ends) take the
+    segment form of the bulk-copy kernel; it must be the kernel that ran, and every field must match the oracle bit for bit"""
+    from fluidx3d_b200 import capi
+    f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
+    before = capi.lib().kernel_kind_counts()
+    for steps in (1, 2, 7):
+        got, want = product(fx, v, dims, D, steps, f, 16), oracle(v, dims, D, steps, f)
+        for a, b in zip(got, want):
+            assert np.array_equal(bits(a), bits(b)), steps
+    after = capi.lib().kernel_kind_counts()
+    assert after[4] > before[4] and after[:3] == before[:3]
+
+
 @pytest.mark.parametrize("D", [(2, 1, 1), (1, 2, 1), (1, 1, 2), (2, 2, 1), (2, 2, 2), (4, 1, 2)], ids=lambda d: "d" + "".join(map(str, d)))
 @pytest.mark.parametrize("v", [(19, SRT, FP32, 0), (19, SRT, FP16C, 0), (27, TRT, FP16S, 3)], ids=["fp32", "fp16c", "q27trt16s"])
 def test_decomposed_domains_bit_identical_to_single(fx, v, D):

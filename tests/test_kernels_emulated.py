@@ -71,10 +71,31 @@ def test_emulated_bulk_copy_kernel_matches_oracle(emul, v, dims, D):
     """the bulk-copy (TMA) form of stream_collide on grids where it is eligible (tile = whole rows): row buffers in shared
     memory, shifted reads/writes of the periodic row, stage recycling, two block barriers per tile"""
     f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
+    before = emul.kernel_kind_counts()
     for steps in (1, 2, 5):
         got, want = product(emul, v, dims, D, steps, f, 16), oracle(v, dims, D, steps, f)
         for a, b in zip(got, want):
             assert np.array_equal(bits(a), bits(b))
+    after = emul.kernel_kind_counts()
+    assert after[3] > before[3] and after[:3] == before[:3], "the whole-row bulk-copy kernel must be the one that ran"
+
+
+SEG_CASES = [((19, SRT, FP16S, 0), (1024, 2, 2), (1, 1, 1)), ((19, SRT, FP16S, 0), (256, 4, 3), (2, 1, 1)), ((19, TRT, FP16S, 3), (1024, 2, 2), (2, 1, 1)), ((19, TRT, FP32, 3), (256, 8, 4), (2, 2, 1)),
+             ((27, SRT, FP16C, 2), (1024, 2, 2), (1, 1, 1)), ((19, SRT, FP32, 1), (1024, 3, 2), (1, 1, 2)), ((27, TRT, FP16S, 3), (512, 8, 2), (4, 2, 1))]
+
+
+@pytest.mark.parametrize("v,dims,D", SEG_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in SEG_CASES])
+def test_emulated_bulk_copy_segments_match_oracle(emul, v, dims, D):
+    """the bulk-copy kernel on tiles that are segments of longer rows (periodic wrap across tiles) and on x-decomposed domains
+    (halo cells at the row ends): padded row buffers, partial bulk stores, single-element stores for the end chunks"""
+    f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
+    before = emul.kernel_kind_counts()
+    for steps in (1, 2, 5):
+        got, want = product(emul, v, dims, D, steps, f, 16), oracle(v, dims, D, steps, f)
+        for a, b in zip(got, want):
+            assert np.array_equal(bits(a), bits(b))
+    after = emul.kernel_kind_counts()
+    assert after[4] > before[4] and after[:3] == before[:3], "the segment bulk-copy kernel must be the one that ran"
 
 
 @pytest.mark.parametrize("variant", [1, 4, 8], ids=["general", "vector4", "pipelined"])
