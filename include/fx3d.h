@@ -105,8 +105,10 @@ int fx3d_stream_collide(const fx3d_lattice* lattice, uint64_t t, float fx, float
 int fx3d_update_fields(const fx3d_lattice* lattice, uint64_t t, float fx, float fy, float fz, fx3d_stream stream);
 /* n consecutive stream_collide steps t0..t0+n-1 of a single (non-decomposed) domain, no host work in between */
 int fx3d_run_steps(const fx3d_lattice* lattice, uint64_t t0, uint64_t steps, float fx, float fy, float fz, fx3d_stream stream);
-/* kernel choice for tests and profiling: 0 library default, 1 general one-cell-per-thread kernel, 2 or 4 vector kernel with
- * that many cells per thread (falls back when the row length does not divide) */
+/* kernel choice for tests and profiling: 0 library default (persistent kernels: TMA bulk copies where the tile spans whole rows,
+ * or -- FP32 -- row segments; else a cp.async ring), 1 general one-cell-per-thread kernel, 2 or 4 vector kernel with that many
+ * cells per thread (falls back when the row length does not divide), 8 persistent kernel with the cp.async ring only,
+ * 16 persistent kernel with bulk copies wherever they are eligible. Results are bit-identical for every choice. */
 int fx3d_set_kernel_variant(int variant);
 /* FX3D_REGION_INTERIOR launches of the persistent kernel leave this many resident-block slots free, so that the halo exchange
  * kernels enqueued on another stream find room beside it (default 8; 0 = occupy every slot) */
