@@ -133,12 +133,12 @@ class Lib:
         self.launch_count(C.byref(v))
         return v.value
 
-    KERNEL_KINDS = ("k_stream_collide_v1", "k_stream_collide_vec", "k_stream_collide_pipe", "k_stream_collide_tma", "k_stream_collide_tma_seg")
+    KERNEL_KINDS = ("k_stream_collide_v1", "k_stream_collide_vec", "k_stream_collide_pipe", "k_stream_collide_tma", "k_stream_collide_tma_seg", "k_stream_collide_hyb")
 
     def kernel_kind_counts(self):
         """stream_collide launches so far per kernel kind (same order as KERNEL_KINDS)"""
         out = []
-        for k in range(5):
+        for k in range(6):
             v = C.c_uint64(0)
             self.stream_collide_launches(k, C.byref(v))
             out.append(v.value)

@@ -14,7 +14,7 @@ void set_error(const std::string& msg) { t_error = msg; }
 std::atomic<uint64_t> g_launches{0ull};
 std::atomic<int> g_variant{0};
 std::atomic<int> g_interior_reserve{8};
-std::atomic<uint64_t> g_kind_launches[5];
+std::atomic<uint64_t> g_kind_launches[6];
 
 // interior (non-halo) extent and the shell / interior split used to overlap the halo exchange with computation.
 // The shell is every non-halo cell within one cell (one 4-cell group along x for the vector kernel) of a halo layer.
@@ -96,7 +96,7 @@ extern "C" {
 const char* fx3d_last_error(void) { return t_error.c_str(); }
 int fx3d_set_kernel_variant(int variant) { if(variant!=0&&variant!=1&&variant!=2&&variant!=4&&variant!=8&&variant!=16) { set_error("variant must be 0 (auto), 1 (general), 2 or 4 (cells per thread), 8 (pipelined, cp.async), 16 (pipelined, bulk copies where eligible)"); return FX3D_ERR_INVALID; } g_variant = variant; return FX3D_OK; }
 int fx3d_set_interior_reserve(int blocks) { if(blocks<0||blocks>1024) { set_error("reserve must be 0..1024 blocks"); return FX3D_ERR_INVALID; } g_interior_reserve = blocks; return FX3D_OK; }
-int fx3d_stream_collide_launches(int kind, uint64_t* launches) { if(kind<0||kind>4||!launches) { set_error("kind must be 0..4"); return FX3D_ERR_INVALID; } *launches = g_kind_launches[kind].load(); return FX3D_OK; }
+int fx3d_stream_collide_launches(int kind, uint64_t* launches) { if(kind<0||kind>5||!launches) { set_error("kind must be 0..5"); return FX3D_ERR_INVALID; } *launches = g_kind_launches[kind].load(); return FX3D_OK; }
 int fx3d_launch_count(uint64_t* launches) { if(!launches) return FX3D_ERR_INVALID; *launches = g_launches.load(); return FX3D_OK; }
 
 size_t fx3d_fi_bytes(const fx3d_lattice* lat) {

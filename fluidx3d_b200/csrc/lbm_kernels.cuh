@@ -959,6 +959,180 @@ __global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_coll
 	if(copier) bulk_wait_all();
 }
 
+// ---- hybrid: bulk loads as in k_stream_collide_tma_seg, stream-out straight from registers as in k_stream_collide_pipe ----
+// tools/microbench/ubench3.cu: it is the *load* half of the LSU path that saturates at low occupancy (bulk loads + STG stores reach
+// the same 6.2 TB/s as bulk loads + bulk stores). Per-thread stores settle the ownership of the row ends by themselves (shuffles
+// inside a warp, one scalar store at warp / segment ends), so there is no write-back into the stage, no second barrier, no fix-up.
+template<int Q, int COLL, int ST, bool VF, int ODD>
+__global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_collide_hyb(const Lattice L, const Region R, const uint32_t tiles_x, const uint32_t tiles_y) {
+	constexpr int K = 4, S = FX3D_TMA_STAGES, NXD = x_dirs<Q>();
+	constexpr uint32_t odd = (uint32_t)ODD;
+	typedef Codec<ST> C;
+	typedef typename C::elem_t E;
+	typedef Pack<ST, K> P;
+	constexpr uint32_t VB = (uint32_t)(sizeof(E)*K), PAD = 16u, CH = PAD/(uint32_t)sizeof(E), SET = tmaseg_set_bytes<Q, ST>(), STAGE = (uint32_t)Q*SET;
+	unsigned char* const smem = dynamic_smem();
+	uint64_t* const full = reinterpret_cast<uint64_t*>(smem);
+	unsigned char* const ring = smem+128;
+	const uint32_t tid = threadIdx.x+threadIdx.y*blockDim.x;
+	const uint32_t W = blockDim.x*(uint32_t)K, row_bytes = blockDim.x*VB, ROWB = row_bytes+2u*PAD; // a row buffer: [pad | W elements | pad]
+	const uint32_t nbuf = (uint32_t)Q*blockDim.y;
+	if(tid==0u) { for(int s=0; s<S; s++) mbar_init(full+s); }
+	fence_async_smem();
+	__syncthreads();
+
+	// buffer c = ty*Q+j of the tile at (X0, rows R.y0+yb*by.., plane z): global address of the segment start, x shift of its direction
+	auto buffer_row = [&](uint32_t c, uint32_t X0, uint32_t yb, uint32_t z, uint32_t& smem_off, int& ex) -> char* {
+		const uint32_t ty = c/(uint32_t)Q, j = c%(uint32_t)Q, y = R.y0+yb*blockDim.y+ty;
+		smem_off = j*SET+ty*ROWB;
+		uint32_t slot = j, yr = y, zr = z;
+		ex = 0;
+		if(j>0u) {
+			const uint32_t i = (j&1u) ? j : j-1u;
+			if(j&1u) slot = odd ? i : i+1u;
+			else { slot = odd ? i+1u : i; yr = step_rt(dir_rt(1, i), y, L.Ny); zr = step_rt(dir_rt(2, i), z, L.Nz); ex = dir_rt(0, i); }
+		}
+		return reinterpret_cast<char*>(L.fi)+((uint64_t)slot*L.slot+row(L, yr, zr)+(uint64_t)(X0+L.xo))*sizeof(E);
+	};
+	const uint32_t first_copy = (tid>>5)+4u*(tid&31u);
+	// One-row tiles (blockDim.y==1, i.e. segments of 512 cells): lane 0 of warp w issues buffers w, w+4, .. from an unrolled list
+	// in which everything but X0, y and z is a compile-time constant; the end-chunk elements are stored by threads n*CH+k.
+	const bool one_row = blockDim.y==1u;
+	const uint32_t warp = __shfl_sync(0xFFFFFFFFu, tid>>5, 0);
+		auto row_ptr = [&](auto J, uint32_t X0, uint32_t y, uint32_t z) -> char* { // segment start of buffer J (compile time) in row y of plane z
+		constexpr int j = decltype(J)::value;
+		constexpr int i = j==0 ? 0 : (j&1) ? j : j-1;
+		constexpr uint32_t slot = j==0 ? 0u : (j&1) ? (ODD ? (uint32_t)i : (uint32_t)i+1u) : (ODD ? (uint32_t)i+1u : (uint32_t)i);
+		constexpr int ey = (j==0 || (j&1)) ? 0 : dir_y(i), ez = (j==0 || (j&1)) ? 0 : dir_z(i);
+		return reinterpret_cast<char*>(L.fi)+((uint64_t)slot*L.slot+row(L, step<ey>(y, L.Ny), step<ez>(z, L.Nz))+(uint64_t)(X0+L.xo))*sizeof(E);
+	};
+	auto copy_rows = [&](auto LOAD, uint32_t X0, uint32_t yb, uint32_t z, uint32_t stage) {
+		constexpr bool load = decltype(LOAD)::value;
+		const uint32_t y = R.y0+yb;
+		unsigned char* const sb = ring+(size_t)stage*STAGE;
+		auto one = [&](auto J) {
+			constexpr int j = J;
+			constexpr int ex = (j==0 || (j&1)) ? 0 : dir_x(j-1);
+			char* g = row_ptr(J, X0, y, z);
+			unsigned char* b = sb+(size_t)j*SET;
+			if constexpr(load) {
+				if constexpr(ex>0) {
+					if(X0+W<L.Nx) bulk_load(b+PAD, g, row_bytes+PAD, full+stage);
+					else { bulk_load(b+PAD, g, row_bytes, full+stage); bulk_load(b+PAD+row_bytes, g-(size_t)X0*sizeof(E), PAD, full+stage); }
+				} else if constexpr(ex<0) {
+					if(X0>0u) bulk_load(b, g-PAD, row_bytes+PAD, full+stage);
+					else { bulk_load(b+PAD, g, row_bytes, full+stage); bulk_load(b, g+(size_t)(L.Nx-CH)*sizeof(E), PAD, full+stage); }
+				} else bulk_load(b+PAD, g, row_bytes, full+stage);
+			} else {
+				if constexpr(ex>0) bulk_store(g+PAD, b+2u*PAD, row_bytes-PAD); else if constexpr(ex<0) bulk_store(g, b+PAD, row_bytes-PAD); else bulk_store(g, b+PAD, row_bytes);
+			}
+		};
+		if(warp==0u) static_for<0, Q, 4>(one); else if(warp==1u) static_for<1, Q, 4>(one); else if(warp==2u) static_for<2, Q, 4>(one); else static_for<3, Q, 4>(one);
+	};
+	auto load_tile = [&](uint32_t X0, uint32_t yb, uint32_t z, uint32_t stage) {
+		if(tid==0u) mbar_expect_tx(full+stage, blockDim.y*((uint32_t)Q*row_bytes+(uint32_t)NXD*PAD));
+		if(one_row) { if((tid&31u)==0u) copy_rows(std::true_type{}, X0, yb, z, stage); }
+		else for(uint32_t c=first_copy; c<nbuf; c+=128u) {
+			uint32_t off; int ex;
+			char* g = buffer_row(c, X0, yb, z, off, ex);
+			unsigned char* b = ring+(size_t)stage*STAGE+off;
+			if(ex>0) { // segment + the element one past it
+				if(X0+W<L.Nx) bulk_load(b+PAD, g, row_bytes+PAD, full+stage);
+				else { bulk_load(b+PAD, g, row_bytes, full+stage); bulk_load(b+PAD+row_bytes, g-(size_t)X0*sizeof(E), PAD, full+stage); } // periodic: the row's first chunk
+			} else if(ex<0) { // the element before the segment + segment
+				if(X0>0u) bulk_load(b, g-PAD, row_bytes+PAD, full+stage);
+				else { bulk_load(b+PAD, g, row_bytes, full+stage); bulk_load(b, g+(size_t)(L.Nx-CH)*sizeof(E), PAD, full+stage); } // periodic: the row's last chunk
+			} else bulk_load(b+PAD, g, row_bytes, full+stage);
+		}
+#if defined(FX3D_HOST_EMULATION)
+		__syncthreads();
+		if(tid==0u) mbar_phase_done_emulated(full+stage);
+#endif
+	};
+	const uint32_t nz = R.z1-R.z0;
+	const uint64_t ntiles = (uint64_t)tiles_x*tiles_y*nz;
+	uint64_t tile = ntiles*blockIdx.x/gridDim.x;
+	const uint64_t tile_end = ntiles*(blockIdx.x+1u)/gridDim.x;
+	uint32_t it = 0u;
+	const uint32_t x0 = (uint32_t)K*threadIdx.x; // my first cell within the segment
+	while(tile<tile_end) {
+		const uint32_t col = (uint32_t)(tile/nz), zoff = (uint32_t)(tile%nz), xb = col%tiles_x, yb = col/tiles_x;
+		const uint32_t zs = R.z0+zoff, ze = (uint64_t)(nz-zoff)<=tile_end-tile ? R.z1 : zs+(uint32_t)(tile_end-tile);
+		tile += ze-zs;
+		const uint32_t X0 = L.Hx+(R.g0+xb*blockDim.x)*(uint32_t)K, y = R.y0+yb*blockDim.y+threadIdx.y;
+		const uint8_t* const my_flags = L.flags+((uint64_t)(X0+x0)+(uint64_t)y*L.Nx);
+		const uint64_t flag_plane = (uint64_t)L.Nx*L.Ny;
+		// my 4 flag bytes come from two aligned words; the words of the next plane are requested a whole tile ahead and only
+		// combined when they are needed (combining at the load would wait for them on the spot)
+		uint32_t fw0, fw1;
+		auto request_flags = [&](uint32_t z) {
+			const uintptr_t a = reinterpret_cast<uintptr_t>(my_flags+(uint64_t)z*flag_plane);
+			fw0 = *reinterpret_cast<const uint32_t*>(a&~(uintptr_t)3u);
+			fw1 = (a&3u) ? *reinterpret_cast<const uint32_t*>((a&~(uintptr_t)3u)+4u) : 0u;
+		};
+		auto combine_flags = [&](uint32_t z) -> uint32_t {
+			const uint32_t sh = 8u*(uint32_t)(reinterpret_cast<uintptr_t>(my_flags+(uint64_t)z*flag_plane)&3u);
+			return sh==0u ? fw0 : (fw0>>sh)|(fw1<<(32u-sh));
+		};
+		// stream-out goes straight from registers (as in k_stream_collide_pipe): my vector in rows y-1, y, y+1 of the current plane
+		const uint32_t xg = X0+x0, lane = tid&31u;
+		const bool has_right = lane<31u && threadIdx.x+1u<blockDim.x, has_left = lane>0u && threadIdx.x>0u;
+		const int dxr = (xg+(uint32_t)K>=L.Nx ? 0 : (int)xg+K)-(int)xg, dxl = (xg==0u ? (int)L.Nx-1 : (int)xg-1)-(int)xg;
+		const uint32_t yy[3] = { dec(y, L.Ny), y, inc(y, L.Ny) };
+		const int64_t plane_bytes = (int64_t)((uint64_t)L.px*L.Ny*sizeof(E));
+		char* colp[3];
+		static_for<0, 3, 1>([&](auto J) { colp[J] = reinterpret_cast<char*>(L.fi)+(row(L, yy[J], zs)+(uint64_t)(xg+L.xo))*sizeof(E); });
+#define FX3D_AT(ey, s) mad_wide(L.slot32, (s)*(uint32_t)sizeof(E), colp[(ey)+1])
+		for(uint32_t k=0u; k<(uint32_t)(S-1); k++) if(zs+k<ze) load_tile(X0, yb, zs+k, (it+k)%(uint32_t)S);
+		request_flags(zs);
+		for(uint32_t z=zs; z<ze; z++, it++) {
+			const uint32_t stage = it%(uint32_t)S;
+			const uint32_t flags4 = combine_flags(z);
+			mbar_wait(full+stage, (it/(uint32_t)S)&1u);
+			unsigned char* const sb = ring+(size_t)stage*STAGE+threadIdx.y*ROWB+PAD;
+			P A[Q];
+			static_for<0, Q, 1>([&](auto I) { A[I].load(reinterpret_cast<const E*>(sb+(size_t)I.value*SET)+x0); });
+			static_for<1, Q, 2>([&](auto I) {
+				constexpr int i = I;
+				const E* rowp = reinterpret_cast<const E*>(sb+(size_t)(i+1)*SET);
+				if constexpr(dir_x(i)>0) A[i+1].push_back(P::bits(rowp[x0+(uint32_t)K]));
+				else if constexpr(dir_x(i)<0) A[i+1].push_front(P::bits(*(rowp+x0-1)));
+			});
+			__syncthreads();
+			if(z+(uint32_t)(S-1)<ze) load_tile(X0, yb, z+(uint32_t)(S-1), (it+(uint32_t)(S-1))%(uint32_t)S);
+			if(z+1u<ze) request_flags(z+1u);
+			collide_tile<Q, COLL, ST, VF, K>(L, A, flags4, X0+x0, y, z);
+			{
+				constexpr unsigned FULL = 0xFFFFFFFFu;
+				const int64_t dzn[3] = { ((int64_t)dec(z, L.Nz)-(int64_t)z)*plane_bytes, 0, ((int64_t)inc(z, L.Nz)-(int64_t)z)*plane_bytes };
+				A[0].store(reinterpret_cast<E*>(FX3D_AT(0, 0u)));
+				static_for<1, Q, 2>([&](auto I) {
+					constexpr int i = I;
+					const uint32_t sl = odd ? (uint32_t)i : (uint32_t)i+1u, sn = odd ? (uint32_t)i+1u : (uint32_t)i;
+					A[i].store(reinterpret_cast<E*>(FX3D_AT(0, sl)));
+					E* q = reinterpret_cast<E*>(FX3D_AT(dir_y(i), sn)+dzn[dir_z(i)+1]);
+					if constexpr(dir_x(i)==0) A[i+1].store(q);
+					else if constexpr(dir_x(i)>0) {
+						const uint32_t last = A[i+1].last_bits();
+						const uint32_t up = __shfl_up_sync(FULL, last, 1u);
+						if(!has_right) q[dxr] = P::from_bits(last);
+						A[i+1].push_front(up);
+						if(has_left) A[i+1].store(q); else A[i+1].store_tail(q);
+					} else {
+						const uint32_t first = A[i+1].first_bits();
+						const uint32_t dn = __shfl_down_sync(FULL, first, 1u);
+						if(!has_left) q[dxl] = P::from_bits(first);
+						A[i+1].push_back(dn);
+						if(has_right) A[i+1].store(q); else A[i+1].store_head(q);
+					}
+				});
+			}
+			static_for<0, 3, 1>([&](auto J) { colp[J] += plane_bytes; });
+		}
+#undef FX3D_AT
+	}
+}
+
 // ================================================================================================================
 // scalar cell access shared by the general kernels (any Nx): one thread per cell, addresses as load_f/store_f
 // ================================================================================================================

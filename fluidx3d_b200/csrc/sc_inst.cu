@@ -105,6 +105,33 @@ template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_tmaseg_par
 template<int Q, int COLL, int ST, bool VF> static int launch_tmaseg(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
 	return L.odd ? launch_tmaseg_parity<Q, COLL, ST, VF, 1>(L, R, block, stream, reserve) : launch_tmaseg_parity<Q, COLL, ST, VF, 0>(L, R, block, stream, reserve);
 }
+template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_hyb_parity(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
+	const uint32_t tiles_x = (R.g1-R.g0)/block.x, tiles_y = (R.y1-R.y0)/block.y, nz = R.z1-R.z0;
+	constexpr uint32_t smem = tmaseg_smem_bytes<Q, ST>();
+	int sms = 148, per_sm = tma_blocks_per_sm<Q, ST>();
+#if !defined(FX3D_HOST_EMULATION)
+	static std::atomic<uint64_t> configured{0ull};
+	int dev = 0; cudaGetDevice(&dev);
+	if(dev>=64 || !((configured.load()>>dev)&1ull)) {
+		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_hyb<Q, COLL, ST, VF, ODD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if(e!=cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stream_collide_hyb)");
+		if(dev<64) configured.fetch_or(1ull<<dev);
+	}
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+#else
+	sms = 2; per_sm = 1;
+#endif
+	const uint64_t all_blocks = (uint64_t)sms*(uint64_t)per_sm, blocks = all_blocks>2ull*(uint64_t)std::max(reserve, 0) ? all_blocks-(uint64_t)std::max(reserve, 0) : all_blocks, ntiles = (uint64_t)tiles_x*tiles_y*nz;
+	if(ntiles==0ull) return FX3D_OK;
+	if((uint64_t)tiles_x*tiles_y>0xFFFFFFFFull) { set_error("region has too many tile columns"); return FX3D_ERR_INVALID; }
+	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, blocks), 1u, 1u);
+	g_kind_launches[5]++;
+	FX3D_LAUNCH_SMEM((k_stream_collide_hyb<Q, COLL, ST, VF, ODD>), grid, block, smem, stream, L, R, tiles_x, tiles_y);
+	return check_launch("stream_collide (bulk loads, direct stores)");
+}
+template<int Q, int COLL, int ST, bool VF> static int launch_hyb(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
+	return L.odd ? launch_hyb_parity<Q, COLL, ST, VF, 1>(L, R, block, stream, reserve) : launch_hyb_parity<Q, COLL, ST, VF, 0>(L, R, block, stream, reserve);
+}
 template<int Q, int COLL, int ST, bool VF> static int launch_tma(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
 	return L.odd ? launch_tma_parity<Q, COLL, ST, VF, 1>(L, R, block, stream, reserve) : launch_tma_parity<Q, COLL, ST, VF, 0>(L, R, block, stream, reserve);
 }
@@ -113,9 +140,11 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 	if(R.g1<=R.g0||R.y1<=R.y0||R.z1<=R.z0) return FX3D_OK;
 	if(cells_per_thread<=0) { // persistent kernels; R.g0/g1 are in groups of pipe_cells<Q,ST>() cells. 0: bulk copies where the tile spans the row, else cp.async; -1: cp.async
 		const dim3 block = block_shape(R.g1-R.g0);
-		// row segments / x halos: measured on B200 the bulk-copy form wins for FP32 (+8 %) but not for 16-bit storage (issue-bound: -3 %), so
-		// the automatic choice takes it for FP32 only; variant 16 (-3) takes it wherever it is eligible
-		if((cells_per_thread==-3 || (cells_per_thread==0 && ST==ST_FP32)) && pipe_cells<Q, ST>()==4 && !tma_eligible(L, R, block) && tmaseg_eligible<Q, ST>(L, R, block)) {
+		if(cells_per_thread==0 && pipe_cells<Q, ST>()==4 && !tma_eligible(L, R, block) && tmaseg_eligible<Q, ST>(L, R, block)) { // row segments / x halos: bulk loads, direct stores
+			if(collision==COLL_SRT) return volume_force ? launch_hyb<Q, COLL_SRT, ST, true>(L, R, block, stream, reserve) : launch_hyb<Q, COLL_SRT, ST, false>(L, R, block, stream, reserve);
+			return volume_force ? launch_hyb<Q, COLL_TRT, ST, true>(L, R, block, stream, reserve) : launch_hyb<Q, COLL_TRT, ST, false>(L, R, block, stream, reserve);
+		}
+		if(cells_per_thread==-3 && pipe_cells<Q, ST>()==4 && !tma_eligible(L, R, block) && tmaseg_eligible<Q, ST>(L, R, block)) { // variant 16: bulk stores as well
 			if(collision==COLL_SRT) return volume_force ? launch_tmaseg<Q, COLL_SRT, ST, true>(L, R, block, stream, reserve) : launch_tmaseg<Q, COLL_SRT, ST, false>(L, R, block, stream, reserve);
 			return volume_force ? launch_tmaseg<Q, COLL_TRT, ST, true>(L, R, block, stream, reserve) : launch_tmaseg<Q, COLL_TRT, ST, false>(L, R, block, stream, reserve);
 		}

@@ -114,7 +114,8 @@ int fx3d_set_kernel_variant(int variant);
  * kernels enqueued on another stream find room beside it (default 8; 0 = occupy every slot) */
 int fx3d_set_interior_reserve(int blocks);
 /* stream_collide launches so far by kernel kind: 0 general (1 cell/thread), 1 vector (2/4 cells/thread), 2 persistent with a
- * cp.async ring, 3 persistent with bulk copies of whole rows, 4 persistent with bulk copies of row segments */
+ * cp.async ring, 3 persistent with bulk copies of whole rows, 4 persistent with bulk copies of row segments, 5 persistent with bulk loads
+ * of row segments and direct stores */
 int fx3d_stream_collide_launches(int kind, uint64_t* launches);
 int fx3d_launch_count(uint64_t* launches);                            /* kernels launched by this library so far */
 

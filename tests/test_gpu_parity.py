@@ -98,6 +98,20 @@ def test_bulk_copy_segment_kernel_bit_exact(fx, v, dims, D):
     assert after[4] > before[4] and after[:3] == before[:3]
 
 
+@pytest.mark.parametrize("v,dims,D", SEG_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in SEG_CASES])
+def test_hybrid_kernel_bit_exact(fx, v, dims, D):
+    """default choice for row segments / x halos: bulk loads, direct stores"""
+    from fluidx3d_b200 import capi
+    f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
+    before = capi.lib().kernel_kind_counts()
+    for steps in (1, 2, 7):
+        got, want = product(fx, v, dims, D, steps, f, 0), oracle(v, dims, D, steps, f)
+        for a, b in zip(got, want):
+            assert np.array_equal(bits(a), bits(b)), steps
+    after = capi.lib().kernel_kind_counts()
+    assert after[5] > before[5] and after[:5] == before[:5]
+
+
 @pytest.mark.parametrize("D", [(2, 1, 1), (1, 2, 1), (1, 1, 2), (2, 2, 1), (2, 2, 2), (4, 1, 2)], ids=lambda d: "d" + "".join(map(str, d)))
 @pytest.mark.parametrize("v", [(19, SRT, FP32, 0), (19, SRT, FP16C, 0), (27, TRT, FP16S, 3)], ids=["fp32", "fp16c", "q27trt16s"])
 def test_decomposed_domains_bit_identical_to_single(fx, v, D):

@@ -98,6 +98,20 @@ def test_emulated_bulk_copy_segments_match_oracle(emul, v, dims, D):
     assert after[4] > before[4] and after[:3] == before[:3], "the segment bulk-copy kernel must be the one that ran"
 
 
+@pytest.mark.parametrize("v,dims,D", SEG_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in SEG_CASES])
+def test_emulated_hybrid_kernel_matches_oracle(emul, v, dims, D):
+    """the default choice for row segments and x-decomposed domains: bulk loads into padded row buffers, stream-out straight
+    from registers with the vector kernel's ownership rules (shuffles inside a warp, scalar stores at warp and segment ends)"""
+    f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
+    before = emul.kernel_kind_counts()
+    for steps in (1, 2, 5):
+        got, want = product(emul, v, dims, D, steps, f, 0), oracle(v, dims, D, steps, f)
+        for a, b in zip(got, want):
+            assert np.array_equal(bits(a), bits(b))
+    after = emul.kernel_kind_counts()
+    assert after[5] > before[5] and after[:5] == before[:5], "the hybrid kernel must be the one that ran"
+
+
 @pytest.mark.parametrize("variant", [1, 4, 8], ids=["general", "vector4", "pipelined"])
 def test_shell_plus_interior_equals_all(emul, variant):
     # FX3D_REGION_SHELL followed by FX3D_REGION_INTERIOR must cover every non-halo cell exactly once

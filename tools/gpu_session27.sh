@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 exec > >(tee gpurun_out/session27.log) 2>&1
-echo "=== parity"; timeout 900 python -m pytest tests -m gpu -q -x -k "segment or decomposed or small" 2>&1 | tail -3
+echo "=== parity"; timeout 900 python -m pytest tests -m gpu -q -x -k "segment or hybrid or decomposed" 2>&1 | tail -3
 for ax in 0 2; do timeout 300 python tools/xhalo_probe.py $ax fp16s; done
 timeout 300 python tools/xhalo_probe.py 0 fp32
 timeout 300 python tools/xhalo_probe.py 0 fp16c

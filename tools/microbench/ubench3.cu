@@ -52,6 +52,34 @@ template<int S> __global__ void __launch_bounds__(TPB) k_tma(char* base, size_t 
   }
   if(tid==0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
+// (c) hybrid: bulk loads into the ring, results stored straight from registers with STG (which half of the LSU path is the limit?)
+template<int S> __global__ void __launch_bounds__(TPB) k_hybrid(char* base, size_t slot_bytes, size_t ntiles){
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  unsigned char* ring = smem+128;
+  const int tid = threadIdx.x;
+  if(tid==0) { for(int s=0;s<S;s++) mbar_init(bars+s, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  const size_t stride = gridDim.x;
+  auto load = [&](size_t tile, int stage) {
+    mbar_expect(bars+stage, Q*ROW);
+    for(int q=0;q<Q;q++) bulk_g2s(ring+(size_t)(stage*Q+q)*ROW, base+q*slot_bytes+tile*ROW, ROW, bars+stage);
+  };
+  size_t t = blockIdx.x; int k = 0;
+  if(tid==0) for(int s=0;s<S-1;s++) if(t+s*stride<ntiles) load(t+s*stride, s);
+  for(; t<ntiles; t+=stride, k++) {
+    const int stage = k%S;
+    mbar_wait(bars+stage, (k/S)&1);
+    uint2 v[Q];
+    const uint2* mine = reinterpret_cast<const uint2*>(ring+(size_t)stage*Q*ROW)+tid;
+    #pragma unroll
+    for(int q=0;q<Q;q++) { v[q] = mine[q*TPB]; v[q].x += 1u; }
+    __syncthreads(); // stage consumed
+    if(tid==0 && t+(S-1)*stride<ntiles) load(t+(S-1)*stride, (k+S-1)%S);
+    #pragma unroll
+    for(int q=0;q<Q;q++) *reinterpret_cast<uint2*>(base+q*slot_bytes+t*ROW+tid*VB) = v[q];
+  }
+}
 // (a) per-thread cp.async ring + direct STG
 template<int S> __global__ void __launch_bounds__(TPB) k_ldgsts(char* base, size_t slot_bytes, size_t ntiles){
   extern __shared__ __align__(128) unsigned char smem[];
@@ -84,7 +112,9 @@ template<int S> void run(char* buf, size_t slot_bytes, size_t ntiles, double byt
     CK(cudaFuncSetAttribute(k_ldgsts<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     float t1 = timeit([&]{ k_tma<S><<<148*bps, TPB, smem>>>(buf, slot_bytes, ntiles); });
     float t2 = timeit([&]{ k_ldgsts<S><<<148*bps, TPB, smem>>>(buf, slot_bytes, ntiles); });
-    printf("stages %d, %d blocks/SM (%2d warps, %3d KB ring/SM): TMA bulk %5.0f GB/s | cp.async+STG %5.0f GB/s\n", S, bps, bps*4, bps*S*Q*ROW/1024, bytes/t1*1e-6, bytes/t2*1e-6);
+    CK(cudaFuncSetAttribute(k_hybrid<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    float t3 = timeit([&]{ k_hybrid<S><<<148*bps, TPB, smem>>>(buf, slot_bytes, ntiles); });
+    printf("stages %d, %d blocks/SM (%2d warps, %3d KB ring/SM): TMA bulk %5.0f GB/s | cp.async+STG %5.0f GB/s | bulk loads+STG %5.0f GB/s\n", S, bps, bps*4, bps*S*Q*ROW/1024, bytes/t1*1e-6, bytes/t2*1e-6, bytes/t3*1e-6);
   }
 }
 int main(){
