@@ -297,7 +297,20 @@ void orc_stream_collide(const orc_grid* g, void* fi, float* rho, float* u, const
 		const int is_e = eb && fb==TYPE_E;
 		if((g->features&ORC_UPDATE_FIELDS) && !is_e) { rho[n] = rhon; u[n] = uxn; u[N+n] = uyn; u[2ull*N+n] = uzn; } /* :1565-1573 */
 		equilibrium(g, rhon, uxn, uyn, uzn, feq);
-		const float w = g->w;
+		float w = g->w;
+		if(g->features&ORC_SUBGRID) { /* Smagorinsky-Lilly subgrid model, :1579-1593: relaxation rate from the non-equilibrium stress tensor */
+			const float tau0 = 1.0f/w;
+			float Hxx = 0.0f, Hyy = 0.0f, Hzz = 0.0f, Hxy = 0.0f, Hxz = 0.0f, Hyz = 0.0f;
+			for(uint32_t i=1u; i<Q; i++) {
+				const float fneqi = fhn[i]-feq[i];
+				const float cxi = (float)EX[i], cyi = (float)EY[i], czi = (float)EZ[i];
+				Hxx += cxi*cxi*fneqi;
+				Hxy += cxi*cyi*fneqi; Hyy += cyi*cyi*fneqi;
+				Hxz += cxi*czi*fneqi; Hyz += cyi*czi*fneqi; Hzz += czi*czi*fneqi;
+			}
+			const float Qs = Hxx*Hxx+Hyy*Hyy+Hzz*Hzz+2.0f*(Hxy*Hxy+Hxz*Hxz+Hyz*Hyz);
+			w = 2.0f/(tau0+sqrtf(tau0*tau0+0.76421222f*sqrtf(Qs)/rhon));
+		}
 		if(g->collision==ORC_SRT) { /* :1595-1604 */
 			if(vf) { const float c_tau = fmaf(w, -0.5f, 1.0f); for(uint32_t i=0u; i<Q; i++) Fin[i] *= c_tau; }
 			for(uint32_t i=0u; i<Q; i++) fhn[i] = is_e ? feq[i] : fmaf(1.0f-w, fhn[i], fmaf(w, feq[i], Fin[i]));

@@ -24,7 +24,7 @@ extern "C" {
 
 enum { ORC_FP32 = 0, ORC_FP16S = 1, ORC_FP16C = 2 };
 enum { ORC_SRT = 0, ORC_TRT = 1 };
-enum { ORC_VOLUME_FORCE = 1u, ORC_EQUILIBRIUM_BOUNDARIES = 2u, ORC_UPDATE_FIELDS = 4u };
+enum { ORC_VOLUME_FORCE = 1u, ORC_EQUILIBRIUM_BOUNDARIES = 2u, ORC_UPDATE_FIELDS = 4u, ORC_SUBGRID = 8u };
 
 /* One LBM_Domain worth of compile-time constants of the reference (src/lbm.cpp:334-425), made run-time. */
 typedef struct orc_grid {
@@ -33,7 +33,7 @@ typedef struct orc_grid {
 	uint32_t Q;            /* velocity set: 19 or 27 */
 	uint32_t collision;    /* ORC_SRT | ORC_TRT */
 	uint32_t storage;      /* ORC_FP32 | ORC_FP16S | ORC_FP16C */
-	uint32_t features;     /* ORC_VOLUME_FORCE | ORC_EQUILIBRIUM_BOUNDARIES | ORC_UPDATE_FIELDS */
+	uint32_t features;     /* ORC_VOLUME_FORCE | ORC_EQUILIBRIUM_BOUNDARIES | ORC_UPDATE_FIELDS | ORC_SUBGRID */
 	float w;               /* relaxation rate def_w = 1/tau, as the device sees it */
 } orc_grid;
 

@@ -11,7 +11,7 @@ plus a tiny NDRange driver.
 
 usage: build_ref.py [--reference /root/reference] [--variants q19_srt_fp32_f0,...]
 Variant name: q<19|27>_<srt|trt>_<fp32|fp16s|fp16c>_f<mask>  (mask bit0 VOLUME_FORCE, bit1 EQUILIBRIUM_BOUNDARIES,
-bit2 UPDATE_FIELDS)
+bit2 UPDATE_FIELDS, bit3 SUBGRID)
 """
 import argparse, os, re, subprocess, sys
 from concurrent.futures import ThreadPoolExecutor
@@ -24,6 +24,7 @@ DEFAULT_VARIANTS = [
     "q19_srt_fp32_f0", "q19_srt_fp16s_f0", "q19_srt_fp16c_f0",
     "q19_trt_fp32_f0", "q19_srt_fp32_f1", "q19_srt_fp32_f2", "q19_trt_fp16s_f3", "q19_srt_fp32_f4",
     "q27_srt_fp32_f0", "q27_trt_fp32_f3", "q27_srt_fp16s_f0", "q27_trt_fp16c_f3",
+    "q19_srt_fp32_f8", "q19_trt_fp16s_f11", "q27_srt_fp16c_f8", "q19_srt_fp16s_f8",  # bit3: SUBGRID (first "next" row of SURVEY 8f)
 ]
 
 # functions on the hot path; everything else in the program text is dropped
@@ -65,6 +66,7 @@ def prologue(q, coll, storage, mask):
     if mask & 1: d.append("#define VOLUME_FORCE")
     if mask & 2: d.append("#define EQUILIBRIUM_BOUNDARIES")
     if mask & 4: d.append("#define UPDATE_FIELDS")
+    if mask & 8: d.append("#define SUBGRID")
     return "\n".join(d) + "\n"
 
 

@@ -27,6 +27,7 @@ static inline float3 make_float3(float x, float y, float z) { return float3{ x, 
 static inline uint as_uint(const float x) { uint u; std::memcpy(&u, &x, 4); return u; }
 static inline float as_float(const uint u) { float x; std::memcpy(&x, &u, 4); return x; }
 static inline float fma(const float a, const float b, const float c) { return __builtin_fmaf(a, b, c); }
+static inline float sqrt(const float x) { return __builtin_sqrtf(x); } // correctly rounded, as OpenCL's sqrt on an IEEE device without fast-math (SUBGRID only)
 static inline float clamp(const float x, const float lo, const float hi) { return __builtin_fminf(__builtin_fmaxf(x, lo), hi); }
 static inline float vload_half(const ulong offset, const half* p) { return (float)p[offset]; }
 static inline void vstore_half_rte(const float x, const ulong offset, half* p) { p[offset] = (half)x; }

@@ -13,7 +13,7 @@ REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 FP32, FP16S, FP16C = 0, 1, 2
 SRT, TRT = 0, 1
-VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS = 1, 2, 4
+VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID = 1, 2, 4, 8
 TYPE_S, TYPE_E = 1, 2
 STORAGE_NAMES = {FP32: "fp32", FP16S: "fp16s", FP16C: "fp16c"}
 COLL_NAMES = {SRT: "srt", TRT: "trt"}

@@ -6,7 +6,8 @@ from helpers import (OracleBackend, RefBackend, HostSim, scenario, load_scenario
                      FP32, FP16S, FP16C, SRT, TRT)
 
 VARIANTS = [(19, SRT, FP32, 0), (19, SRT, FP16S, 0), (19, SRT, FP16C, 0), (19, TRT, FP32, 0), (19, SRT, FP32, 1), (19, SRT, FP32, 2),
-            (19, TRT, FP16S, 3), (19, SRT, FP32, 4), (27, SRT, FP32, 0), (27, TRT, FP32, 3), (27, SRT, FP16S, 0), (27, TRT, FP16C, 3)]
+            (19, TRT, FP16S, 3), (19, SRT, FP32, 4), (27, SRT, FP32, 0), (27, TRT, FP32, 3), (27, SRT, FP16S, 0), (27, TRT, FP16C, 3),
+            (19, SRT, FP32, 8), (19, TRT, FP16S, 11), (27, SRT, FP16C, 8), (19, SRT, FP16S, 8)]  # feature bit 3: SUBGRID
 
 
 def bits(a):
