@@ -33,6 +33,8 @@ WORKLOADS = {
     "d3q19_srt_fp16c_1024": (19, "srt", "fp16c", 0, (1024, 1024, 1024), "D3Q19 SRT FP16C 1024^3 per GPU; with --gpus 8 --split 2,2,2 the 2048^3 domain of BASELINE configs[3] (run with --no-e2e: 18 GB of host fields per GPU)"),
     "d3q27_trt_fp32_windtunnel": (27, "trt", "fp32", 3, (256, 512, 256), "D3Q27 TRT FP32 wind tunnel with sphere, TYPE_E faces + VOLUME_FORCE (BASELINE configs[2], half size)"),
     "d3q27_trt_fp32_windtunnel_full": (27, "trt", "fp32", 3, (512, 1024, 512), "D3Q27 TRT FP32 wind tunnel with sphere, TYPE_E faces + VOLUME_FORCE, 512x1024x512 (BASELINE configs[2], SURVEY 8d C3)"),
+    "d3q19_srt_fp32_512_subgrid": (19, "srt", "fp32", 8, (512, 512, 512), "D3Q19 SRT FP32 512^3 periodic box with the SUBGRID (Smagorinsky-Lilly) model, SURVEY 8f rank 2"),
+    "d3q19_srt_fp16s_512_subgrid": (19, "srt", "fp16s", 8, (512, 512, 512), "D3Q19 SRT FP16S 512^3 periodic box with the SUBGRID model"),
     "d3q19_srt_fp32_256_cavity": (19, "srt", "fp32", 2, (256, 256, 256), "D3Q19 SRT FP32 256^3 lid-driven cavity inside the hot-path feature set: TYPE_S walls, TYPE_E lid u=(0,0.1,0), Re=1000 (SURVEY 8d C1w)"),
 }
 DEFAULT_OVERLAP = False  # multi-GPU step: overlap the halo exchange with the interior cells

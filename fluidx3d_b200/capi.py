@@ -8,7 +8,7 @@ DEFAULT_LIB = os.environ.get("FX3D_LIB", os.path.join(HERE, "libfx3d_cuda.so")) 
 
 FP32, FP16S, FP16C = 0, 1, 2
 SRT, TRT = 0, 1
-VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS = 1, 2, 4
+VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID = 1, 2, 4, 8
 REGION_ALL, REGION_SHELL, REGION_INTERIOR = 0, 1, 2
 TYPE_S, TYPE_E = 0x01, 0x02  # src/defines.hpp:52-53
 OK, ERR_NO_DEVICE, ERR_INVALID, ERR_OUT_OF_MEMORY, ERR_CUDA, ERR_TIMEOUT = 0, -1, -2, -3, -4, -5

@@ -67,6 +67,28 @@ static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int re
 	}
 	std::vector<Region> regs;
 	const bool vf = (lat->features&FX3D_VOLUME_FORCE)!=0u;
+	if(lat->features&FX3D_SUBGRID) { // whole-row bulk-copy kernel where eligible, else the general kernel (any size)
+		const int reserve = region==FX3D_REGION_INTERIOR ? g_interior_reserve.load() : 0;
+		if(want!=1 && inner%4u==0u) {
+			regions_of(L, region, 4u, regs);
+			bool all = !regs.empty();
+			for(size_t k=0u; k<regs.size() && all; k++) {
+				int rc;
+				FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, regs[k], 0, (int)lat->collision, vf, stream, reserve, true); })
+				if(rc==1 && k==0u) all = false;
+				else if(rc!=FX3D_OK) return rc==1 ? FX3D_ERR_INVALID : rc;
+			}
+			if(all) return FX3D_OK;
+			regs.clear();
+		}
+		regions_of(L, region, 1u, regs);
+		for(const Region& R : regs) {
+			int rc;
+			FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, 1, (int)lat->collision, vf, stream, reserve, true); })
+			if(rc!=FX3D_OK) return rc;
+		}
+		return FX3D_OK;
+	}
 	if(pipelined && want!=8 && K==2u && inner%4u==0u) { // D3Q27 FP32: the bulk-copy kernel (4 cells per thread) where the tile spans whole rows
 		regions_of(L, region, 4u, regs);
 		bool all = !regs.empty();

@@ -384,7 +384,7 @@ FX3D_HD unsigned char* dynamic_smem() {
 
 // ---- collision of the K cells a thread holds in A (raw storage vectors, stream-in order), pair by pair in packed arithmetic;
 // on return A holds what streams out through the same slots. flags4: the flag bytes of the cells (TYPE_S for cells to skip).
-template<int Q, int COLL, int ST, bool VF, int K> FX3D_HD void collide_tile(const Lattice& L, Pack<ST, K> (&A)[Q], const uint32_t flags4, const uint32_t x0, const uint32_t yc, const uint32_t z) {
+template<int Q, int COLL, int ST, bool VF, int K, bool SG = false> FX3D_HD void collide_tile(const Lattice& L, Pack<ST, K> (&A)[Q], const uint32_t flags4, const uint32_t x0, const uint32_t yc, const uint32_t z) {
 	typedef Codec<ST> C;
 	typedef typename C::elem_t E;
 	static_for<0, K/2, 1>([&](auto Pp) {
@@ -401,7 +401,7 @@ template<int Q, int COLL, int ST, bool VF, int K> FX3D_HD void collide_tile(cons
 			}
 			F2 rhon, uxn, uyn, uzn;
 			const bool both = act_lo && act_hi;
-			if constexpr(pipe_collide_mode<Q, ST>()==2) {
+			if constexpr(!SG && pipe_collide_mode<Q, ST>()==2) {
 			// populations are unpacked on demand and the results packed straight into the slot they stream out through:
 			// store_f() sends fhn[i] to the neighbour-side slot (A[i+1]) and fhn[i+1] to the local slot (A[i])
 			auto get = [&](auto I) { return A[I.value].template get_pair<p>(); };
@@ -422,7 +422,8 @@ template<int Q, int COLL, int ST, bool VF, int K> FX3D_HD void collide_tile(cons
 			} else {
 			F2 f[Q];
 			static_for<0, Q, 1>([&](auto I) { f[I] = A[I].template get_pair<p>(); });
-			if constexpr(pipe_collide_mode<Q, ST>()==1) collide_cell_fused<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+			if constexpr(SG) collide_cell<Q, COLL, VF, F2, true>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn); // SUBGRID: all populations and equilibria at once
+			else if constexpr(pipe_collide_mode<Q, ST>()==1) collide_cell_fused<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
 			else collide_cell<Q, COLL, VF, F2>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
 			if(both) {
 				A[0].template set_pair<p>(f[0]);
@@ -629,7 +630,7 @@ FX3D_HD void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "m
 FX3D_HD void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); } // my shared-memory writes become visible to the bulk-copy engine
 #endif
 
-template<int Q, int COLL, int ST, bool VF, int ODD>
+template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false>
 __global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_collide_tma(const Lattice L, const Region R, const uint32_t tiles_y) {
 	constexpr int K = 4, S = FX3D_TMA_STAGES;
 	constexpr uint32_t odd = (uint32_t)ODD;
@@ -734,7 +735,7 @@ __global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_coll
 			// refill the other stage(s) now rather than at the top of the iteration: the bulk stores issued from it at the end of the
 			// previous iteration have had the stream-in to finish reading it, so the copying threads rarely wait here
 			if(z+(uint32_t)(S-1)<ze) { if(copier) bulk_wait_read(); load_tile(yb, z+(uint32_t)(S-1), (it+(uint32_t)(S-1))%(uint32_t)S); }
-			collide_tile<Q, COLL, ST, VF, K>(L, A, flags4, x0, y, z);
+			collide_tile<Q, COLL, ST, VF, K, SG>(L, A, flags4, x0, y, z);
 			// ---- stream out into the same row buffers ----
 			A[0].store(reinterpret_cast<E*>(sb+tid*VB));
 			static_for<1, Q, 2>([&](auto I) {
@@ -1173,7 +1174,7 @@ FX3D_HD bool region_cell(const Region& R, uint32_t& x, uint32_t& y, uint32_t& z)
 }
 
 // general stream_collide (any grid size): one thread per cell, scalar accesses -- the reference's own access pattern
-template<int Q, int COLL, int ST, bool VF>
+template<int Q, int COLL, int ST, bool VF, bool SG = false>
 __global__ void __launch_bounds__(128) k_stream_collide_v1(const Lattice L, const Region R) {
 	uint32_t x, y, z;
 	if(!region_cell(R, x, y, z)) return;
@@ -1187,7 +1188,7 @@ __global__ void __launch_bounds__(128) k_stream_collide_v1(const Lattice L, cons
 	float rho_e = 1.0f, ux_e = 0.0f, uy_e = 0.0f, uz_e = 0.0f;
 	if(is_e) { rho_e = L.rho[n]; ux_e = L.u[n]; uy_e = L.u[N+n]; uz_e = L.u[2ull*N+n]; }
 	float rhon, uxn, uyn, uzn;
-	collide_cell<Q, COLL, VF, float>(f, 1.0f, 1.0f, is_e, false, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+	collide_cell<Q, COLL, VF, float, SG>(f, 1.0f, 1.0f, is_e, false, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
 	if(L.upd!=0u && !is_e) { L.rho[n] = rhon; L.u[n] = uxn; L.u[N+n] = uyn; L.u[2ull*N+n] = uzn; }
 	io.push(L, L.odd, f);
 }

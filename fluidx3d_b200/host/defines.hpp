@@ -23,13 +23,13 @@
 //#define VOLUME_FORCE
 //#define EQUILIBRIUM_BOUNDARIES
 //#define UPDATE_FIELDS
+//#define SUBGRID // Smagorinsky-Lilly subgrid turbulence model (runs the whole-row bulk-copy kernel or the general kernel)
 
 // extensions of the reference that this build does not provide
 //#define FORCE_FIELD
 //#define MOVING_BOUNDARIES
 //#define SURFACE
 //#define TEMPERATURE
-//#define SUBGRID
 //#define PARTICLES
 //#define INTERACTIVE_GRAPHICS
 //#define INTERACTIVE_GRAPHICS_ASCII
@@ -69,8 +69,8 @@
 #undef GRAPHICS
 #endif
 
-#if defined(FORCE_FIELD) || defined(MOVING_BOUNDARIES) || defined(SURFACE) || defined(TEMPERATURE) || defined(SUBGRID) || defined(PARTICLES)
-#error "FORCE_FIELD / MOVING_BOUNDARIES / SURFACE / TEMPERATURE / SUBGRID / PARTICLES are not part of the B200 hot-path build (see DESIGN.md, out of scope)"
+#if defined(FORCE_FIELD) || defined(MOVING_BOUNDARIES) || defined(SURFACE) || defined(TEMPERATURE) || defined(PARTICLES)
+#error "FORCE_FIELD / MOVING_BOUNDARIES / SURFACE / TEMPERATURE / PARTICLES are not part of the B200 hot-path build (see DESIGN.md, out of scope)"
 #endif
 #if defined(INTERACTIVE_GRAPHICS) || defined(INTERACTIVE_GRAPHICS_ASCII) || defined(GRAPHICS)
 #error "graphics are not part of the B200 hot-path build (see DESIGN.md, out of scope)"

@@ -34,6 +34,9 @@ static uint extension_mask() {
 #ifdef UPDATE_FIELDS
 	m |= FX3D_UPDATE_FIELDS;
 #endif
+#ifdef SUBGRID
+	m |= FX3D_SUBGRID;
+#endif
 	return m;
 }
 

@@ -17,7 +17,7 @@ The C++ twin of this file (what setup.cpp scenes compile against) is fluidx3d_b2
 import ctypes as C
 import numpy as np
 from . import capi
-from .capi import (FP32, FP16S, FP16C, SRT, TRT, VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, TYPE_S, TYPE_E,
+from .capi import (FP32, FP16S, FP16C, SRT, TRT, VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID, TYPE_S, TYPE_E,
                    REGION_ALL, REGION_SHELL, REGION_INTERIOR, Fx3dError)
 
 max_ulong = 2 ** 64 - 1

@@ -29,7 +29,8 @@ typedef enum fx3d_status {
 
 enum { FX3D_FP32 = 0, FX3D_FP16S = 1, FX3D_FP16C = 2 };                 /* defines.hpp: (none) | FP16S | FP16C */
 enum { FX3D_SRT = 0, FX3D_TRT = 1 };                                    /* defines.hpp: SRT | TRT */
-enum { FX3D_VOLUME_FORCE = 1, FX3D_EQUILIBRIUM_BOUNDARIES = 2, FX3D_UPDATE_FIELDS = 4 }; /* defines.hpp extension flags on the path */
+enum { FX3D_VOLUME_FORCE = 1, FX3D_EQUILIBRIUM_BOUNDARIES = 2, FX3D_UPDATE_FIELDS = 4, FX3D_SUBGRID = 8 }; /* defines.hpp extension flags on the path;
+ * SUBGRID (Smagorinsky-Lilly, kernel.cpp:1579-1593) is the first widening beyond the north_star feature set */
 enum { FX3D_REGION_ALL = 0, FX3D_REGION_SHELL = 1, FX3D_REGION_INTERIOR = 2 };
 
 const char* fx3d_last_error(void); /* thread-local, valid until the next failing call on this thread */
@@ -87,7 +88,7 @@ typedef struct fx3d_lattice {
 	uint32_t velocity_set;     /* 19 or 27 */
 	uint32_t collision;        /* FX3D_SRT | FX3D_TRT */
 	uint32_t storage;          /* FX3D_FP32 | FX3D_FP16S | FX3D_FP16C */
-	uint32_t features;         /* FX3D_VOLUME_FORCE | FX3D_EQUILIBRIUM_BOUNDARIES | FX3D_UPDATE_FIELDS */
+	uint32_t features;         /* FX3D_VOLUME_FORCE | FX3D_EQUILIBRIUM_BOUNDARIES | FX3D_UPDATE_FIELDS | FX3D_SUBGRID */
 	float w;                   /* def_w = 1/tau exactly as the device must see it (see fx3d_relaxation_rate) */
 	void* fi;                  /* DDFs, device only, fx3d_fi_bytes() bytes, library-private padded SoA layout */
 	float* rho;                /* [N] */

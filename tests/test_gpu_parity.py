@@ -78,6 +78,22 @@ def test_fields_bit_exact_medium_100_steps(fx, v, variant):
             assert np.array_equal(bits(a), bits(b)), dims
 
 
+SG_CASES = [((19, SRT, FP32, 8), (9, 7, 5), (1, 1, 1)), ((19, TRT, FP16S, 11), (12, 6, 6), (2, 1, 2)), ((27, SRT, FP16C, 8), (10, 6, 4), (1, 1, 1)),
+            ((19, SRT, FP16S, 8), (64, 8, 6), (1, 1, 1)), ((19, TRT, FP32, 11), (128, 4, 4), (1, 2, 1)), ((27, TRT, FP16C, 9), (32, 16, 3), (1, 1, 1)),
+            ((19, SRT, FP32, 8), (256, 8, 4), (1, 1, 2))]
+
+
+@pytest.mark.parametrize("v,dims,D", SG_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in SG_CASES])
+def test_subgrid_bit_exact(fx, v, dims, D):
+    """SUBGRID (Smagorinsky-Lilly, feature bit 3; the first widening beyond the north_star feature set): general kernel on ragged
+    grids, whole-row bulk-copy kernel where eligible; low viscosity so that the eddy term changes the relaxation rate"""
+    f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
+    for steps in (1, 2, 9):
+        got, want = product(fx, v, dims, D, steps, f, 0, nu=0.002), oracle(v, dims, D, steps, f, nu=0.002)
+        for a, b in zip(got, want):
+            assert np.array_equal(bits(a), bits(b)), steps
+
+
 SEG_CASES = [((19, SRT, FP16S, 0), (1024, 4, 3), (1, 1, 1)), ((19, SRT, FP16S, 0), (256, 8, 6), (2, 1, 1)), ((19, TRT, FP32, 3), (256, 8, 4), (2, 2, 1)),
              ((27, SRT, FP16C, 2), (1024, 2, 2), (1, 1, 1)), ((19, SRT, FP32, 1), (2048, 3, 2), (1, 1, 2)), ((27, TRT, FP16S, 3), (512, 8, 2), (4, 2, 1)),
              ((19, SRT, FP16C, 0), (1024, 8, 8), (2, 2, 2))]

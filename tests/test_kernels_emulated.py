@@ -112,6 +112,21 @@ def test_emulated_hybrid_kernel_matches_oracle(emul, v, dims, D):
     assert after[5] > before[5] and after[:5] == before[:5], "the hybrid kernel must be the one that ran"
 
 
+SG_CASES = [((19, SRT, FP32, 8), (9, 7, 5), (1, 1, 1)), ((19, TRT, FP16S, 11), (12, 6, 6), (2, 1, 2)), ((27, SRT, FP16C, 8), (10, 6, 4), (1, 1, 1)),  # general kernel
+            ((19, SRT, FP16S, 8), (32, 16, 4), (1, 1, 1)), ((19, TRT, FP32, 11), (64, 8, 4), (1, 2, 1)), ((27, TRT, FP16C, 9), (32, 16, 3), (1, 1, 1))]    # whole-row bulk-copy kernel
+
+
+@pytest.mark.parametrize("v,dims,D", SG_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in SG_CASES])
+def test_emulated_subgrid_matches_oracle(emul, v, dims, D):
+    """SUBGRID (feature bit 3, Smagorinsky-Lilly): per-cell relaxation rate from the non-equilibrium stress tensor, in scalar
+    arithmetic (general kernel) and in packed lanes at the FP16S working scale (bulk-copy kernel); low viscosity so it matters"""
+    f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
+    for steps in (1, 4):
+        got, want = product(emul, v, dims, D, steps, f, 0, nu=0.002), oracle(v, dims, D, steps, f, nu=0.002)
+        for a, b in zip(got, want):
+            assert np.array_equal(bits(a), bits(b))
+
+
 @pytest.mark.parametrize("variant", [1, 4, 8], ids=["general", "vector4", "pipelined"])
 def test_shell_plus_interior_equals_all(emul, variant):
     # FX3D_REGION_SHELL followed by FX3D_REGION_INTERIOR must cover every non-halo cell exactly once
