@@ -401,7 +401,7 @@ template<int Q, int COLL, int ST, bool VF, int K, bool SG = false> FX3D_HD void 
 			}
 			F2 rhon, uxn, uyn, uzn;
 			const bool both = act_lo && act_hi;
-			if constexpr(!SG && pipe_collide_mode<Q, ST>()==2) {
+			if constexpr(pipe_collide_mode<Q, ST>()==2) {
 			// populations are unpacked on demand and the results packed straight into the slot they stream out through:
 			// store_f() sends fhn[i] to the neighbour-side slot (A[i+1]) and fhn[i+1] to the local slot (A[i])
 			auto get = [&](auto I) { return A[I.value].template get_pair<p>(); };
@@ -418,7 +418,7 @@ template<int Q, int COLL, int ST, bool VF, int K, bool SG = false> FX3D_HD void 
 				A[dst].template set_masked<p>(v, em);
 			};
 			// within a direction pair both members are read before either is written, so the in-place swap is safe
-			collide_cell_stream<Q, COLL, VF, F2>(get, put, put_e, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+			collide_cell_stream<Q, COLL, VF, F2, SG>(get, put, put_e, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
 			} else {
 			F2 f[Q];
 			static_for<0, Q, 1>([&](auto I) { f[I] = A[I].template get_pair<p>(); });
