@@ -22,6 +22,8 @@
 #define TYPE_S 0x01u
 #define TYPE_E 0x02u
 #define TYPE_BO 0x03u  /* src/lbm.cpp:393-408 */
+#define TYPE_MS 0x03u  /* cell next to a moving solid boundary */
+#define TYPE_T 0x04u
 
 static int g_threads = 0;
 void orc_set_threads(int n) { g_threads = n; }
@@ -247,16 +249,57 @@ static void forcing_terms(const orc_grid* g, float ux, float uy, float uz, float
 
 static inline float clamp_c(float x) { const float c = 0.57735027f; return fminf(fmaxf(x, -c), c); } /* OpenCL clamp(), def_c src/lbm.cpp:366 */
 
-/* ---- initialize: src/kernel.cpp:1358-1430 (non-MOVING_BOUNDARIES, non-SURFACE, non-TEMPERATURE build) ---- */
-void orc_initialize(const orc_grid* g, void* fi, const float* rho, float* u, uint8_t* flags) {
+/* is any neighbour of n a TYPE_S cell with non-zero velocity? (:1381-1385, :1442-1446) */
+static int next_to_moving_solid(const orc_grid* g, const uint64_t* j, const float* u, const uint8_t* flags) {
+	const uint64_t N = cells_of(g);
+	int r = 0;
+	for(uint32_t i=1u; i<g->Q; i++) r = r || ((flags[j[i]]&TYPE_BO)==TYPE_S && (u[j[i]]!=0.0f || u[N+j[i]]!=0.0f || u[2ull*N+j[i]]!=0.0f));
+	return r;
+}
+/* ---- apply_moving_boundaries: src/kernel.cpp:1104-1113 (Dirichlet velocity boundary, rho_wall = 1) ---- */
+static void apply_moving_boundaries(const orc_grid* g, float* fhn, const uint64_t* j, const float* u, const uint8_t* flags) {
+	const uint64_t N = cells_of(g);
+	const weights_t k = weights_of(g->Q);
+	for(uint32_t i=1u; i<g->Q; i+=2u) {
+		const float w6 = -6.0f*weight_of(&k, i);
+		uint64_t ji = j[i+1u];
+		if((flags[ji]&TYPE_BO)==TYPE_S) fhn[i   ] = fmaf(w6, (float)EX[i+1u]*u[ji]+(float)EY[i+1u]*u[N+ji]+(float)EZ[i+1u]*u[2ull*N+ji], fhn[i   ]);
+		ji = j[i];
+		if((flags[ji]&TYPE_BO)==TYPE_S) fhn[i+1u] = fmaf(w6, (float)EX[i   ]*u[ji]+(float)EY[i   ]*u[N+ji]+(float)EZ[i   ]*u[2ull*N+ji], fhn[i+1u]);
+	}
+}
+/* ---- update_moving_boundaries: src/kernel.cpp:1432-1450 ---- */
+void orc_update_moving_boundaries(const orc_grid* g, const float* u, uint8_t* flags) {
 	const uint64_t N = cells_of(g);
 	ORC_PARALLEL_FOR
 	for(uint64_t n=0ull; n<N; n++) {
 		const xyz_t c = coords_of(g, n);
 		if(halo_cell(g, c)) continue;
-		if((flags[n]&TYPE_BO)==TYPE_S) { u[n] = 0.0f; u[N+n] = 0.0f; u[2ull*N+n] = 0.0f; } /* :1376-1379 */
+		const uint8_t fn = flags[n], fb = fn&TYPE_BO;
+		if(fb==TYPE_S || fb==TYPE_E || (fn&TYPE_T)) continue;
+		uint64_t j[QMAX];
+		neighbours_of(g, n, j);
+		flags[n] = next_to_moving_solid(g, j, u, flags) ? (uint8_t)(fn|TYPE_MS) : (uint8_t)(fn&~TYPE_MS);
+	}
+}
+
+/* ---- initialize: src/kernel.cpp:1358-1430 (non-SURFACE, non-TEMPERATURE build) ---- */
+void orc_initialize(const orc_grid* g, void* fi, const float* rho, float* u, uint8_t* flags) {
+	const uint64_t N = cells_of(g);
+	const int mb = (g->features&ORC_MOVING_BOUNDARIES)!=0u;
+	ORC_PARALLEL_FOR
+	for(uint64_t n=0ull; n<N; n++) {
+		const xyz_t c = coords_of(g, n);
+		if(halo_cell(g, c)) continue;
 		uint64_t j[QMAX]; float feq[QMAX];
 		neighbours_of(g, n, j);
+		const uint8_t fb = flags[n]&TYPE_BO;
+		if(!mb) { if(fb==TYPE_S) { u[n] = 0.0f; u[N+n] = 0.0f; u[2ull*N+n] = 0.0f; } } /* :1376-1379 */
+		else if(fb==TYPE_S) { /* :1374-1377: only solids enclosed by solids lose their velocity */
+			int only_s = 1;
+			for(uint32_t i=1u; i<g->Q; i++) only_s = only_s && (flags[j[i]]&TYPE_BO)==TYPE_S;
+			if(only_s) { u[n] = 0.0f; u[N+n] = 0.0f; u[2ull*N+n] = 0.0f; }
+		} else if(fb!=TYPE_E) flags[n] = next_to_moving_solid(g, j, u, flags) ? (uint8_t)(flags[n]|TYPE_MS) : (uint8_t)(flags[n]&~TYPE_MS); /* :1380-1386 */
 		equilibrium(g, rho[n], u[n], u[N+n], u[2ull*N+n], feq);
 		push_ddfs(g, n, feq, fi, j, 1ull); /* :1429: odd-step layout */
 	}
@@ -273,6 +316,7 @@ static int cell_front(const orc_grid* g, const void* fi, const float* rho, const
 	*flag_bo = fb;
 	neighbours_of(g, n, j);
 	pull_ddfs(g, n, fhn, fi, j, t);
+	if((g->features&ORC_MOVING_BOUNDARIES) && fb==TYPE_MS) apply_moving_boundaries(g, fhn, j, u, flags); /* :1477-1479 / :1813-1815 */
 	if(allow_preset && (g->features&ORC_EQUILIBRIUM_BOUNDARIES) && fb==TYPE_E) { /* :1482-1493 */
 		*rhon = rho[n]; *uxn = u[n]; *uyn = u[N+n]; *uzn = u[2ull*N+n];
 	} else moments(g, fhn, rhon, uxn, uyn, uzn);

@@ -24,7 +24,7 @@ extern "C" {
 
 enum { ORC_FP32 = 0, ORC_FP16S = 1, ORC_FP16C = 2 };
 enum { ORC_SRT = 0, ORC_TRT = 1 };
-enum { ORC_VOLUME_FORCE = 1u, ORC_EQUILIBRIUM_BOUNDARIES = 2u, ORC_UPDATE_FIELDS = 4u, ORC_SUBGRID = 8u };
+enum { ORC_VOLUME_FORCE = 1u, ORC_EQUILIBRIUM_BOUNDARIES = 2u, ORC_UPDATE_FIELDS = 4u, ORC_SUBGRID = 8u, ORC_MOVING_BOUNDARIES = 16u };
 
 /* One LBM_Domain worth of compile-time constants of the reference (src/lbm.cpp:334-425), made run-time. */
 typedef struct orc_grid {
@@ -33,7 +33,7 @@ typedef struct orc_grid {
 	uint32_t Q;            /* velocity set: 19 or 27 */
 	uint32_t collision;    /* ORC_SRT | ORC_TRT */
 	uint32_t storage;      /* ORC_FP32 | ORC_FP16S | ORC_FP16C */
-	uint32_t features;     /* ORC_VOLUME_FORCE | ORC_EQUILIBRIUM_BOUNDARIES | ORC_UPDATE_FIELDS | ORC_SUBGRID */
+	uint32_t features;     /* ORC_VOLUME_FORCE | ORC_EQUILIBRIUM_BOUNDARIES | ORC_UPDATE_FIELDS | ORC_SUBGRID | ORC_MOVING_BOUNDARIES */
 	float w;               /* relaxation rate def_w = 1/tau, as the device sees it */
 } orc_grid;
 
@@ -51,6 +51,8 @@ int   orc_float_to_string(float x, char* out, int cap);
 void orc_initialize(const orc_grid* g, void* fi, const float* rho, float* u, uint8_t* flags);
 void orc_stream_collide(const orc_grid* g, void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t, float fx, float fy, float fz);
 void orc_update_fields(const orc_grid* g, const void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t, float fx, float fy, float fz);
+/* MOVING_BOUNDARIES: mark / unmark the cells next to TYPE_S cells with non-zero velocity as TYPE_MS (src/kernel.cpp:1432-1450) */
+void orc_update_moving_boundaries(const orc_grid* g, const float* u, uint8_t* flags);
 
 /* halo transfer kernels; axis 0|1|2; buffers hold transfers*A elements of the storage type (fi) or 17*A bytes */
 uint32_t orc_transfers(const orc_grid* g);

@@ -11,7 +11,7 @@ plus a tiny NDRange driver.
 
 usage: build_ref.py [--reference /root/reference] [--variants q19_srt_fp32_f0,...]
 Variant name: q<19|27>_<srt|trt>_<fp32|fp16s|fp16c>_f<mask>  (mask bit0 VOLUME_FORCE, bit1 EQUILIBRIUM_BOUNDARIES,
-bit2 UPDATE_FIELDS, bit3 SUBGRID)
+bit2 UPDATE_FIELDS, bit3 SUBGRID, bit4 MOVING_BOUNDARIES)
 """
 import argparse, os, re, subprocess, sys
 from concurrent.futures import ThreadPoolExecutor
@@ -25,13 +25,14 @@ DEFAULT_VARIANTS = [
     "q19_trt_fp32_f0", "q19_srt_fp32_f1", "q19_srt_fp32_f2", "q19_trt_fp16s_f3", "q19_srt_fp32_f4",
     "q27_srt_fp32_f0", "q27_trt_fp32_f3", "q27_srt_fp16s_f0", "q27_trt_fp16c_f3",
     "q19_srt_fp32_f8", "q19_trt_fp16s_f11", "q27_srt_fp16c_f8", "q19_srt_fp16s_f8",  # bit3: SUBGRID (first "next" row of SURVEY 8f)
+    "q19_srt_fp32_f16", "q19_trt_fp16s_f19", "q27_srt_fp16c_f18", "q19_srt_fp16s_f24",  # bit4: MOVING_BOUNDARIES
 ]
 
 # functions on the hot path; everything else in the program text is dropped
 WANTED = [
     "sq", "coordinates", "index", "is_halo", "half_to_float_custom", "float_to_half_custom", "index_f", "c", "w",
     "calculate_indices", "neighbors", "load3", "store3", "calculate_f_eq", "calculate_rho_u", "calculate_forcing_terms",
-    "load_f", "store_f", "initialize", "stream_collide", "update_fields",
+    "apply_moving_boundaries", "load_f", "store_f", "initialize", "update_moving_boundaries", "stream_collide", "update_fields",
     "get_area", "index_extract_p", "index_extract_m", "index_insert_p", "index_insert_m", "index_transfer",
     "extract_fi", "insert_fi", "transfer_extract_fi", "transfer__insert_fi",
     "extract_rho_u_flags", "insert_rho_u_flags", "transfer_extract_rho_u_flags", "transfer__insert_rho_u_flags",
@@ -67,6 +68,7 @@ def prologue(q, coll, storage, mask):
     if mask & 2: d.append("#define EQUILIBRIUM_BOUNDARIES")
     if mask & 4: d.append("#define UPDATE_FIELDS")
     if mask & 8: d.append("#define SUBGRID")
+    if mask & 16: d.append("#define MOVING_BOUNDARIES")
     return "\n".join(d) + "\n"
 
 
@@ -108,6 +110,9 @@ void ref_transfer_extract_fi(uint direction, ulong t, void* bp, void* bm, const 
 void ref_transfer_insert_fi(uint direction, ulong t, const void* bp, const void* bm, void* fi) { NDRANGE(get_area(direction), transfer__insert_fi(direction, t, (const fpxx_copy*)bp, (const fpxx_copy*)bm, (fpxx_copy*)fi)) }
 void ref_transfer_extract_rho_u_flags(uint direction, ulong t, void* bp, void* bm, const float* rho, const float* u, const uchar* flags) { NDRANGE(get_area(direction), transfer_extract_rho_u_flags(direction, t, (char*)bp, (char*)bm, rho, u, flags)) }
 void ref_transfer_insert_rho_u_flags(uint direction, ulong t, const void* bp, const void* bm, float* rho, float* u, uchar* flags) { NDRANGE(get_area(direction), transfer__insert_rho_u_flags(direction, t, (const char*)bp, (const char*)bm, rho, u, flags)) }
+#ifdef MOVING_BOUNDARIES
+void ref_update_moving_boundaries(const float* u, uchar* flags) { NDRANGE(g_N, update_moving_boundaries(u, flags)) }
+#endif
 ushort ref_float_to_half_custom(float x) { return float_to_half_custom(x); }
 float ref_half_to_float_custom(ushort x) { return half_to_float_custom(x); }
 }
@@ -127,6 +132,8 @@ def build_variant(name, cl_path):
     body = []
     for fn in WANTED:
         if fn == "calculate_forcing_terms" and not (mask & 1):
+            continue
+        if fn in ("apply_moving_boundaries", "update_moving_boundaries") and not (mask & 16):
             continue
         if fn not in funcs:
             raise SystemExit(f"{name}: function {fn} not found in the reference program text")

@@ -13,7 +13,8 @@ REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 FP32, FP16S, FP16C = 0, 1, 2
 SRT, TRT = 0, 1
-VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID = 1, 2, 4, 8
+VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID, MOVING_BOUNDARIES = 1, 2, 4, 8, 16
+TYPE_MS = 3
 TYPE_S, TYPE_E = 1, 2
 STORAGE_NAMES = {FP32: "fp32", FP16S: "fp16s", FP16C: "fp16c"}
 COLL_NAMES = {SRT: "srt", TRT: "trt"}
@@ -75,6 +76,9 @@ class OracleBackend:
     def update_fields(self, fi, rho, u, flags, t, fx=0.0, fy=0.0, fz=0.0):
         self.lib.orc_update_fields(C.byref(self.g), _p(fi), _p(rho), _p(u), _p(flags), C.c_uint64(t), C.c_float(fx), C.c_float(fy), C.c_float(fz))
 
+    def update_moving_boundaries(self, u, flags):
+        self.lib.orc_update_moving_boundaries(C.byref(self.g), _p(u), _p(flags))
+
     def extract_fi(self, axis, t, bp, bm, fi):
         self.lib.orc_transfer_extract_fi(C.byref(self.g), C.c_uint32(axis), C.c_uint64(t), _p(bp), _p(bm), _p(fi))
 
@@ -122,6 +126,9 @@ class RefBackend:
 
     def update_fields(self, fi, rho, u, flags, t, fx=0.0, fy=0.0, fz=0.0):
         self.lib.ref_update_fields(_p(fi), _p(rho), _p(u), _p(flags), C.c_uint64(t), C.c_float(fx), C.c_float(fy), C.c_float(fz))
+
+    def update_moving_boundaries(self, u, flags):
+        self.lib.ref_update_moving_boundaries(_p(u), _p(flags))
 
     def extract_fi(self, axis, t, bp, bm, fi):
         self.lib.ref_transfer_extract_fi(C.c_uint32(axis), C.c_uint64(t), _p(bp), _p(bm), _p(fi))
@@ -238,6 +245,11 @@ class HostSim:
                 self.b.stream_collide(d.fi, d.rho, d.u, d.flags, self.t, *self.f)
             self._communicate("fi")
             self.t += 1
+
+    def update_moving_boundaries(self):  # src/lbm.cpp:1018-1027 (the flags halo travels with rho and u here; both are unchanged copies)
+        for d in self.dom:
+            self.b.update_moving_boundaries(d.u, d.flags)
+        self._communicate("ruf")
 
     def update_fields(self):  # src/lbm.cpp:977-980
         for d in self.dom:

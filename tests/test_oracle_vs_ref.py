@@ -7,7 +7,8 @@ from helpers import (OracleBackend, RefBackend, HostSim, scenario, load_scenario
 
 VARIANTS = [(19, SRT, FP32, 0), (19, SRT, FP16S, 0), (19, SRT, FP16C, 0), (19, TRT, FP32, 0), (19, SRT, FP32, 1), (19, SRT, FP32, 2),
             (19, TRT, FP16S, 3), (19, SRT, FP32, 4), (27, SRT, FP32, 0), (27, TRT, FP32, 3), (27, SRT, FP16S, 0), (27, TRT, FP16C, 3),
-            (19, SRT, FP32, 8), (19, TRT, FP16S, 11), (27, SRT, FP16C, 8), (19, SRT, FP16S, 8)]  # feature bit 3: SUBGRID
+            (19, SRT, FP32, 8), (19, TRT, FP16S, 11), (27, SRT, FP16C, 8), (19, SRT, FP16S, 8),  # feature bit 3: SUBGRID
+            (19, SRT, FP32, 16), (19, TRT, FP16S, 19), (27, SRT, FP16C, 18), (19, SRT, FP16S, 24)]  # feature bit 4: MOVING_BOUNDARIES
 
 
 def bits(a):
@@ -21,6 +22,17 @@ def run(cls, v, dims, D, steps, seed):
     rho, u, flags = scenario(sim.Nx, sim.Ny, sim.Nz, seed=seed, eq_frac=0.03 if feat & 2 else 0.0)
     load_scenario(sim, rho, u, flags)
     sim.run(steps)
+    if feat & 16:  # MOVING_BOUNDARIES: the boundaries change speed (one stops, one starts), the marks are refreshed, the run continues
+        for d in sim.dom:
+            solid = (d.flags & 3) == 1
+            idx = np.flatnonzero(solid)
+            N = d.flags.size
+            if idx.size > 1:
+                for a in range(3): d.u[a * N + idx[0]] = 0.0
+                d.u[idx[1]] = np.float32(0.02)
+        sim._communicate("ruf")
+        sim.update_moving_boundaries()
+        sim.run(2)
     return list(sim.fields()) + [d.fi for d in sim.dom]
 
 
