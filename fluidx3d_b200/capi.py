@@ -8,7 +8,7 @@ DEFAULT_LIB = os.environ.get("FX3D_LIB", os.path.join(HERE, "libfx3d_cuda.so")) 
 
 FP32, FP16S, FP16C = 0, 1, 2
 SRT, TRT = 0, 1
-VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID = 1, 2, 4, 8
+VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID, MOVING_BOUNDARIES = 1, 2, 4, 8, 16
 REGION_ALL, REGION_SHELL, REGION_INTERIOR = 0, 1, 2
 TYPE_S, TYPE_E = 0x01, 0x02  # src/defines.hpp:52-53
 OK, ERR_NO_DEVICE, ERR_INVALID, ERR_OUT_OF_MEMORY, ERR_CUDA, ERR_TIMEOUT = 0, -1, -2, -3, -4, -5
@@ -65,6 +65,7 @@ _SIGS = {
     "fx3d_relaxation_rate": (_F, [_F], False),
     "fx3d_bytes_per_cell_per_step": (_U32, [_LP], False),
     "fx3d_initialize": (_I, [_LP, _VP], True),
+    "fx3d_update_moving_boundaries": (_I, [_LP, _VP], True),
     "fx3d_stream_collide_launches": (_I, [_I, C.POINTER(_U64)], True),
     "fx3d_set_interior_reserve": (_I, [_I], True),
     "fx3d_stream_collide": (_I, [_LP, _U64, _F, _F, _F, _I, _VP], True),

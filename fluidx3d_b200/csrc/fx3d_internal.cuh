@@ -48,6 +48,7 @@ inline bool make_lattice(const fx3d_lattice* in, uint64_t t, float fx, float fy,
 	L.odd = (uint32_t)(t&1ull);
 	L.eb = (in->features&FX3D_EQUILIBRIUM_BOUNDARIES) ? 1u : 0u;
 	L.upd = (in->features&FX3D_UPDATE_FIELDS) ? 1u : 0u;
+	L.mb = (in->features&FX3D_MOVING_BOUNDARIES) ? 1u : 0u;
 	return true;
 }
 inline size_t elem_bytes(uint32_t storage) { return storage==FX3D_FP32 ? 4u : 2u; }

@@ -67,6 +67,17 @@ static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int re
 	}
 	std::vector<Region> regs;
 	const bool vf = (lat->features&FX3D_VOLUME_FORCE)!=0u;
+	if(lat->features&FX3D_MOVING_BOUNDARIES) { // general kernel only (with or without SUBGRID)
+		const int reserve = 0;
+		const bool sg = (lat->features&FX3D_SUBGRID)!=0u;
+		regions_of(L, region, 1u, regs);
+		for(const Region& R : regs) {
+			int rc;
+			FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, 1, (int)lat->collision, vf, stream, reserve, sg); })
+			if(rc!=FX3D_OK) return rc;
+		}
+		return FX3D_OK;
+	}
 	if(lat->features&FX3D_SUBGRID) { // whole-row bulk-copy kernel where eligible, else the general kernel (any size)
 		const int reserve = region==FX3D_REGION_INTERIOR ? g_interior_reserve.load() : 0;
 		if(want!=1 && inner%4u==0u) {
@@ -189,6 +200,17 @@ int fx3d_update_fields(const fx3d_lattice* lat, uint64_t t, float fx, float fy, 
 	if(lat->features&FX3D_VOLUME_FORCE) { FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { FX3D_LAUNCH((k_update_fields<Q, ST, true>), g, b, stream, L, R); }) }
 	else { FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { FX3D_LAUNCH((k_update_fields<Q, ST, false>), g, b, stream, L, R); }) }
 	return check_launch("update_fields");
+}
+
+int fx3d_update_moving_boundaries(const fx3d_lattice* lat, fx3d_stream stream) {
+	Lattice L;
+	if(!make_lattice(lat, 0ull, 0.0f, 0.0f, 0.0f, L)) return FX3D_ERR_INVALID;
+	if(!(lat->features&FX3D_MOVING_BOUNDARIES)) { set_error("update_moving_boundaries needs the MOVING_BOUNDARIES feature"); return FX3D_ERR_INVALID; }
+	if(int rc = use_device(lat->device)) return rc;
+	const Region R = all_cells(L);
+	const dim3 b = cell_block(R.g1-R.g0), g = cell_grid(R, b);
+	if(lat->velocity_set==19u) FX3D_LAUNCH((k_update_moving_boundaries<19>), g, b, stream, L, R); else FX3D_LAUNCH((k_update_moving_boundaries<27>), g, b, stream, L, R);
+	return check_launch("update_moving_boundaries");
 }
 
 static bool face_setup(const fx3d_lattice* lat, uint32_t axis, uint64_t t, Lattice& L, dim3& g, dim3& b) {

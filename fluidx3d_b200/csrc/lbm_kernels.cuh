@@ -46,6 +46,7 @@ struct Lattice { // one LBM_Domain as the device sees it (passed by value)
 	uint32_t odd;        // t&1
 	uint32_t eb;         // EQUILIBRIUM_BOUNDARIES enabled
 	uint32_t upd;        // UPDATE_FIELDS enabled
+	uint32_t mb;         // MOVING_BOUNDARIES enabled (general kernels only)
 };
 struct Region { uint32_t g0, g1, y0, y1, z0, z1; }; // x-group range [g0,g1), cell ranges in y and z
 
@@ -1173,6 +1174,42 @@ FX3D_HD bool region_cell(const Region& R, uint32_t& x, uint32_t& y, uint32_t& z)
 	return x<R.g1 && y<R.y1;
 }
 
+// ---- MOVING_BOUNDARIES, general kernels only ----
+// linear index of the neighbour of (x,y,z) in direction I
+template<int I> FX3D_HD uint64_t neighbour_lin(const Lattice& L, uint32_t x, uint32_t y, uint32_t z) { return lin(L, step<dir_x(I)>(x, L.Nx), step<dir_y(I)>(y, L.Ny), step<dir_z(I)>(z, L.Nz)); }
+// is any neighbour a TYPE_S cell with non-zero velocity? (src/kernel.cpp:1381-1385, :1442-1446)
+template<int Q> FX3D_HD bool next_to_moving_solid(const Lattice& L, uint32_t x, uint32_t y, uint32_t z) {
+	const uint64_t N = cells(L);
+	bool r = false;
+	static_for<1, Q, 1>([&](auto I) {
+		const uint64_t j = neighbour_lin<I.value>(L, x, y, z);
+		r = r || ((L.flags[j]&TYPE_BO)==TYPE_S && (L.u[j]!=0.0f || L.u[N+j]!=0.0f || L.u[2ull*N+j]!=0.0f));
+	});
+	return r;
+}
+// apply_moving_boundaries, src/kernel.cpp:1104-1113: Dirichlet velocity correction of the streamed-in populations of a TYPE_MS cell
+template<int Q> FX3D_HD void apply_moving_boundaries(const Lattice& L, uint32_t x, uint32_t y, uint32_t z, float (&f)[Q]) {
+	const uint64_t N = cells(L);
+	static_for<1, Q, 2>([&](auto I) {
+		constexpr int i = I;
+		const float w6 = -6.0f*weight<Q>(i);
+		uint64_t j = neighbour_lin<i+1>(L, x, y, z);
+		if((L.flags[j]&TYPE_BO)==TYPE_S) f[i  ] = fmaf(w6, (float)dir_x(i+1)*L.u[j]+(float)dir_y(i+1)*L.u[N+j]+(float)dir_z(i+1)*L.u[2ull*N+j], f[i  ]);
+		j = neighbour_lin<i>(L, x, y, z);
+		if((L.flags[j]&TYPE_BO)==TYPE_S) f[i+1] = fmaf(w6, (float)dir_x(i  )*L.u[j]+(float)dir_y(i  )*L.u[N+j]+(float)dir_z(i  )*L.u[2ull*N+j], f[i+1]);
+	});
+}
+// update_moving_boundaries, src/kernel.cpp:1432-1450
+template<int Q>
+__global__ void __launch_bounds__(128) k_update_moving_boundaries(const Lattice L, const Region R) {
+	uint32_t x, y, z;
+	if(!region_cell(R, x, y, z)) return;
+	const uint64_t n = lin(L, x, y, z);
+	const uint32_t fn = L.flags[n], fb = fn&TYPE_BO;
+	if(fb==TYPE_S || fb==TYPE_E || (fn&TYPE_T)) return;
+	L.flags[n] = (uint8_t)(next_to_moving_solid<Q>(L, x, y, z) ? fn|TYPE_MS : fn&~TYPE_MS);
+}
+
 // general stream_collide (any grid size): one thread per cell, scalar accesses -- the reference's own access pattern
 template<int Q, int COLL, int ST, bool VF, bool SG = false>
 __global__ void __launch_bounds__(128) k_stream_collide_v1(const Lattice L, const Region R) {
@@ -1184,6 +1221,7 @@ __global__ void __launch_bounds__(128) k_stream_collide_v1(const Lattice L, cons
 	CellIO<Q, ST> io; io.locate(L, x, y, z);
 	float f[Q];
 	io.pull(L, L.odd, f);
+	if(L.mb!=0u && fb==TYPE_MS) apply_moving_boundaries<Q>(L, x, y, z, f); // :1477-1479
 	const bool is_e = L.eb!=0u && fb==TYPE_E;
 	float rho_e = 1.0f, ux_e = 0.0f, uy_e = 0.0f, uz_e = 0.0f;
 	if(is_e) { rho_e = L.rho[n]; ux_e = L.u[n]; uy_e = L.u[N+n]; uz_e = L.u[2ull*N+n]; }
@@ -1199,7 +1237,13 @@ __global__ void __launch_bounds__(128) k_initialize(const Lattice L, const Regio
 	uint32_t x, y, z;
 	if(!region_cell(R, x, y, z)) return;
 	const uint64_t n = lin(L, x, y, z), N = cells(L);
-	if((L.flags[n]&TYPE_BO)==TYPE_S) { L.u[n] = 0.0f; L.u[N+n] = 0.0f; L.u[2ull*N+n] = 0.0f; }
+	const uint32_t fn = L.flags[n], fb = fn&TYPE_BO;
+	if(L.mb==0u) { if(fb==TYPE_S) { L.u[n] = 0.0f; L.u[N+n] = 0.0f; L.u[2ull*N+n] = 0.0f; } }
+	else if(fb==TYPE_S) { // MOVING_BOUNDARIES (:1374-1386): only solids enclosed by solids lose their velocity ...
+		bool only_s = true;
+		static_for<1, Q, 1>([&](auto I) { only_s = only_s && (L.flags[neighbour_lin<I.value>(L, x, y, z)]&TYPE_BO)==TYPE_S; });
+		if(only_s) { L.u[n] = 0.0f; L.u[N+n] = 0.0f; L.u[2ull*N+n] = 0.0f; }
+	} else if(fb!=TYPE_E) L.flags[n] = (uint8_t)(next_to_moving_solid<Q>(L, x, y, z) ? fn|TYPE_MS : fn&~TYPE_MS); // ... and cells next to a moving solid are marked
 	float feq[Q];
 	equilibrium<Q, float>(L.rho[n], L.u[n], L.u[N+n], L.u[2ull*N+n], 1.0f, feq);
 	CellIO<Q, ST> io; io.locate(L, x, y, z);
@@ -1217,6 +1261,7 @@ __global__ void __launch_bounds__(128) k_update_fields(const Lattice L, const Re
 	CellIO<Q, ST> io; io.locate(L, x, y, z);
 	float f[Q];
 	io.pull(L, L.odd, f);
+	if(L.mb!=0u && fb==TYPE_MS) apply_moving_boundaries<Q>(L, x, y, z, f); // :1813-1815
 	float rhon, uxn, uyn, uzn;
 	fields_of_cell<Q, VF>(f, L.fx, L.fy, L.fz, rhon, uxn, uyn, uzn);
 	if(L.eb!=0u && fb==TYPE_E) return;

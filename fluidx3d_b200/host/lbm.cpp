@@ -37,6 +37,9 @@ static uint extension_mask() {
 #ifdef SUBGRID
 	m |= FX3D_SUBGRID;
 #endif
+#ifdef MOVING_BOUNDARIES
+	m |= FX3D_MOVING_BOUNDARIES;
+#endif
 	return m;
 }
 
@@ -89,6 +92,9 @@ uint LBM_Domain::get_velocity_set() const { return velocity_set; }
 void LBM_Domain::enqueue_initialize() { fx3d_check(fx3d_initialize(&lattice, device.get_stream()), "initialize"); }
 void LBM_Domain::enqueue_stream_collide(const int region) { fx3d_check(fx3d_stream_collide(&lattice, t, fx, fy, fz, region, device.get_stream()), "stream_collide"); }
 void LBM_Domain::enqueue_run_steps(const ulong steps) { fx3d_check(fx3d_run_steps(&lattice, t, steps, fx, fy, fz, device.get_stream()), "stream_collide"); }
+#ifdef MOVING_BOUNDARIES
+void LBM_Domain::enqueue_update_moving_boundaries() { fx3d_check(fx3d_update_moving_boundaries(&lattice, device.get_stream()), "update_moving_boundaries"); }
+#endif
 void LBM_Domain::enqueue_update_fields() {
 #ifndef UPDATE_FIELDS
 	if(t!=t_last_update_fields) { // rho/u on the device are stale only if time has advanced since the last update
@@ -286,6 +292,13 @@ void LBM::communicate_field(const bool ddfs) { // x, then y, then z, so that edg
 	}
 	rendezvous(); // nobody overwrites what a neighbour is still reading
 }
+#ifdef MOVING_BOUNDARIES
+void LBM::update_moving_boundaries() { // src/lbm.cpp:1018-1027
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_update_moving_boundaries();
+	if(get_D()>1u) communicate_rho_u_flags(); // the reference exchanges the flags alone; rho and u halos are unchanged copies
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue();
+}
+#endif
 void LBM::communicate_fi() { communicate_field(true); }
 void LBM::communicate_rho_u_flags() { communicate_field(false); }
 

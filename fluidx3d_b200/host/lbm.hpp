@@ -41,6 +41,9 @@ public:
 	void enqueue_stream_collide(const int region=FX3D_REGION_ALL);
 	void enqueue_run_steps(const ulong steps); // D==1 only: `steps` stream_collide launches without host work in between
 	void enqueue_update_fields();
+#ifdef MOVING_BOUNDARIES
+	void enqueue_update_moving_boundaries(); // mark/unmark cells next to TYPE_S cells with velocity!=0 with TYPE_MS
+#endif
 	void enqueue_exchange_fi(const uint axis, const LBM_Domain& plus, const LBM_Domain& minus);
 	void enqueue_pack_x_faces(); // stage my outgoing x layers (transfer_extract_fi) before the rendezvous
 	void enqueue_exchange_rho_u_flags(const uint axis, const LBM_Domain& plus, const LBM_Domain& minus);
@@ -178,6 +181,9 @@ public:
 
 	void run(const ulong steps=max_ulong, const ulong total_steps=max_ulong); // first call initialises; run(0) only initialises
 	void update_fields();
+#ifdef MOVING_BOUNDARIES
+	void update_moving_boundaries(); // mark/unmark cells next to TYPE_S cells with velocity!=0 with TYPE_MS (call after changing boundary velocities)
+#endif
 	void reset();
 
 	uint get_Nx() const { return Nx; }

@@ -17,7 +17,7 @@ The C++ twin of this file (what setup.cpp scenes compile against) is fluidx3d_b2
 import ctypes as C
 import numpy as np
 from . import capi
-from .capi import (FP32, FP16S, FP16C, SRT, TRT, VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID, TYPE_S, TYPE_E,
+from .capi import (FP32, FP16S, FP16C, SRT, TRT, VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID, MOVING_BOUNDARIES, TYPE_S, TYPE_E,
                    REGION_ALL, REGION_SHELL, REGION_INTERIOR, Fx3dError)
 
 max_ulong = 2 ** 64 - 1
@@ -116,6 +116,9 @@ class LBM_Domain:
 
     def enqueue_stream_collide(self, region=REGION_ALL, stream=None):  # src/lbm.cpp:181-183: t, fx, fy, fz are per-launch arguments
         self.lib.stream_collide(C.byref(self.lat), self.t, self.fx, self.fy, self.fz, region, stream if stream is not None else self.stream)
+
+    def enqueue_update_moving_boundaries(self):  # src/lbm.cpp:241-243
+        self.lib.update_moving_boundaries(C.byref(self.lat), self.stream)
 
     def enqueue_update_fields(self):  # src/lbm.cpp:184-191
         if not (self.features & UPDATE_FIELDS) and self.t != self.t_last_update_fields:
@@ -305,7 +308,7 @@ class LBM:
             solid = bo == TYPE_S
             if np.any(solid):
                 moving |= bool(np.any((dom.u.host[:N][solid] != 0) | (dom.u.host[N:2 * N][solid] != 0) | (dom.u.host[2 * N:][solid] != 0)))
-        if moving: print_warning("Some boundary cells have non-zero velocity, but MOVING_BOUNDARIES is not enabled.")
+        if moving and not (self.features & MOVING_BOUNDARIES): print_warning("Some boundary cells have non-zero velocity, but MOVING_BOUNDARIES is not enabled.")
         if used_e and not (self.features & EQUILIBRIUM_BOUNDARIES):
             raise ValueError("Some cells are set as equilibrium boundaries with the TYPE_E flag, but EQUILIBRIUM_BOUNDARIES is not enabled.")
         if not used_e and (self.features & EQUILIBRIUM_BOUNDARIES):
@@ -447,6 +450,15 @@ class LBM:
     def update_fields(self):
         if self._streams2: self._join_streams()
         for _, dom in self.local_domains(): dom.enqueue_update_fields()
+        for _, dom in self.local_domains(): dom.finish_queue()
+
+    def update_moving_boundaries(self):
+        """mark / unmark the cells next to TYPE_S cells with non-zero velocity with TYPE_MS, after the boundary velocities in
+        lbm.u / lbm.flags were changed and written to the device (src/lbm.cpp:1018-1027)"""
+        if not (self.features & MOVING_BOUNDARIES): raise ValueError("update_moving_boundaries() needs the MOVING_BOUNDARIES extension")
+        if self._streams2: self._join_streams()
+        for _, dom in self.local_domains(): dom.enqueue_update_moving_boundaries()
+        if self.get_D() > 1: self.communicate_rho_u_flags()  # the reference exchanges the flags alone; rho and u halos are unchanged copies
         for _, dom in self.local_domains(): dom.finish_queue()
 
     def reset(self): self.initialized = False

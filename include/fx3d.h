@@ -29,8 +29,9 @@ typedef enum fx3d_status {
 
 enum { FX3D_FP32 = 0, FX3D_FP16S = 1, FX3D_FP16C = 2 };                 /* defines.hpp: (none) | FP16S | FP16C */
 enum { FX3D_SRT = 0, FX3D_TRT = 1 };                                    /* defines.hpp: SRT | TRT */
-enum { FX3D_VOLUME_FORCE = 1, FX3D_EQUILIBRIUM_BOUNDARIES = 2, FX3D_UPDATE_FIELDS = 4, FX3D_SUBGRID = 8 }; /* defines.hpp extension flags on the path;
- * SUBGRID (Smagorinsky-Lilly, kernel.cpp:1579-1593) is the first widening beyond the north_star feature set */
+enum { FX3D_VOLUME_FORCE = 1, FX3D_EQUILIBRIUM_BOUNDARIES = 2, FX3D_UPDATE_FIELDS = 4, FX3D_SUBGRID = 8, FX3D_MOVING_BOUNDARIES = 16 }; /* defines.hpp extension flags on the path;
+ * SUBGRID (Smagorinsky-Lilly, kernel.cpp:1579-1593) and MOVING_BOUNDARIES (kernel.cpp:1104-1113,1378-1387,1432-1450) are the first
+ * widenings beyond the north_star feature set */
 enum { FX3D_REGION_ALL = 0, FX3D_REGION_SHELL = 1, FX3D_REGION_INTERIOR = 2 };
 
 const char* fx3d_last_error(void); /* thread-local, valid until the next failing call on this thread */
@@ -88,7 +89,7 @@ typedef struct fx3d_lattice {
 	uint32_t velocity_set;     /* 19 or 27 */
 	uint32_t collision;        /* FX3D_SRT | FX3D_TRT */
 	uint32_t storage;          /* FX3D_FP32 | FX3D_FP16S | FX3D_FP16C */
-	uint32_t features;         /* FX3D_VOLUME_FORCE | FX3D_EQUILIBRIUM_BOUNDARIES | FX3D_UPDATE_FIELDS | FX3D_SUBGRID */
+	uint32_t features;         /* FX3D_VOLUME_FORCE | FX3D_EQUILIBRIUM_BOUNDARIES | FX3D_UPDATE_FIELDS | FX3D_SUBGRID | FX3D_MOVING_BOUNDARIES */
 	float w;                   /* def_w = 1/tau exactly as the device must see it (see fx3d_relaxation_rate) */
 	void* fi;                  /* DDFs, device only, fx3d_fi_bytes() bytes, library-private padded SoA layout */
 	float* rho;                /* [N] */
@@ -104,6 +105,9 @@ uint32_t fx3d_bytes_per_cell_per_step(const fx3d_lattice* lattice);   /* bandwid
 int fx3d_initialize(const fx3d_lattice* lattice, fx3d_stream stream);
 int fx3d_stream_collide(const fx3d_lattice* lattice, uint64_t t, float fx, float fy, float fz, int region, fx3d_stream stream);
 int fx3d_update_fields(const fx3d_lattice* lattice, uint64_t t, float fx, float fy, float fz, fx3d_stream stream);
+/* MOVING_BOUNDARIES: re-mark the cells next to TYPE_S cells with non-zero velocity as TYPE_MS after the boundary velocities
+ * changed (kernel update_moving_boundaries, kernel.cpp:1432-1450; LBM::update_moving_boundaries, lbm.cpp:1018-1027) */
+int fx3d_update_moving_boundaries(const fx3d_lattice* lattice, fx3d_stream stream);
 /* n consecutive stream_collide steps t0..t0+n-1 of a single (non-decomposed) domain, no host work in between */
 int fx3d_run_steps(const fx3d_lattice* lattice, uint64_t t0, uint64_t steps, float fx, float fy, float fz, fx3d_stream stream);
 /* kernel choice for tests and profiling: 0 library default (persistent kernels: TMA bulk copies where the tile spans whole rows,

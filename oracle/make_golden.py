@@ -28,6 +28,9 @@ CASES = [  # (Q, collision, storage, features, (Nx,Ny,Nz), (Dx,Dy,Dz), steps, nu
     (19, SRT, FP32, 8, (12, 10, 8), (1, 1, 1), 6, 0.002, (0, 0, 0)),               # SUBGRID (feature bit 3), low viscosity so that the eddy term matters
     (19, TRT, FP16S, 11, (12, 10, 8), (2, 1, 2), 6, 0.002, (2e-4, 0, -1e-4)),
     (27, SRT, FP16C, 8, (12, 10, 8), (1, 1, 1), 5, 0.004, (0, 0, 0)),
+    (19, SRT, FP32, 16, (12, 10, 8), (1, 1, 1), 6, 0.05, (0, 0, 0)),               # MOVING_BOUNDARIES (feature bit 4): the random scene's solids keep their velocity
+    (19, TRT, FP16S, 19, (12, 10, 8), (2, 1, 2), 6, 0.03, (2e-4, 0, -1e-4)),
+    (27, SRT, FP16C, 18, (12, 10, 8), (1, 1, 1), 5, 0.05, (0, 0, 0)),
 ]
 
 

@@ -94,6 +94,47 @@ def test_subgrid_bit_exact(fx, v, dims, D):
             assert np.array_equal(bits(a), bits(b)), steps
 
 
+MB_CASES = [((19, SRT, FP32, 16), (9, 7, 5), (1, 1, 1)), ((19, TRT, FP16S, 19), (12, 6, 6), (2, 1, 2)), ((27, SRT, FP16C, 18), (10, 6, 4), (1, 1, 1)),
+            ((19, SRT, FP16S, 24), (64, 8, 4), (1, 2, 1)), ((19, SRT, FP32, 16), (128, 16, 8), (1, 1, 1))]
+
+
+@pytest.mark.parametrize("v,dims,D", MB_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in MB_CASES])
+def test_moving_boundaries_bit_exact(fx, v, dims, D):
+    """MOVING_BOUNDARIES (feature bit 4; second widening): TYPE_MS marking in initialize, Dirichlet correction in stream_collide and
+    update_fields, update_moving_boundaries() after two boundaries changed speed -- fields AND flags bit-identical to the oracle"""
+    Q, coll, st, feat = v
+    f = (1e-4, -2e-4, 3e-4) if feat & 1 else (0.0, 0.0, 0.0)
+    sim = fx.LBM(*dims, 0.05, *f, Dx=D[0], Dy=D[1], Dz=D[2], velocity_set=Q, collision=coll, storage=st, features=feat, devices=[0] * (D[0] * D[1] * D[2]))
+    ref = HostSim(OracleBackend(Q, coll, st, feat), *dims, *D, nu=0.05, fx=f[0], fy=f[1], fz=f[2])
+    rho, u, flags = scenario(sim.Nx, sim.Ny, sim.Nz, seed=7, eq_frac=0.03 if feat & 2 else 0.0)
+    sim.rho.set_global(rho); [sim.u.set_global(u[a], a) for a in range(3)]; sim.flags.set_global(flags)
+    load_scenario(ref, rho, u, flags)
+    sim.run(3); ref.run(3)
+    solid = np.argwhere((flags & 3) == 1)
+    u2 = [a.copy() for a in u]
+    (z0, y0, x0), (z1, y1, x1) = solid[0], solid[1]
+    for a in range(3): u2[a][z0, y0, x0] = 0.0
+    u2[0][z1, y1, x1] = np.float32(0.02)
+    for m in (sim.rho, sim.u, sim.flags): m.read_from_device()
+    cur_flags = sim.flags.get_global()
+    [sim.u.set_global(np.where((cur_flags & 3) == 1, u2[a], sim.u.get_global(a)), a) for a in range(3)]
+    sim.u.write_to_device()
+    if sim.get_D() > 1: sim.communicate_rho_u_flags()
+    sim.update_moving_boundaries()
+    rf = ref.fields()
+    for a in range(3): ref.set_global("u", np.where((rf[4] & 3) == 1, u2[a], rf[1 + a]), a)
+    ref._communicate("ruf")
+    ref.update_moving_boundaries()
+    sim.run(4); ref.run(4)
+    for m in (sim.rho, sim.u, sim.flags): m.read_from_device()
+    got = (sim.rho.get_global(), sim.u.get_global(0), sim.u.get_global(1), sim.u.get_global(2), sim.flags.get_global())
+    want = ref.fields()
+    assert np.any((want[4] & 3) == 3)
+    for a, b in zip(got, want):
+        assert np.array_equal(bits(a), bits(b))
+    sim.close()
+
+
 SEG_CASES = [((19, SRT, FP16S, 0), (1024, 4, 3), (1, 1, 1)), ((19, SRT, FP16S, 0), (256, 8, 6), (2, 1, 1)), ((19, TRT, FP32, 3), (256, 8, 4), (2, 2, 1)),
              ((27, SRT, FP16C, 2), (1024, 2, 2), (1, 1, 1)), ((19, SRT, FP32, 1), (2048, 3, 2), (1, 1, 2)), ((27, TRT, FP16S, 3), (512, 8, 2), (4, 2, 1)),
              ((19, SRT, FP16C, 0), (1024, 8, 8), (2, 2, 2))]
