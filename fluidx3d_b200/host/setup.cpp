@@ -79,14 +79,19 @@ void main_setup() { // Poiseuille flow validation; required extensions in define
 #endif // SCENE_POISEUILLE
 
 #ifdef SCENE_CAVITY
-void main_setup() { // lid-driven cavity inside the hot-path feature set: TYPE_S walls, TYPE_E lid carrying u; required: EQUILIBRIUM_BOUNDARIES
+void main_setup() { // lid-driven cavity; required: MOVING_BOUNDARIES (the reference's formulation: a solid lid that moves) or EQUILIBRIUM_BOUNDARIES (TYPE_E lid carrying u)
 	const uint L = 128u;
 	const float Re = 1000.0f, u0 = 0.1f;
 	LBM lbm(L, L, L, units.nu_from_Re(Re, (float)(L-2u), u0));
 	const uint Nx=lbm.get_Nx(), Ny=lbm.get_Ny(), Nz=lbm.get_Nz();
 	parallel_for(lbm.get_N(), [&](ulong n) { uint x=0u, y=0u, z=0u; lbm.coordinates(n, x, y, z);
+#ifdef MOVING_BOUNDARIES
+		if(z==Nz-1u) lbm.u.y[n] = u0;
+		if(x==0u||x==Nx-1u||y==0u||y==Ny-1u||z==0u||z==Nz-1u) lbm.flags[n] = TYPE_S; // all non periodic
+#else
 		if(z==Nz-1u) { lbm.flags[n] = TYPE_E; lbm.u.y[n] = u0; }
 		else if(x==0u||x==Nx-1u||y==0u||y==Ny-1u||z==0u) lbm.flags[n] = TYPE_S;
+#endif
 	});
 	lbm.run(10000u);
 	lbm.u.read_from_device();
