@@ -33,6 +33,7 @@ WORKLOADS = {
     "d3q19_srt_fp16c_1024": (19, "srt", "fp16c", 0, (1024, 1024, 1024), "D3Q19 SRT FP16C 1024^3 per GPU; with --gpus 8 --split 2,2,2 the 2048^3 domain of BASELINE configs[3] (run with --no-e2e: 18 GB of host fields per GPU)"),
     "d3q27_trt_fp32_windtunnel": (27, "trt", "fp32", 3, (256, 512, 256), "D3Q27 TRT FP32 wind tunnel with sphere, TYPE_E faces + VOLUME_FORCE (BASELINE configs[2], half size)"),
     "d3q27_trt_fp32_windtunnel_full": (27, "trt", "fp32", 3, (512, 1024, 512), "D3Q27 TRT FP32 wind tunnel with sphere, TYPE_E faces + VOLUME_FORCE, 512x1024x512 (BASELINE configs[2], SURVEY 8d C3)"),
+    "d3q19_srt_fp32_256_cavity_mb": (19, "srt", "fp32", 16, (256, 256, 256), "D3Q19 SRT FP32 256^3 lid-driven cavity in the reference's own formulation (src/setup.cpp:212-249): six TYPE_S walls, the lid moves with u=(0,0.1,0), MOVING_BOUNDARIES, Re=1000"),
     "d3q19_srt_fp32_512_subgrid": (19, "srt", "fp32", 8, (512, 512, 512), "D3Q19 SRT FP32 512^3 periodic box with the SUBGRID (Smagorinsky-Lilly) model, SURVEY 8f rank 2"),
     "d3q19_srt_fp16s_512_subgrid": (19, "srt", "fp16s", 8, (512, 512, 512), "D3Q19 SRT FP16S 512^3 periodic box with the SUBGRID model"),
     "d3q19_srt_fp32_256_cavity": (19, "srt", "fp32", 2, (256, 256, 256), "D3Q19 SRT FP32 256^3 lid-driven cavity inside the hot-path feature set: TYPE_S walls, TYPE_E lid u=(0,0.1,0), Re=1000 (SURVEY 8d C1w)"),
@@ -48,6 +49,11 @@ def make_scene(workload, fx, Nx, Ny, Nz):
     import numpy as np
     zz, yy, xx = np.meshgrid(np.arange(Nz), np.arange(Ny), np.arange(Nx), indexing="ij", sparse=True)
     flags = np.zeros((Nz, Ny, Nx), np.uint8)
+    if "cavity_mb" in workload:  # the reference's cavity: all six faces solid, the lid (z = Nz-1) moves along +y
+        for sl in [np.s_[0, :, :], np.s_[-1, :, :], np.s_[:, 0, :], np.s_[:, -1, :], np.s_[:, :, 0], np.s_[:, :, -1]]:
+            flags[sl] = fx.TYPE_S
+        uy = np.zeros((Nz, Ny, Nx), np.float32); uy[-1, :, :] = 0.1
+        return flags, uy
     if "cavity" in workload:  # walls on five faces, equilibrium lid on z = Nz-1 moving along +y
         for sl in [np.s_[0, :, :], np.s_[:, 0, :], np.s_[:, -1, :], np.s_[:, :, 0], np.s_[:, :, -1]]:
             flags[sl] = fx.TYPE_S
@@ -212,9 +218,9 @@ def main():
     force = (0.0, 1e-6, 0.0) if feat & 1 else (0.0, 0.0, 0.0)
     nu = 0.1 * (Nz - 2) / 1000.0 if "cavity" in args.workload else 1.0
     sim = fx.LBM(Nx, Ny, Nz, nu, *force, Dx=Dx, Dy=Dy, Dz=Dz, velocity_set=Q, collision=collision, storage=storage, features=feat,
-                 comm=comm, devices=None if comm else [device], host_fields=bool(feat & 2), benchmark=True, overlap=overlap)
+                 comm=comm, devices=None if comm else [device], host_fields=bool(feat & (2 | 16)), benchmark=True, overlap=overlap)
     scene_flags, scene_uy = None, None
-    if feat & 2:
+    if feat & (2 | 16):
         scene_flags, scene_uy = make_scene(args.workload, fx, Nx, Ny, Nz)
         sim.flags.set_global(scene_flags); sim.u.set_global(scene_uy, 1)
     (d0, dom), = sim.local_domains()
@@ -266,7 +272,7 @@ def main():
     if not args.no_e2e:
         sim = fx.LBM(Nx, Ny, Nz, nu, *force, Dx=Dx, Dy=Dy, Dz=Dz, velocity_set=Q, collision=collision, storage=storage, features=feat,
                      comm=comm, devices=None if comm else [device], host_fields=True, benchmark=True, overlap=overlap)
-        if feat & 2:
+        if feat & (2 | 16):
             sim.flags.set_global(scene_flags); sim.u.set_global(scene_uy, 1)
         (d0, dom), = sim.local_domains()
         h2d = dom.rho.nbytes + dom.u.nbytes + dom.flags.nbytes

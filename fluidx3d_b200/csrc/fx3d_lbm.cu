@@ -67,25 +67,15 @@ static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int re
 	}
 	std::vector<Region> regs;
 	const bool vf = (lat->features&FX3D_VOLUME_FORCE)!=0u;
-	if(lat->features&FX3D_MOVING_BOUNDARIES) { // general kernel only (with or without SUBGRID)
-		const int reserve = 0;
-		const bool sg = (lat->features&FX3D_SUBGRID)!=0u;
-		regions_of(L, region, 1u, regs);
-		for(const Region& R : regs) {
-			int rc;
-			FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, 1, (int)lat->collision, vf, stream, reserve, sg); })
-			if(rc!=FX3D_OK) return rc;
-		}
-		return FX3D_OK;
-	}
-	if(lat->features&FX3D_SUBGRID) { // whole-row bulk-copy kernel where eligible, else the general kernel (any size)
+	if(lat->features&(FX3D_SUBGRID|FX3D_MOVING_BOUNDARIES)) { // widenings: whole-row bulk-copy kernel where eligible, else the general kernel (any size)
 		const int reserve = region==FX3D_REGION_INTERIOR ? g_interior_reserve.load() : 0;
+		const int ext = ((lat->features&FX3D_SUBGRID) ? 1 : 0)|((lat->features&FX3D_MOVING_BOUNDARIES) ? 2 : 0);
 		if(want!=1 && inner%4u==0u) {
 			regions_of(L, region, 4u, regs);
 			bool all = !regs.empty();
 			for(size_t k=0u; k<regs.size() && all; k++) {
 				int rc;
-				FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, regs[k], 0, (int)lat->collision, vf, stream, reserve, true); })
+				FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, regs[k], 0, (int)lat->collision, vf, stream, reserve, ext); })
 				if(rc==1 && k==0u) all = false;
 				else if(rc!=FX3D_OK) return rc==1 ? FX3D_ERR_INVALID : rc;
 			}
@@ -95,7 +85,7 @@ static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int re
 		regions_of(L, region, 1u, regs);
 		for(const Region& R : regs) {
 			int rc;
-			FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, 1, (int)lat->collision, vf, stream, reserve, true); })
+			FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, 1, (int)lat->collision, vf, stream, 0, ext); })
 			if(rc!=FX3D_OK) return rc;
 		}
 		return FX3D_OK;

@@ -383,9 +383,35 @@ FX3D_HD unsigned char* dynamic_smem() {
 #endif
 }
 
+// ---- MOVING_BOUNDARIES ----
+// linear index of the neighbour of (x,y,z) in direction I
+template<int I> FX3D_HD uint64_t neighbour_lin(const Lattice& L, uint32_t x, uint32_t y, uint32_t z) { return lin(L, step<dir_x(I)>(x, L.Nx), step<dir_y(I)>(y, L.Ny), step<dir_z(I)>(z, L.Nz)); }
+// is any neighbour a TYPE_S cell with non-zero velocity? (src/kernel.cpp:1381-1385, :1442-1446)
+template<int Q> FX3D_HD bool next_to_moving_solid(const Lattice& L, uint32_t x, uint32_t y, uint32_t z) {
+	const uint64_t N = cells(L);
+	bool r = false;
+	static_for<1, Q, 1>([&](auto I) {
+		const uint64_t j = neighbour_lin<I.value>(L, x, y, z);
+		r = r || ((L.flags[j]&TYPE_BO)==TYPE_S && (L.u[j]!=0.0f || L.u[N+j]!=0.0f || L.u[2ull*N+j]!=0.0f));
+	});
+	return r;
+}
+// apply_moving_boundaries, src/kernel.cpp:1104-1113: Dirichlet velocity correction of the streamed-in populations of a TYPE_MS cell;
+// f at working scale S (S*fma(w6, cu, f) == fma(w6*S, cu, S*f): power-of-two scaling commutes with the rounding)
+template<int Q> FX3D_HD void apply_moving_boundaries(const Lattice& L, uint32_t x, uint32_t y, uint32_t z, float (&f)[Q], const float S = 1.0f) {
+	const uint64_t N = cells(L);
+	static_for<1, Q, 2>([&](auto I) {
+		constexpr int i = I;
+		const float w6 = (-6.0f*weight<Q>(i))*S;
+		uint64_t j = neighbour_lin<i+1>(L, x, y, z);
+		if((L.flags[j]&TYPE_BO)==TYPE_S) f[i  ] = fmaf(w6, (float)dir_x(i+1)*L.u[j]+(float)dir_y(i+1)*L.u[N+j]+(float)dir_z(i+1)*L.u[2ull*N+j], f[i  ]);
+		j = neighbour_lin<i>(L, x, y, z);
+		if((L.flags[j]&TYPE_BO)==TYPE_S) f[i+1] = fmaf(w6, (float)dir_x(i  )*L.u[j]+(float)dir_y(i  )*L.u[N+j]+(float)dir_z(i  )*L.u[2ull*N+j], f[i+1]);
+	});
+}
 // ---- collision of the K cells a thread holds in A (raw storage vectors, stream-in order), pair by pair in packed arithmetic;
 // on return A holds what streams out through the same slots. flags4: the flag bytes of the cells (TYPE_S for cells to skip).
-template<int Q, int COLL, int ST, bool VF, int K, bool SG = false> FX3D_HD void collide_tile(const Lattice& L, Pack<ST, K> (&A)[Q], const uint32_t flags4, const uint32_t x0, const uint32_t yc, const uint32_t z) {
+template<int Q, int COLL, int ST, bool VF, int K, bool SG = false, bool MB = false> FX3D_HD void collide_tile(const Lattice& L, Pack<ST, K> (&A)[Q], const uint32_t flags4, const uint32_t x0, const uint32_t yc, const uint32_t z) {
 	typedef Codec<ST> C;
 	typedef typename C::elem_t E;
 	static_for<0, K/2, 1>([&](auto Pp) {
@@ -402,7 +428,26 @@ template<int Q, int COLL, int ST, bool VF, int K, bool SG = false> FX3D_HD void 
 			}
 			F2 rhon, uxn, uyn, uzn;
 			const bool both = act_lo && act_hi;
-			if constexpr(pipe_collide_mode<Q, ST>()==2) {
+			bool moving = false;
+			if constexpr(MB) moving = fb_lo==TYPE_MS || fb_hi==TYPE_MS;
+			if(moving) { // MOVING_BOUNDARIES, rare lanes: all populations unpacked, the Dirichlet term added lane by lane, then the array collision
+				F2 f[Q];
+				static_for<0, Q, 1>([&](auto I) { f[I] = A[I].template get_pair<p>(); });
+				float fl[Q];
+				if(fb_lo==TYPE_MS) {
+					static_for<0, Q, 1>([&](auto I) { fl[I] = f2_lo(f[I]); });
+					apply_moving_boundaries<Q>(L, x0+2u*(uint32_t)p, yc, z, fl, C::scale);
+					static_for<0, Q, 1>([&](auto I) { f[I] = make_f2(fl[I], f2_hi(f[I])); });
+				}
+				if(fb_hi==TYPE_MS) {
+					static_for<0, Q, 1>([&](auto I) { fl[I] = f2_hi(f[I]); });
+					apply_moving_boundaries<Q>(L, x0+2u*(uint32_t)p+1u, yc, z, fl, C::scale);
+					static_for<0, Q, 1>([&](auto I) { f[I] = make_f2(f2_lo(f[I]), fl[I]); });
+				}
+				collide_cell<Q, COLL, VF, F2, SG>(f, C::scale, C::inv_scale, e_lo, e_hi, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+				A[0].template set_lanes<p>(f[0], act_lo, act_hi);
+				static_for<1, Q, 2>([&](auto I) { constexpr int i = I; A[i+1].template set_lanes<p>(f[i], act_lo, act_hi); A[i].template set_lanes<p>(f[i+1], act_lo, act_hi); });
+			} else if constexpr(pipe_collide_mode<Q, ST>()==2) {
 			// populations are unpacked on demand and the results packed straight into the slot they stream out through:
 			// store_f() sends fhn[i] to the neighbour-side slot (A[i+1]) and fhn[i+1] to the local slot (A[i])
 			auto get = [&](auto I) { return A[I.value].template get_pair<p>(); };
@@ -631,7 +676,7 @@ FX3D_HD void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "m
 FX3D_HD void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); } // my shared-memory writes become visible to the bulk-copy engine
 #endif
 
-template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false>
+template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false>
 __global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_collide_tma(const Lattice L, const Region R, const uint32_t tiles_y) {
 	constexpr int K = 4, S = FX3D_TMA_STAGES;
 	constexpr uint32_t odd = (uint32_t)ODD;
@@ -736,7 +781,7 @@ __global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_coll
 			// refill the other stage(s) now rather than at the top of the iteration: the bulk stores issued from it at the end of the
 			// previous iteration have had the stream-in to finish reading it, so the copying threads rarely wait here
 			if(z+(uint32_t)(S-1)<ze) { if(copier) bulk_wait_read(); load_tile(yb, z+(uint32_t)(S-1), (it+(uint32_t)(S-1))%(uint32_t)S); }
-			collide_tile<Q, COLL, ST, VF, K, SG>(L, A, flags4, x0, y, z);
+			collide_tile<Q, COLL, ST, VF, K, SG, MB>(L, A, flags4, x0, y, z);
 			// ---- stream out into the same row buffers ----
 			A[0].store(reinterpret_cast<E*>(sb+tid*VB));
 			static_for<1, Q, 2>([&](auto I) {
@@ -1174,31 +1219,6 @@ FX3D_HD bool region_cell(const Region& R, uint32_t& x, uint32_t& y, uint32_t& z)
 	return x<R.g1 && y<R.y1;
 }
 
-// ---- MOVING_BOUNDARIES, general kernels only ----
-// linear index of the neighbour of (x,y,z) in direction I
-template<int I> FX3D_HD uint64_t neighbour_lin(const Lattice& L, uint32_t x, uint32_t y, uint32_t z) { return lin(L, step<dir_x(I)>(x, L.Nx), step<dir_y(I)>(y, L.Ny), step<dir_z(I)>(z, L.Nz)); }
-// is any neighbour a TYPE_S cell with non-zero velocity? (src/kernel.cpp:1381-1385, :1442-1446)
-template<int Q> FX3D_HD bool next_to_moving_solid(const Lattice& L, uint32_t x, uint32_t y, uint32_t z) {
-	const uint64_t N = cells(L);
-	bool r = false;
-	static_for<1, Q, 1>([&](auto I) {
-		const uint64_t j = neighbour_lin<I.value>(L, x, y, z);
-		r = r || ((L.flags[j]&TYPE_BO)==TYPE_S && (L.u[j]!=0.0f || L.u[N+j]!=0.0f || L.u[2ull*N+j]!=0.0f));
-	});
-	return r;
-}
-// apply_moving_boundaries, src/kernel.cpp:1104-1113: Dirichlet velocity correction of the streamed-in populations of a TYPE_MS cell
-template<int Q> FX3D_HD void apply_moving_boundaries(const Lattice& L, uint32_t x, uint32_t y, uint32_t z, float (&f)[Q]) {
-	const uint64_t N = cells(L);
-	static_for<1, Q, 2>([&](auto I) {
-		constexpr int i = I;
-		const float w6 = -6.0f*weight<Q>(i);
-		uint64_t j = neighbour_lin<i+1>(L, x, y, z);
-		if((L.flags[j]&TYPE_BO)==TYPE_S) f[i  ] = fmaf(w6, (float)dir_x(i+1)*L.u[j]+(float)dir_y(i+1)*L.u[N+j]+(float)dir_z(i+1)*L.u[2ull*N+j], f[i  ]);
-		j = neighbour_lin<i>(L, x, y, z);
-		if((L.flags[j]&TYPE_BO)==TYPE_S) f[i+1] = fmaf(w6, (float)dir_x(i  )*L.u[j]+(float)dir_y(i  )*L.u[N+j]+(float)dir_z(i  )*L.u[2ull*N+j], f[i+1]);
-	});
-}
 // update_moving_boundaries, src/kernel.cpp:1432-1450
 template<int Q>
 __global__ void __launch_bounds__(128) k_update_moving_boundaries(const Lattice L, const Region R) {

@@ -46,7 +46,7 @@ template<int Q, int COLL, int ST, bool VF> static int launch_pipe(const Lattice&
 static bool tma_eligible(const Lattice& L, const Region& R, const dim3& block) {
 	return L.Hx==0u && L.xo==0u && R.g0==0u && R.g1*4u==L.Nx && block.x*4u==L.Nx && L.Nx%16u==0u && block.x*block.y==128u && (R.y1-R.y0)%block.y==0u;
 }
-template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false> static int launch_tma_parity(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
+template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false> static int launch_tma_parity(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
 	const uint32_t tiles_y = (R.y1-R.y0)/block.y, nz = R.z1-R.z0;
 	constexpr uint32_t smem = tma_smem_bytes<Q, ST>();
 	int sms = 148, per_sm = tma_blocks_per_sm<Q, ST>();
@@ -54,7 +54,7 @@ template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false> static int 
 	static std::atomic<uint64_t> configured{0ull};
 	int dev = 0; cudaGetDevice(&dev);
 	if(dev>=64 || !((configured.load()>>dev)&1ull)) {
-		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if(e!=cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stream_collide_tma)");
 		if(dev<64) configured.fetch_or(1ull<<dev);
 	}
@@ -66,7 +66,7 @@ template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false> static int 
 	if(ntiles==0ull) return FX3D_OK;
 	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, blocks), 1u, 1u);
 	g_kind_launches[3]++;
-	FX3D_LAUNCH_SMEM((k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG>), grid, block, smem, stream, L, R, tiles_y);
+	FX3D_LAUNCH_SMEM((k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG, MB>), grid, block, smem, stream, L, R, tiles_y);
 	return check_launch("stream_collide (bulk copies)");
 }
 // segment form: tiles are full 4*block.x-cell segments of longer rows, or rows with x halos
@@ -132,24 +132,30 @@ template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_hyb_parity
 template<int Q, int COLL, int ST, bool VF> static int launch_hyb(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
 	return L.odd ? launch_hyb_parity<Q, COLL, ST, VF, 1>(L, R, block, stream, reserve) : launch_hyb_parity<Q, COLL, ST, VF, 0>(L, R, block, stream, reserve);
 }
-template<int Q, int COLL, int ST, bool VF, bool SG = false> static int launch_tma(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
-	return L.odd ? launch_tma_parity<Q, COLL, ST, VF, 1, SG>(L, R, block, stream, reserve) : launch_tma_parity<Q, COLL, ST, VF, 0, SG>(L, R, block, stream, reserve);
+template<int Q, int COLL, int ST, bool VF, bool SG = false, bool MB = false> static int launch_tma(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
+	return L.odd ? launch_tma_parity<Q, COLL, ST, VF, 1, SG, MB>(L, R, block, stream, reserve) : launch_tma_parity<Q, COLL, ST, VF, 0, SG, MB>(L, R, block, stream, reserve);
 }
 
-template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, int cells_per_thread, int collision, bool volume_force, void* stream, int reserve, bool subgrid) {
+template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, int cells_per_thread, int collision, bool volume_force, void* stream, int reserve, int ext) {
 	if(R.g1<=R.g0||R.y1<=R.y0||R.z1<=R.z0) return FX3D_OK;
-	if(subgrid) { // SUBGRID (first 'next' row): the whole-row bulk-copy kernel (cells_per_thread 0, regions in groups of 4) or the general kernel (1)
+	if(ext!=0) { // SUBGRID (bit 0) and/or MOVING_BOUNDARIES (bit 1): the whole-row bulk-copy kernel (cells_per_thread 0, regions in groups of 4) or the general kernel (1)
 		const dim3 block = block_shape(R.g1-R.g0);
+		const bool sg = (ext&1)!=0, mb = (ext&2)!=0;
 		if(cells_per_thread==0) {
 			if(!tma_eligible(L, R, block)) return 1; // not eligible: nothing launched, the caller falls back to the general kernel
-			if(collision==COLL_SRT) return volume_force ? launch_tma<Q, COLL_SRT, ST, true, true>(L, R, block, stream, reserve) : launch_tma<Q, COLL_SRT, ST, false, true>(L, R, block, stream, reserve);
-			return volume_force ? launch_tma<Q, COLL_TRT, ST, true, true>(L, R, block, stream, reserve) : launch_tma<Q, COLL_TRT, ST, false, true>(L, R, block, stream, reserve);
+#define FX3D_TMA_EXT(COLL, VF) (sg ? (mb ? launch_tma<Q, COLL, ST, VF, true, true>(L, R, block, stream, reserve) : launch_tma<Q, COLL, ST, VF, true, false>(L, R, block, stream, reserve)) \
+                                   : launch_tma<Q, COLL, ST, VF, false, true>(L, R, block, stream, reserve))
+			if(collision==COLL_SRT) return volume_force ? FX3D_TMA_EXT(COLL_SRT, true) : FX3D_TMA_EXT(COLL_SRT, false);
+			return volume_force ? FX3D_TMA_EXT(COLL_TRT, true) : FX3D_TMA_EXT(COLL_TRT, false);
+#undef FX3D_TMA_EXT
 		}
 		const dim3 grid((R.g1-R.g0+block.x-1u)/block.x, (R.y1-R.y0+block.y-1u)/block.y, R.z1-R.z0);
 		g_kind_launches[0]++;
-		if(collision==COLL_SRT) { if(volume_force) FX3D_LAUNCH((k_stream_collide_v1<Q, COLL_SRT, ST, true, true>), grid, block, stream, L, R); else FX3D_LAUNCH((k_stream_collide_v1<Q, COLL_SRT, ST, false, true>), grid, block, stream, L, R); }
-		else { if(volume_force) FX3D_LAUNCH((k_stream_collide_v1<Q, COLL_TRT, ST, true, true>), grid, block, stream, L, R); else FX3D_LAUNCH((k_stream_collide_v1<Q, COLL_TRT, ST, false, true>), grid, block, stream, L, R); }
-		return check_launch("stream_collide (subgrid)");
+#define FX3D_V1_EXT(COLL, VF) do { if(sg) FX3D_LAUNCH((k_stream_collide_v1<Q, COLL, ST, VF, true>), grid, block, stream, L, R); else FX3D_LAUNCH((k_stream_collide_v1<Q, COLL, ST, VF, false>), grid, block, stream, L, R); } while(0)
+		if(collision==COLL_SRT) { if(volume_force) FX3D_V1_EXT(COLL_SRT, true); else FX3D_V1_EXT(COLL_SRT, false); }
+		else { if(volume_force) FX3D_V1_EXT(COLL_TRT, true); else FX3D_V1_EXT(COLL_TRT, false); }
+#undef FX3D_V1_EXT
+		return check_launch("stream_collide (extensions)");
 	}
 	if(cells_per_thread<=0) { // persistent kernels; R.g0/g1 are in groups of pipe_cells<Q,ST>() cells. 0: bulk copies where the tile spans the row, else cp.async; -1: cp.async
 		const dim3 block = block_shape(R.g1-R.g0);
@@ -185,6 +191,6 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 #undef FX3D_SC
 	return check_launch("stream_collide");
 }
-template int launch_stream_collide<FX3D_Q, FX3D_ST>(const Lattice&, const Region&, int, int, bool, void*, int, bool);
+template int launch_stream_collide<FX3D_Q, FX3D_ST>(const Lattice&, const Region&, int, int, bool, void*, int, int);
 
 } // namespace fx3d
