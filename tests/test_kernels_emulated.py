@@ -222,3 +222,21 @@ def test_constructor_checks():
     with pytest.raises(ValueError): LBM(4, 4, 4, -1.0, lib=lib)
     with pytest.raises(ValueError): LBM(4, 4, 4, 0.1, 1e-3, 0.0, 0.0, lib=lib)  # force without VOLUME_FORCE
     with pytest.raises(ValueError): LBM(4, 4, 4, 0.1, Dx=0, lib=lib)
+
+
+def test_c_abi_error_behaviour(emul):
+    """every entry point returns a status code and leaves a message; nothing exits (the C++ wrapper maps them to print_error)"""
+    import ctypes as C
+    from fluidx3d_b200.capi import Fx3dError
+    for bad in (3, 5, 7, -1, 64):
+        with pytest.raises(Fx3dError, match="variant must be"): emul.set_kernel_variant(bad)
+    for ok in (0, 1, 2, 4, 8, 16, 0): emul.set_kernel_variant(ok)
+    with pytest.raises(Fx3dError, match="reserve"): emul.set_interior_reserve(-1)
+    emul.set_interior_reserve(8)
+    n = C.c_uint64(0)
+    with pytest.raises(Fx3dError, match="kind"): emul.stream_collide_launches(9, C.byref(n))
+    sim = LBM(8, 4, 4, 0.1, lib=emul)  # no MOVING_BOUNDARIES
+    with pytest.raises(ValueError): sim.update_moving_boundaries()
+    (_, dom), = sim.local_domains()
+    with pytest.raises(Fx3dError, match="MOVING_BOUNDARIES"): emul.update_moving_boundaries(C.byref(dom.lat), dom.stream)
+    sim.close()
