@@ -1010,7 +1010,7 @@ __global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_coll
 // tools/microbench/ubench3.cu: it is the *load* half of the LSU path that saturates at low occupancy (bulk loads + STG stores reach
 // the same 6.2 TB/s as bulk loads + bulk stores). Per-thread stores settle the ownership of the row ends by themselves (shuffles
 // inside a warp, one scalar store at warp / segment ends), so there is no write-back into the stage, no second barrier, no fix-up.
-template<int Q, int COLL, int ST, bool VF, int ODD>
+template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false>
 __global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_collide_hyb(const Lattice L, const Region R, const uint32_t tiles_x, const uint32_t tiles_y) {
 	constexpr int K = 4, S = FX3D_TMA_STAGES, NXD = x_dirs<Q>();
 	constexpr uint32_t odd = (uint32_t)ODD;
@@ -1148,7 +1148,7 @@ __global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_coll
 			__syncthreads();
 			if(z+(uint32_t)(S-1)<ze) load_tile(X0, yb, z+(uint32_t)(S-1), (it+(uint32_t)(S-1))%(uint32_t)S);
 			if(z+1u<ze) request_flags(z+1u);
-			collide_tile<Q, COLL, ST, VF, K>(L, A, flags4, X0+x0, y, z);
+			collide_tile<Q, COLL, ST, VF, K, SG, MB>(L, A, flags4, X0+x0, y, z);
 			{
 				constexpr unsigned FULL = 0xFFFFFFFFu;
 				const int64_t dzn[3] = { ((int64_t)dec(z, L.Nz)-(int64_t)z)*plane_bytes, 0, ((int64_t)inc(z, L.Nz)-(int64_t)z)*plane_bytes };

@@ -105,7 +105,7 @@ template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_tmaseg_par
 template<int Q, int COLL, int ST, bool VF> static int launch_tmaseg(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
 	return L.odd ? launch_tmaseg_parity<Q, COLL, ST, VF, 1>(L, R, block, stream, reserve) : launch_tmaseg_parity<Q, COLL, ST, VF, 0>(L, R, block, stream, reserve);
 }
-template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_hyb_parity(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
+template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false> static int launch_hyb_parity(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
 	const uint32_t tiles_x = (R.g1-R.g0)/block.x, tiles_y = (R.y1-R.y0)/block.y, nz = R.z1-R.z0;
 	constexpr uint32_t smem = tmaseg_smem_bytes<Q, ST>();
 	int sms = 148, per_sm = tma_blocks_per_sm<Q, ST>();
@@ -113,7 +113,7 @@ template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_hyb_parity
 	static std::atomic<uint64_t> configured{0ull};
 	int dev = 0; cudaGetDevice(&dev);
 	if(dev>=64 || !((configured.load()>>dev)&1ull)) {
-		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_hyb<Q, COLL, ST, VF, ODD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_hyb<Q, COLL, ST, VF, ODD, SG, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if(e!=cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stream_collide_hyb)");
 		if(dev<64) configured.fetch_or(1ull<<dev);
 	}
@@ -126,11 +126,11 @@ template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_hyb_parity
 	if((uint64_t)tiles_x*tiles_y>0xFFFFFFFFull) { set_error("region has too many tile columns"); return FX3D_ERR_INVALID; }
 	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, blocks), 1u, 1u);
 	g_kind_launches[5]++;
-	FX3D_LAUNCH_SMEM((k_stream_collide_hyb<Q, COLL, ST, VF, ODD>), grid, block, smem, stream, L, R, tiles_x, tiles_y);
+	FX3D_LAUNCH_SMEM((k_stream_collide_hyb<Q, COLL, ST, VF, ODD, SG, MB>), grid, block, smem, stream, L, R, tiles_x, tiles_y);
 	return check_launch("stream_collide (bulk loads, direct stores)");
 }
-template<int Q, int COLL, int ST, bool VF> static int launch_hyb(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
-	return L.odd ? launch_hyb_parity<Q, COLL, ST, VF, 1>(L, R, block, stream, reserve) : launch_hyb_parity<Q, COLL, ST, VF, 0>(L, R, block, stream, reserve);
+template<int Q, int COLL, int ST, bool VF, bool SG = false, bool MB = false> static int launch_hyb(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
+	return L.odd ? launch_hyb_parity<Q, COLL, ST, VF, 1, SG, MB>(L, R, block, stream, reserve) : launch_hyb_parity<Q, COLL, ST, VF, 0, SG, MB>(L, R, block, stream, reserve);
 }
 template<int Q, int COLL, int ST, bool VF, bool SG = false, bool MB = false> static int launch_tma(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
 	return L.odd ? launch_tma_parity<Q, COLL, ST, VF, 1, SG, MB>(L, R, block, stream, reserve) : launch_tma_parity<Q, COLL, ST, VF, 0, SG, MB>(L, R, block, stream, reserve);
@@ -142,7 +142,14 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 		const dim3 block = block_shape(R.g1-R.g0);
 		const bool sg = (ext&1)!=0, mb = (ext&2)!=0;
 		if(cells_per_thread==0) {
-			if(!tma_eligible(L, R, block)) return 1; // not eligible: nothing launched, the caller falls back to the general kernel
+			if(!tma_eligible(L, R, block)) { // row segments / x halos: bulk loads + direct stores; else nothing launched, the caller falls back to the general kernel
+				if(!tmaseg_eligible<Q, ST>(L, R, block)) return 1;
+#define FX3D_HYB_EXT(COLL, VF) (sg ? (mb ? launch_hyb<Q, COLL, ST, VF, true, true>(L, R, block, stream, reserve) : launch_hyb<Q, COLL, ST, VF, true, false>(L, R, block, stream, reserve)) \
+                                   : launch_hyb<Q, COLL, ST, VF, false, true>(L, R, block, stream, reserve))
+				if(collision==COLL_SRT) return volume_force ? FX3D_HYB_EXT(COLL_SRT, true) : FX3D_HYB_EXT(COLL_SRT, false);
+				return volume_force ? FX3D_HYB_EXT(COLL_TRT, true) : FX3D_HYB_EXT(COLL_TRT, false);
+#undef FX3D_HYB_EXT
+			}
 #define FX3D_TMA_EXT(COLL, VF) (sg ? (mb ? launch_tma<Q, COLL, ST, VF, true, true>(L, R, block, stream, reserve) : launch_tma<Q, COLL, ST, VF, true, false>(L, R, block, stream, reserve)) \
                                    : launch_tma<Q, COLL, ST, VF, false, true>(L, R, block, stream, reserve))
 			if(collision==COLL_SRT) return volume_force ? FX3D_TMA_EXT(COLL_SRT, true) : FX3D_TMA_EXT(COLL_SRT, false);

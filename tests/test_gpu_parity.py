@@ -80,7 +80,8 @@ def test_fields_bit_exact_medium_100_steps(fx, v, variant):
 
 SG_CASES = [((19, SRT, FP32, 8), (9, 7, 5), (1, 1, 1)), ((19, TRT, FP16S, 11), (12, 6, 6), (2, 1, 2)), ((27, SRT, FP16C, 8), (10, 6, 4), (1, 1, 1)),
             ((19, SRT, FP16S, 8), (64, 8, 6), (1, 1, 1)), ((19, TRT, FP32, 11), (128, 4, 4), (1, 2, 1)), ((27, TRT, FP16C, 9), (32, 16, 3), (1, 1, 1)),
-            ((19, SRT, FP32, 8), (256, 8, 4), (1, 1, 2))]
+            ((19, SRT, FP32, 8), (256, 8, 4), (1, 1, 2)),
+            ((19, SRT, FP16S, 8), (1024, 4, 3), (1, 1, 1)), ((19, TRT, FP32, 11), (256, 8, 4), (2, 1, 1)), ((27, SRT, FP16C, 10), (1024, 2, 2), (2, 1, 1))]  # row segments / x halos: hybrid kernel
 
 
 @pytest.mark.parametrize("v,dims,D", SG_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in SG_CASES])
@@ -96,7 +97,8 @@ def test_subgrid_bit_exact(fx, v, dims, D):
 
 MB_CASES = [((19, SRT, FP32, 16), (9, 7, 5), (1, 1, 1)), ((19, TRT, FP16S, 19), (12, 6, 6), (2, 1, 2)), ((27, SRT, FP16C, 18), (10, 6, 4), (1, 1, 1)),
             ((19, SRT, FP16S, 24), (64, 8, 4), (1, 2, 1)), ((19, SRT, FP32, 16), (128, 16, 8), (1, 1, 1)),
-            ((19, TRT, FP16S, 19), (64, 8, 6), (1, 1, 2)), ((27, SRT, FP16C, 18), (32, 16, 3), (1, 1, 1)), ((19, SRT, FP16S, 24), (64, 8, 4), (1, 1, 1))]  # bulk-copy kernel
+            ((19, TRT, FP16S, 19), (64, 8, 6), (1, 1, 2)), ((27, SRT, FP16C, 18), (32, 16, 3), (1, 1, 1)), ((19, SRT, FP16S, 24), (64, 8, 4), (1, 1, 1)),  # bulk-copy kernel
+            ((19, SRT, FP16S, 16), (1024, 4, 3), (1, 1, 1)), ((19, TRT, FP32, 19), (256, 8, 4), (2, 2, 1)), ((27, SRT, FP16C, 26), (1024, 2, 2), (2, 1, 1))]  # row segments / x halos: hybrid kernel
 
 
 @pytest.mark.parametrize("v,dims,D", MB_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in MB_CASES])
