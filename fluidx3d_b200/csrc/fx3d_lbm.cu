@@ -16,28 +16,37 @@ std::atomic<int> g_variant{0};
 std::atomic<int> g_interior_reserve{8};
 std::atomic<uint64_t> g_kind_launches[6];
 
-// interior (non-halo) extent and the shell / interior split used to overlap the halo exchange with computation.
-// The shell is every non-halo cell within one cell (one 4-cell group along x for the vector kernel) of a halo layer.
-static void regions_of(const Lattice& L, int region, uint32_t K, std::vector<Region>& out) { // K cells per thread along x
-	const uint32_t gx0 = K>1u ? 0u : L.Hx, gx1 = K>1u ? (L.Nx-2u*L.Hx)/K : L.Nx-L.Hx;
-	const uint32_t y0 = L.Hy, y1 = L.Ny-L.Hy, z0 = L.Hz, z1 = L.Nz-L.Hz;
+// Non-halo extent and the shell / interior split used to overlap the halo exchange with computation, in CELLS. The shell is
+// every non-halo cell within one cell of a halo layer in y and z, and within XS cells in x, where XS (4, 2 or 1) is the largest
+// cells-per-thread count that divides the non-halo row length: the split must not depend on which kernel (and which K) later
+// runs a region, or the SHELL and INTERIOR passes of one step would overlap or leave cells out.
+struct CellRegion { uint32_t x0, x1, y0, y1, z0, z1; };
+static uint32_t x_shell_width(const Lattice& L) { const uint32_t inner = L.Nx-2u*L.Hx; return inner%4u==0u ? 4u : inner%2u==0u ? 2u : 1u; }
+static void regions_of(const Lattice& L, int region, std::vector<CellRegion>& out) {
+	const uint32_t x0 = L.Hx, x1 = L.Nx-L.Hx, y0 = L.Hy, y1 = L.Ny-L.Hy, z0 = L.Hz, z1 = L.Nz-L.Hz;
 	if(region==FX3D_REGION_ALL || (L.Hx|L.Hy|L.Hz)==0u) {
-		if(region!=FX3D_REGION_SHELL) out.push_back(Region{ gx0, gx1, y0, y1, z0, z1 });
+		if(region!=FX3D_REGION_SHELL) out.push_back(CellRegion{ x0, x1, y0, y1, z0, z1 });
 		return;
 	}
-	// interior box: shrink by one layer (group) on every decomposed axis; empty if the domain is too thin
-	const uint32_t ix0 = gx0+L.Hx, ix1 = gx1>=gx0+2u*L.Hx ? gx1-L.Hx : gx0+L.Hx;
+	// interior box: shrink by one layer (XS cells along x) on every decomposed axis; empty if the domain is too thin
+	const uint32_t xs = L.Hx ? x_shell_width(L) : 0u;
+	const uint32_t ix0 = x0+xs, ix1 = x1>=x0+2u*xs ? x1-xs : x0+xs;
 	const uint32_t iy0 = y0+L.Hy, iy1 = y1>=y0+2u*L.Hy ? y1-L.Hy : y0+L.Hy;
 	const uint32_t iz0 = z0+L.Hz, iz1 = z1>=z0+2u*L.Hz ? z1-L.Hz : z0+L.Hz;
 	const bool has_interior = ix1>ix0 && iy1>iy0 && iz1>iz0;
 	if(region==FX3D_REGION_INTERIOR) {
-		if(has_interior) out.push_back(Region{ ix0, ix1, iy0, iy1, iz0, iz1 });
+		if(has_interior) out.push_back(CellRegion{ ix0, ix1, iy0, iy1, iz0, iz1 });
 		return;
 	}
-	if(!has_interior) { out.push_back(Region{ gx0, gx1, y0, y1, z0, z1 }); return; } // everything is shell
-	if(L.Hz) { out.push_back(Region{ gx0, gx1, y0, y1, z0, iz0 }); out.push_back(Region{ gx0, gx1, y0, y1, iz1, z1 }); }
-	if(L.Hy) { out.push_back(Region{ gx0, gx1, y0, iy0, iz0, iz1 }); out.push_back(Region{ gx0, gx1, iy1, y1, iz0, iz1 }); }
-	if(L.Hx) { out.push_back(Region{ gx0, ix0, iy0, iy1, iz0, iz1 }); out.push_back(Region{ ix1, gx1, iy0, iy1, iz0, iz1 }); }
+	if(!has_interior) { out.push_back(CellRegion{ x0, x1, y0, y1, z0, z1 }); return; } // everything is shell
+	if(L.Hz) { out.push_back(CellRegion{ x0, x1, y0, y1, z0, iz0 }); out.push_back(CellRegion{ x0, x1, y0, y1, iz1, z1 }); }
+	if(L.Hy) { out.push_back(CellRegion{ x0, x1, y0, iy0, iz0, iz1 }); out.push_back(CellRegion{ x0, x1, iy1, y1, iz0, iz1 }); }
+	if(L.Hx) { out.push_back(CellRegion{ x0, ix0, iy0, iy1, iz0, iz1 }); out.push_back(CellRegion{ ix1, x1, iy0, iy1, iz0, iz1 }); }
+}
+// the kernels address x in groups of K cells counted from the first non-halo cell (K>1) or in absolute cells (K==1)
+static Region to_groups(const Lattice& L, const CellRegion& c, uint32_t K) {
+	if(K<=1u) return Region{ c.x0, c.x1, c.y0, c.y1, c.z0, c.z1 };
+	return Region{ (c.x0-L.Hx)/K, (c.x1-L.Hx)/K, c.y0, c.y1, c.z0, c.z1 };
 }
 
 static inline dim3 cell_block(uint32_t nx) { uint32_t bx = 1u; while(bx<nx && bx<128u) bx <<= 1; return dim3(bx, 128u/bx, 1u); }
@@ -51,61 +60,46 @@ static inline Region all_cells(const Lattice& L) { return Region{ L.Hx, L.Nx-L.H
 static uint32_t default_cells_per_thread(int storage) { (void)storage; return 4u; } // tuned on B200, see DESIGN.md
 static bool default_pipelined(int region) { return region!=FX3D_REGION_SHELL; } // the persistent pipelined kernel marches in z; the one-cell shell slabs go to the vector kernel
 
-static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int region, void* stream) {
-	// cells per thread: the vector kernels need the non-halo row length to be a multiple of K; the general kernel takes any size
-	const uint32_t inner = L.Nx-2u*L.Hx;
+// One region, one kernel. Kernel forms are tried in order of preference; a form that is not eligible for this region's shape
+// launches nothing (launch_stream_collide returns 1) and the next one is tried, so a multi-slab SHELL can mix forms safely:
+// every cell of the region list is advanced by exactly one launch.
+static int stream_collide_region(const fx3d_lattice* lat, const Lattice& L, const CellRegion& c, int region, void* stream) {
+	const uint32_t width = c.x1-c.x0; // every x bound is a multiple of x_shell_width() cells from the first non-halo cell
 	const int want = g_variant.load();
-	uint32_t K = 1u;
-	bool pipelined = false;
-	if(want==8 || want==16 || (want==0 && default_pipelined(region))) { // pipelined kernel: 4 cells per thread (2 for D3Q27 FP32)
-		const uint32_t pk = pipe_cells_of(lat->velocity_set, lat->storage);
-		if(inner%pk==0u) { K = pk; pipelined = true; }
-	}
-	if(!pipelined && want!=1) {
-		const uint32_t pref = want==2 ? 2u : want==4 ? 4u : default_cells_per_thread((int)lat->storage);
-		if(inner%pref==0u) K = pref; else if(inner%2u==0u) K = 2u;
-	}
-	std::vector<Region> regs;
 	const bool vf = (lat->features&FX3D_VOLUME_FORCE)!=0u;
-	if(lat->features&(FX3D_SUBGRID|FX3D_MOVING_BOUNDARIES)) { // widenings: whole-row bulk-copy kernel where eligible, else the general kernel (any size)
-		const int reserve = region==FX3D_REGION_INTERIOR ? g_interior_reserve.load() : 0;
-		const int ext = ((lat->features&FX3D_SUBGRID) ? 1 : 0)|((lat->features&FX3D_MOVING_BOUNDARIES) ? 2 : 0);
-		if(want!=1 && inner%4u==0u) {
-			regions_of(L, region, 4u, regs);
-			bool all = !regs.empty();
-			for(size_t k=0u; k<regs.size() && all; k++) {
-				int rc;
-				FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, regs[k], 0, (int)lat->collision, vf, stream, reserve, ext); })
-				if(rc==1 && k==0u) all = false;
-				else if(rc!=FX3D_OK) return rc==1 ? FX3D_ERR_INVALID : rc;
-			}
-			if(all) return FX3D_OK;
-			regs.clear();
-		}
-		regions_of(L, region, 1u, regs);
-		for(const Region& R : regs) {
-			int rc;
-			FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, 1, (int)lat->collision, vf, stream, 0, ext); })
-			if(rc!=FX3D_OK) return rc;
-		}
-		return FX3D_OK;
-	}
-	if(pipelined && want!=8 && K==2u && inner%4u==0u) { // D3Q27 FP32: the bulk-copy kernel (4 cells per thread) where the tile spans whole rows
-		regions_of(L, region, 4u, regs);
-		bool all = !regs.empty();
-		for(size_t k=0u; k<regs.size() && all; k++) {
-			int rc;
-			FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, regs[k], -2, (int)lat->collision, vf, stream, region==FX3D_REGION_INTERIOR ? g_interior_reserve.load() : 0); })
-			if(rc==1 && k==0u) all = false; // not eligible: nothing was launched
-			else if(rc!=FX3D_OK) return rc==1 ? FX3D_ERR_INVALID : rc;
-		}
-		if(all) return FX3D_OK;
-		regs.clear();
-	}
-	regions_of(L, region, K, regs);
-	for(const Region& R : regs) {
+	const int reserve = region==FX3D_REGION_INTERIOR ? g_interior_reserve.load() : 0;
+	auto launch = [&](uint32_t K, int mode, int ext) -> int {
+		const Region R = to_groups(L, c, K);
 		int rc;
-		FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, pipelined ? (want==8 ? -1 : want==16 ? -3 : 0) : (int)K, (int)lat->collision, vf, stream, region==FX3D_REGION_INTERIOR ? g_interior_reserve.load() : 0); })
+		FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, mode, (int)lat->collision, vf, stream, reserve, ext); })
+		return rc;
+	};
+	const bool div4 = width%4u==0u && (c.x0-L.Hx)%4u==0u, div2 = width%2u==0u && (c.x0-L.Hx)%2u==0u;
+	if(lat->features&(FX3D_SUBGRID|FX3D_MOVING_BOUNDARIES)) { // widenings: bulk-copy / hybrid kernel where eligible, else the general kernel (any size)
+		const int ext = ((lat->features&FX3D_SUBGRID) ? 1 : 0)|((lat->features&FX3D_MOVING_BOUNDARIES) ? 2 : 0);
+		if(want!=1 && div4) { const int rc = launch(4u, 0, ext); if(rc!=1) return rc; }
+		return launch(1u, 1, ext);
+	}
+	const uint32_t pk = pipe_cells_of(lat->velocity_set, lat->storage);
+	const bool pipelined = (want==8 || want==16 || (want==0 && default_pipelined(region))) && (pk==4u ? div4 : div2);
+	if(pipelined) {
+		if(want!=8 && pk==2u && div4) { const int rc = launch(4u, -2, 0); if(rc!=1) return rc; } // D3Q27 FP32: the bulk-copy kernel (4 cells per thread) where the tile spans whole rows
+		return launch(pk, want==8 ? -1 : want==16 ? -3 : 0, 0);
+	}
+	uint32_t K = 1u;
+	if(want!=1) {
+		const uint32_t pref = want==2 ? 2u : want==4 ? 4u : default_cells_per_thread((int)lat->storage);
+		if(pref==4u && div4) K = 4u; else if(div2) K = 2u;
+	}
+	return launch(K, (int)K, 0);
+}
+
+static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int region, void* stream) {
+	std::vector<CellRegion> regs;
+	regions_of(L, region, regs);
+	for(const CellRegion& c : regs) {
+		const int rc = stream_collide_region(lat, L, c, region, stream);
+		if(rc==1) { set_error("stream_collide: no kernel form accepts this region"); return FX3D_ERR_INVALID; }
 		if(rc!=FX3D_OK) return rc;
 	}
 	return FX3D_OK;
@@ -129,7 +123,8 @@ size_t fx3d_fi_bytes(const fx3d_lattice* lat) {
 }
 uint32_t fx3d_bytes_per_cell_per_step(const fx3d_lattice* lat) { // src/lbm.cpp:52-57
 	if(!lat) return 0u;
-	return lat->velocity_set*2u*(uint32_t)elem_bytes(lat->storage)+1u+((lat->features&FX3D_UPDATE_FIELDS) ? 16u : 0u);
+	return lat->velocity_set*2u*(uint32_t)elem_bytes(lat->storage)+1u+((lat->features&FX3D_UPDATE_FIELDS) ? 16u : 0u)
+		+((lat->features&FX3D_MOVING_BOUNDARIES) ? lat->velocity_set-1u : 0u); // the reference counts the neighbour flags every cell of a MOVING_BOUNDARIES build loads (:62-64)
 }
 float fx3d_relaxation_rate(float nu) {
 	// def_w = to_string(1.0f/tau)+"f" (src/lbm.cpp:367): the reference formats 1/tau with 1+8 significant decimal digits in

@@ -159,7 +159,8 @@ int fx3d_malloc(int device, size_t bytes, void** ptr) {
 	*ptr = nullptr;
 	if(int rc = use_device(device)) return rc;
 	FX3D_CUDA(cudaMalloc(ptr, bytes ? bytes : 1u), "cudaMalloc");
-	const cudaError_t e = cudaMemset(*ptr, 0, bytes);
+	cudaError_t e = cudaMemset(*ptr, 0, bytes);
+	if(e==cudaSuccess) e = cudaStreamSynchronize(0); // the library's streams are non-blocking: the zero fill must have landed before any of them touches the buffer
 	if(e!=cudaSuccess) { cudaFree(*ptr); *ptr = nullptr; return cuda_fail(e, "cudaMemset"); }
 	return FX3D_OK;
 }

@@ -24,16 +24,7 @@ double Info::time() const {
 	return ((double)steps/done-1.0)*(runtime_total-runtime_total_last);
 }
 void Info::print_logo() const {
-	println(".-----------------------------------------------------------------------------.");
-	println("|  fx3d-b200: lattice Boltzmann stream_collide + halo exchange for NVIDIA B200 |");
-	println("|  behind the FluidX3D host API (LBM / LBM_Domain / Memory<T>)                 |");
-	println("|-----------------------------------------------------------------------------|");
-}
-static string hms(const double seconds) {
-	const ulong s = (ulong)max(seconds, 0.0);
-	char b[64];
-	std::snprintf(b, sizeof(b), "%luh %02lum %02lus", (unsigned long)(s/3600ull), (unsigned long)((s/60ull)%60ull), (unsigned long)(s%60ull));
-	return b;
+	println("fx3d-b200 -- lattice Boltzmann stream_collide + halo exchange for NVIDIA B200 behind the FluidX3D host API");
 }
 void Info::print_initialize(LBM* l) {
 	std::lock_guard<std::mutex> lock(allow_printing);
@@ -52,34 +43,26 @@ void Info::print_initialize(LBM* l) {
 #endif
 	cpu_mem_required = (uint)(lbm->get_N()*(ulong)bytes_per_cell_host()/1048576ull);
 	gpu_mem_required = lbm->lbm_domain[0]->get_device().info.memory_used;
-	const float Re = lbm->get_Re_max();
-	println("|-----------------.-----------------------------------------------------------|");
-	println("| Grid Resolution | "+alignr(57u, to_string(lbm->get_Nx())+" x "+to_string(lbm->get_Ny())+" x "+to_string(lbm->get_Nz())+" = "+to_string(lbm->get_N()))+" |");
-	println("| Grid Domains    | "+alignr(57u, to_string(lbm->get_Dx())+" x "+to_string(lbm->get_Dy())+" x "+to_string(lbm->get_Dz())+" = "+to_string(lbm->get_D()))+" |");
-	println("| LBM Type        | "+alignr(57u, "D3Q"+to_string(lbm->get_velocity_set())+" "+collision)+" |");
-	println("| Memory Usage    | "+alignr(54u, "CPU "+to_string(cpu_mem_required)+" MB, GPU "+to_string(lbm->get_D())+"x "+to_string(gpu_mem_required))+" MB |");
-	println("| Time Steps      | "+alignr(57u, steps==max_ulong ? string("infinite") : to_string(steps))+" |");
-	println("| Kin. Viscosity  | "+alignr(57u, to_string(lbm->get_nu(), 8u))+" |");
-	println("| Relaxation Time | "+alignr(57u, to_string(lbm->get_tau(), 8u))+" |");
-	println("| Reynolds Number | "+alignr(57u, "Re < "+(Re>=100.0f ? to_string(to_uint(Re)) : to_string(Re, 6u)))+" |");
-#ifdef VOLUME_FORCE
-	println("| Volume Force    | "+alignr(57u, alignr(15u, to_string(lbm->get_fx(), 8u))+","+alignr(15u, to_string(lbm->get_fy(), 8u))+","+alignr(15u, to_string(lbm->get_fz(), 8u)))+" |");
-#endif
-	println("|---------.-------'-----.-----------.-------------------.---------------------|");
-	println("| MLUPs   | Bandwidth   | Steps/s   | Current Step      | "+string(steps==max_ulong ? "Elapsed Time  " : "Time Remaining")+"      |");
+	// one summary line instead of the reference's console table (the table is OUT OF SCOPE; the metric is not)
+	char b[512];
+	std::snprintf(b, sizeof(b), "grid %ux%ux%u = %llu cells in %ux%ux%u domains | D3Q%u %s | nu %.8g tau %.8g | host %u MB, device %ux %u MB | steps %s",
+		lbm->get_Nx(), lbm->get_Ny(), lbm->get_Nz(), (unsigned long long)lbm->get_N(), lbm->get_Dx(), lbm->get_Dy(), lbm->get_Dz(), lbm->get_velocity_set(), collision.c_str(),
+		(double)lbm->get_nu(), (double)lbm->get_tau(), cpu_mem_required, lbm->get_D(), gpu_mem_required, steps==max_ulong ? "unbounded" : to_string(steps).c_str());
+	println(b);
 	clock.start();
 }
 void Info::print_update() const {
 	if(lbm==nullptr) return;
 	std::lock_guard<std::mutex> lock(const_cast<std::mutex&>(allow_printing));
 	if(lbm==nullptr) return;
-	const double dt = runtime_lbm_timestep_smooth;
-	std::cout << "\r|" << alignr(8u, to_string(to_uint((double)lbm->get_N()*1E-6/dt))) << " |"
-		<< alignr(7u, to_string(to_uint((double)lbm->get_N()*(double)bandwidth_bytes_per_cell_device()*1E-9/dt))) << " GB/s |"
-		<< alignr(10u, to_string(to_uint(1.0/dt))) << " | " << alignr(17u, to_string(lbm->get_t())) << " | " << alignr(19u, hms(time())) << " |" << std::flush;
+	const double dt = runtime_lbm_timestep_smooth; // MLUPs/s = N*1e-6/dt (src/info.cpp:109), GB/s = MLUPs * bytes per cell and step (src/lbm.cpp:52)
+	char b[256];
+	std::snprintf(b, sizeof(b), "\r%9u MLUPs/s %7u GB/s %8u steps/s   t = %llu   %s %.0f s   ", to_uint((double)lbm->get_N()*1E-6/dt),
+		to_uint((double)lbm->get_N()*(double)bandwidth_bytes_per_cell_device()*1E-9/dt), to_uint(1.0/dt), (unsigned long long)lbm->get_t(), steps==max_ulong ? "elapsed" : "remaining", time());
+	std::cout << b << std::flush;
 }
 void Info::print_finalize() {
 	std::lock_guard<std::mutex> lock(allow_printing);
 	lbm = nullptr;
-	println("\n|---------'-------------'-----------'-------------------'---------------------|");
+	println("");
 }

@@ -248,7 +248,9 @@ void LBM::sanity_checks_initialization() { // which extensions do the flags call
 	});
 	bool e = false, m = false; uchar used = 0u;
 	for(uint t=0u; t<threads; t++) { e = e||uses_e[t]; m = m||moving[t]; used = used|any[t]; }
-	if(m) print_warning("Some boundary cells have non-zero velocity, but MOVING_BOUNDARIES is not part of this build.");
+#ifndef MOVING_BOUNDARIES
+	if(m) print_warning("Some boundary cells have non-zero velocity, but MOVING_BOUNDARIES is not enabled.");
+#endif
 #ifndef EQUILIBRIUM_BOUNDARIES
 	if(e) print_error("Some cells are set as equilibrium boundaries with the TYPE_E flag, but EQUILIBRIUM_BOUNDARIES is not enabled. Uncomment \"#define EQUILIBRIUM_BOUNDARIES\" in defines.hpp.");
 #else

@@ -198,6 +198,32 @@ def test_shell_plus_interior_equals_all(emul, variant):
         assert np.array_equal(bits(a), bits(b))
 
 
+OVERLAP_CASES = [((27, SRT, FP32, 0), (24, 6, 6), (2, 1, 1)),      # SHELL on the vector kernel (K=4), INTERIOR on the ring kernel (K=2): the x split must not follow K
+                 ((19, SRT, FP32, 8), (1040, 2, 2), (2, 1, 1)),    # SUBGRID: general kernel for one region, hybrid kernel for the other
+                 ((19, SRT, FP16S, 8), (128, 16, 8), (1, 2, 2)),   # SUBGRID: z slabs eligible for the bulk-copy kernel, one-row y slabs not (per-region fallback)
+                 ((19, TRT, FP16S, 19), (24, 10, 8), (2, 2, 2)),   # MOVING_BOUNDARIES + force + TYPE_E
+                 ((19, SRT, FP16C, 0), (22, 6, 6), (2, 1, 2)),     # row length divisible by 2 only
+                 ((27, TRT, FP16S, 3), (18, 5, 7), (2, 1, 1))]     # odd row length: one-cell x shell
+
+
+@pytest.mark.parametrize("v,dims,D", OVERLAP_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in OVERLAP_CASES])
+def test_shell_plus_interior_default_dispatch(emul, v, dims, D):
+    """overlap mode with the library's own kernel choice (variant 0): the SHELL and INTERIOR passes may pick different kernel
+    forms with different cells per thread, and still every non-halo cell must be advanced exactly once (round-1 advisor finding)"""
+    f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
+    emul.set_kernel_variant(0)
+    sim = LBM(*dims, 0.05, *f, Dx=D[0], Dy=D[1], Dz=D[2], velocity_set=v[0], collision=v[1], storage=v[2], features=v[3], lib=emul, overlap=True)
+    rho, u, flags = scenario(sim.Nx, sim.Ny, sim.Nz, seed=3, eq_frac=0.03 if v[3] & 2 else 0.0)
+    sim.rho.set_global(rho); [sim.u.set_global(u[a], a) for a in range(3)]; sim.flags.set_global(flags)
+    sim.run(3)
+    for m in (sim.rho, sim.u, sim.flags): m.read_from_device()
+    got = (sim.rho.get_global(), sim.u.get_global(0), sim.u.get_global(1), sim.u.get_global(2), sim.flags.get_global())
+    sim.close()
+    want = oracle(v, dims, D, 3, f)
+    for a, b in zip(got, want):
+        assert np.array_equal(bits(a), bits(b))
+
+
 def test_library_exports_every_declared_symbol():
     # the product library itself (built by nvcc) must load without a GPU and export everything include/fx3d.h declares
     import re
