@@ -5,9 +5,13 @@ the HBM roofline, on the workload BASELINE.json's metric is quoted on.
   python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
 
 N=1 workload (BASELINE.json configs[1]): D3Q19 SRT, FP16S-compressed DDFs, 512^3 fully periodic box, default fields.
-N>1 (torchrun, one process per GPU): weak scaling, every GPU owns one 512^3 FP16S domain of a Dx x Dy x Dz decomposition
-(2x1x1, 2x2x1, 2x2x2) and exchanges halos with its neighbours by direct NVLink peer loads.
+N>1 (torchrun, one process per GPU): weak scaling, every GPU owns one 512^3 FP16S domain of a Dx x Dy x Dz decomposition --
+by default the reference's convention 2x1x1, 2x2x1, 2x2x2 (README.md:1425; x is decomposed first), `--split` for any other --
+and exchanges halos with its neighbours over NVLink (CUDA-IPC peer memory; no host round trip).
 A "step" is one LBM time step (stream_collide over every cell, plus the halo exchange when decomposed).
+Before anything is timed, every run verifies the path it is about to measure: a 64^3-per-GPU perturbed-IC case of the same
+lattice model runs 20 steps on the same devices / peer links and rank 0 compares every domain's rho and u with the CPU oracle's
+decomposed run bit for bit ("verify" in the JSON line; a mismatch ends the run with a non-zero exit code).
 
 One JSON line on stdout (rank 0). Keys follow the driver contract; see DESIGN.md section "Measurement".
 """
@@ -40,8 +44,9 @@ WORKLOADS = {
 }
 DEFAULT_OVERLAP = False  # multi-GPU step: overlap the halo exchange with the interior cells
 DEFAULT_WORKLOAD = "d3q19_srt_fp16s_512"
-# weak scaling: every GPU keeps the full per-GPU box; domains are stacked along z first, then y (faces that are contiguous in memory)
-SPLITS = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (1, 2, 4)}
+# weak scaling: every GPU keeps the full per-GPU box. Default domain grid = the reference's multi-GPU convention (README.md:1425,
+# src/setup.cpp:20-23): x first. `--split 1,2,4` stacks along z and y instead (faces that are contiguous in memory).
+SPLITS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 
 
 def make_scene(workload, fx, Nx, Ny, Nz):
@@ -115,8 +120,8 @@ def reference_arm(args, wl_name):
     Q, coll, st, feat, box, desc = WORKLOADS[wl_name]
     collision, storage = {"srt": H.SRT, "trt": H.TRT}[coll], {"fp32": H.FP32, "fp16s": H.FP16S, "fp16c": H.FP16C}[st]
     kind = "reference" if H.ref_available(Q, collision, storage, feat) else "port"
-    backend = (H.RefBackend if kind == "reference" else H.OracleBackend)(Q, collision, storage, feat)
-    cores = os.cpu_count() or 1
+    cores = os.cpu_count() or 1  # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
+    backend = (H.RefBackend if kind == "reference" else H.OracleBackend)(Q, collision, storage, feat, threads=cores)
     n = 128 if cores < 32 else 192  # bounded sample: an n^3 sub-box of the workload, same kernels, same IC
     sim = H.HostSim(backend, n, n, n, nu=1.0)
     sim.run(0)
@@ -141,8 +146,8 @@ def cpu_baseline(wl_name, budget_s=15.0):
     Q, coll, st, feat, box, desc = WORKLOADS[wl_name]
     collision, storage = {"srt": H.SRT, "trt": H.TRT}[coll], {"fp32": H.FP32, "fp16s": H.FP16S, "fp16c": H.FP16C}[st]
     kind = "reference" if H.ref_available(Q, collision, storage, feat) else "port"
-    backend = (H.RefBackend if kind == "reference" else H.OracleBackend)(Q, collision, storage, feat)
     cores = os.cpu_count() or 1
+    backend = (H.RefBackend if kind == "reference" else H.OracleBackend)(Q, collision, storage, feat, threads=cores)
     n = 128
     sim = H.HostSim(backend, n, n, n, nu=1.0)
     sim.run(2)
@@ -153,6 +158,45 @@ def cpu_baseline(wl_name, budget_s=15.0):
     return {"value": round(n ** 3 * steps / dt * 1e-6, 2), "unit": "MLUPs/s", "cores": cores, "kind": kind,
             "sample": f"{n}^3 sub-box of the workload, {steps} steps, {cores} OpenMP threads, "
                       + ("reference kernel.cpp device code compiled natively (oracle/_ref)" if kind == "reference" else "oracle port")}
+
+
+def verify(fx, comm, Q, collision, storage, feat, split, device, overlap):
+    """the path about to be timed, checked first: 64^3 cells per GPU, perturbed initial condition (plus random TYPE_S / TYPE_E cells where
+    the workload has boundaries), 20 steps on the same devices and peer links; rank 0 compares every domain with the oracle bit for bit"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import helpers as H
+    Dx, Dy, Dz = split
+    n, steps, nu = 64, 20, 0.05
+    Nx, Ny, Nz = n * Dx, n * Dy, n * Dz
+    f = (1e-5, -2e-5, 3e-5) if feat & 1 else (0.0, 0.0, 0.0)
+    rho, u, flags = H.scenario(Nx, Ny, Nz, seed=21, solid_frac=0.05 if feat & (2 | 16) else 0.0, eq_frac=0.03 if feat & 2 else 0.0)
+    sim = fx.LBM(Nx, Ny, Nz, nu, *f, Dx=Dx, Dy=Dy, Dz=Dz, velocity_set=Q, collision=collision, storage=storage, features=feat,
+                 comm=comm, devices=None if comm else [device], overlap=overlap)
+    sim.rho.set_global(rho); [sim.u.set_global(u[a], a) for a in range(3)]; sim.flags.set_global(flags)
+    sim.run(steps)
+    sim.rho.read_from_device(); sim.u.read_from_device()
+    mine = [sim.rho.get_global(), sim.u.get_global(0), sim.u.get_global(1), sim.u.get_global(2)]  # zero outside the domain this process owns
+    (d, _), = sim.local_domains()
+    sim.close()
+    parts = comm.allgather((d, mine)) if comm is not None else [(d, mine)]
+    rank = comm.rank if comm is not None else 0
+    result = None
+    if rank == 0:
+        ref = H.HostSim(H.OracleBackend(Q, collision, storage, feat, threads=os.cpu_count() or 1), Nx, Ny, Nz, Dx, Dy, Dz, nu=nu, fx=f[0], fy=f[1], fz=f[2])
+        H.load_scenario(ref, rho, u, flags)
+        ref.run(steps)
+        want = ref.fields()[:4]
+        bad = 0
+        for dd, arrs in parts:
+            x, y, z = (dd % (Dx * Dy)) % Dx, (dd % (Dx * Dy)) // Dx, dd // (Dx * Dy)
+            sl = (slice(z * n, (z + 1) * n), slice(y * n, (y + 1) * n), slice(x * n, (x + 1) * n))
+            bad += sum(int(np.sum(a[sl].view(np.uint32) != b[sl].view(np.uint32))) for a, b in zip(arrs, want))
+        result = {"ok": bad == 0, "split": [Dx, Dy, Dz], "grid": [Nx, Ny, Nz], "steps": steps, "mismatching_values": bad,
+                  "what": "rho and u of every domain vs the CPU oracle's decomposed run, bit for bit, on the devices and peer links of the timed run"}
+    if comm is not None:
+        result = comm.allgather(result)[0]
+    return result
 
 
 def main():
@@ -168,7 +212,9 @@ def main():
     ap.add_argument("--reserve", type=int, default=-1, help="resident-block slots the interior kernel leaves free for the exchange (with --overlap 1)")
     ap.add_argument("--strong", action="store_true", help="strong scaling: the workload's box is the GLOBAL grid, divided among the GPUs")
     ap.add_argument("--split", default="", help="Dx,Dy,Dz domain grid for multi-GPU runs (default: z first, then y)")
-    ap.add_argument("--variant", type=int, default=0, help="kernel choice: 0 default (pipelined), 1 general one-cell-per-thread, 2 or 4 cells per thread, 8 pipelined")
+    ap.add_argument("--variant", type=int, default=0, help="kernel choice (fx3d_set_kernel_variant): 0 library default (bulk-copy kernels where eligible), 1 general one-cell-per-thread, "
+                    "2 or 4 vector kernel with that many cells per thread, 8 persistent kernel with the cp.async ring, 16 bulk copies wherever eligible (incl. bulk stores on row segments)")
+    ap.add_argument("--no-verify", action="store_true", help="skip the bit-exact check against the oracle that precedes the timed region")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -214,6 +260,12 @@ def main():
 
     overlap = DEFAULT_OVERLAP if args.overlap < 0 else bool(args.overlap)
     if args.reserve >= 0: lib.set_interior_reserve(args.reserve)
+    verified = None
+    if not args.no_verify:
+        verified = verify(fx, comm, Q, collision, storage, feat, (Dx, Dy, Dz), device, overlap)
+        if not verified["ok"]:
+            if rank == 0: print(json.dumps({"metric": "MLUPs/s", "value": None, "verify": verified, "error": "the CUDA path differs from the oracle; nothing was timed"}), flush=True)
+            return 3
     # ---------------- device-resident arm: `value` ----------------
     force = (0.0, 1e-6, 0.0) if feat & 1 else (0.0, 0.0, 0.0)
     nu = 0.1 * (Nz - 2) / 1000.0 if "cavity" in args.workload else 1.0
@@ -252,7 +304,10 @@ def main():
         ms_total = float(t.item())
     cells = Nx * Ny * Nz
     mlups = cells * K / (ms_total * 1e-3) * 1e-6
-    bytes_per_cell = sim.bandwidth_bytes_per_cell_device()
+    # algorithmic bytes per cell and step: 2*Q*sizeof(fpxx)+1 (+16 with UPDATE_FIELDS), SURVEY 8d. The reference's own accounting
+    # (bandwidth_bytes_per_cell_device, src/lbm.cpp:52-64) adds Q-1 neighbour-flag bytes for MOVING_BOUNDARIES builds; this path reads
+    # those flags only for the few TYPE_MS cells, so they are not counted here (that would flatter the roofline fraction)
+    bytes_per_cell = 2 * Q * (4 if st == "fp32" else 2) + 1 + (16 if feat & 4 else 0)
     peak, peak_src = measured_peaks()
     per_gpu_gbs = (cells / n_gpus) * bytes_per_cell * K / (ms_total * 1e-3) * 1e-9
     traffic = None
@@ -304,7 +359,7 @@ def main():
                 "dtype": "f32 arithmetic, " + st + " DDF storage", "data": "synthetic",
                 "config": {"workload": args.workload, "description": desc, "global_grid": [Nx, Ny, Nz], "domains": [Dx, Dy, Dz], "overlap": bool(overlap and n_gpus > 1),
                            "cache": "DDF working set per GPU (%.1f GB) is far larger than the 126 MB L2; no flush needed" % (cells / n_gpus * Q * (4 if st == "fp32" else 2) * 1e-9)},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "verify": verified}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

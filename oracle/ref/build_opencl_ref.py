@@ -8,7 +8,9 @@ is copied to a scratch directory under /tmp, src/defines.hpp is switched per con
 own #define lines, nothing else), and it is compiled with the reference's own command line (make.sh:26).
 
   FluidX3D_bench_<fp32|fp16s|fp16c>    the reference's own BENCHMARK setup (src/setup.cpp:5-36), untouched: prints "Peak MLUPs/s"
-  FluidX3D_<variant>                   src/setup.cpp replaced by oracle/ref/opencl_setup.cpp (file in, N steps, file out / timing)
+  FluidX3D_<variant>                   src/setup.cpp replaced by tests/scenes/file_scene.cpp (file in, N steps, file out / timing)
+  FluidX3D_<variant>+ptx               the same, compiled with the reference's own -DPTX switch (src/opencl.hpp:328-330): the program also
+                                       writes the driver-generated PTX of its kernels to ./bin/kernel.ptx (read with ptxas -v / cuobjdump)
 
 Variant names as in build_ref.py: q<19|27>_<srt|trt>_<fp32|fp16s|fp16c>_f<mask> (bit0 VOLUME_FORCE, bit1 EQUILIBRIUM_BOUNDARIES,
 bit3 SUBGRID, bit4 MOVING_BOUNDARIES).
@@ -19,14 +21,16 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(os.path.dirname(HERE), "_ref", "opencl")
 CXX = "/usr/bin/g++"
+SCENE = os.path.join(os.path.dirname(os.path.dirname(HERE)), "tests", "scenes", "file_scene.cpp")
 DEFAULT = ["bench_fp32", "bench_fp16s", "bench_fp16c",
            "q19_srt_fp32_f0", "q19_srt_fp16s_f0", "q19_srt_fp16c_f0", "q19_trt_fp16s_f3", "q27_trt_fp32_f3", "q27_srt_fp16c_f0",
-           "q19_srt_fp32_f16", "q19_srt_fp16s_f8"]
+           "q19_srt_fp32_f16", "q19_srt_fp16s_f8", "q19_srt_fp32_f0+ptx", "q19_srt_fp16s_f0+ptx", "q19_srt_fp16c_f0+ptx"]
 SWITCHES = ["D2Q9", "D3Q15", "D3Q19", "D3Q27", "SRT", "TRT", "FP16S", "FP16C", "BENCHMARK", "VOLUME_FORCE", "FORCE_FIELD", "EQUILIBRIUM_BOUNDARIES",
             "MOVING_BOUNDARIES", "SURFACE", "TEMPERATURE", "SUBGRID", "PARTICLES", "INTERACTIVE_GRAPHICS", "INTERACTIVE_GRAPHICS_ASCII", "GRAPHICS"]
 
 
 def wanted_defines(name):
+    name = name.split("+")[0]
     if name.startswith("bench_"):
         st = name.split("_")[1]
         on = {"D3Q19", "SRT", "BENCHMARK"}
@@ -61,14 +65,15 @@ def build(name, ref, scratch):
     if not name.startswith("bench_"):
         spath = os.path.join(src, "setup.cpp")
         os.chmod(spath, 0o644)
-        shutil.copyfile(os.path.join(HERE, "opencl_setup.cpp"), spath)
+        shutil.copyfile(SCENE, spath)
     objs = []
     cpps = sorted(f for f in os.listdir(src) if f.endswith(".cpp"))
     jobs = []
     for f in cpps:
         o = os.path.join(scratch, name, f[:-4] + ".o")
         objs.append(o)
-        jobs.append([CXX, "-c", os.path.join(src, f), "-o", o, "-std=c++17", "-pthread", "-O", "-Wno-comment", "-w", "-I" + os.path.join(src, "OpenCL", "include")])
+        jobs.append([CXX, "-c", os.path.join(src, f), "-o", o, "-std=c++17", "-pthread", "-O", "-Wno-comment", "-w", "-I" + os.path.join(src, "OpenCL", "include")]
+                    + (["-DPTX"] if name.endswith("+ptx") else []))
     return name, src, objs, jobs
 
 
@@ -80,7 +85,7 @@ def main():
     args = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
     stamp = lambda n: os.path.join(OUT, "FluidX3D_" + n)
-    newest_input = max(os.path.getmtime(os.path.join(HERE, f)) for f in ("opencl_setup.cpp", "build_opencl_ref.py"))
+    newest_input = max(os.path.getmtime(SCENE), os.path.getmtime(os.path.join(HERE, "build_opencl_ref.py")))
     names = [n for n in args.variants.split(",") if n and (args.force or not os.path.exists(stamp(n)) or os.path.getmtime(stamp(n)) < newest_input)]
     if not names:
         print("oracle/_ref/opencl is up to date"); return 0

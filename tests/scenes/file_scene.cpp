@@ -1,7 +1,9 @@
-// opencl_setup.cpp -- TEST INFRASTRUCTURE ONLY. A main_setup() for the UNMODIFIED reference program (FluidX3D v3.7), compiled
-// in place of its src/setup.cpp by oracle/ref/build_opencl_ref.py, so that the reference's own OpenCL implementation can run
-// beside this repository's CUDA path on the same B200 (SURVEY 8d "Reference beside it (i)", 8c "On the B200 box").
-// Uses only the reference's public host API (class LBM, Memory_Container, run(), read_from_device(); src/lbm.hpp:208-611).
+// file_scene.cpp -- TEST INFRASTRUCTURE ONLY. One main_setup() written against the reference's public host API (class LBM,
+// Memory_Container, run(), read_from_device(), update_moving_boundaries(); FluidX3D v3.7 src/lbm.hpp:208-611) and compiled twice:
+//   * in place of the reference's src/setup.cpp (oracle/ref/build_opencl_ref.py), so that the UNMODIFIED reference program runs
+//     its own OpenCL implementation beside this repository's CUDA path on the same B200 (SURVEY 8d "Reference beside it (i)")
+//   * against this repository's C++ host surface fluidx3d_b200/host/ (tests/test_host_scene.py): the same scene source is the
+//     drop-in proof, and its output is compared with the oracle bit for bit.
 // Everything is steered by environment variables, because the reference's command line carries device IDs (src/lbm.cpp:658):
 //   FX3D_REF_IN     input file: uint32 Nx,Ny,Nz, then rho[N], ux[N], uy[N], uz[N] (float32) and flags[N] (uint8), n = x+(y+z*Ny)*Nx
 //                   (absent: the constructor defaults rho=1, u=0, flags=0 and FX3D_REF_N="Nx,Ny,Nz")

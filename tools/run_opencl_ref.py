@@ -3,7 +3,7 @@
 /root/reference tree) beside this repository's CUDA path on the same B200 (SURVEY 8d "Reference beside it (i)").
 
   * its BENCHMARK setup (src/setup.cpp:5-36) for FP32 / FP16S / FP16C at 256^3 -> "Peak MLUPs/s"
-  * the same box sizes as bench.py's workloads through oracle/ref/opencl_setup.cpp (host-clock MLUPs/s over N steps)
+  * the same box sizes as bench.py's workloads through tests/scenes/file_scene.cpp (host-clock MLUPs/s over N steps)
   * parity: identical perturbed initial conditions, N steps, fields dumped by read_from_device(): flags must be identical,
     rho/u within 1e-5 (FP32) / 1e-3 (FP16 storage) relative -- the north_star's literal correctness clause
 
@@ -151,6 +151,8 @@ def main():
             print("   cells with |du| > 1e-6:", int(np.sum(diff.max(axis=0) > 1e-6)), "of", int(fluid.sum()), "fluid cells; median |du|", float(np.median(diff.max(axis=0)[fluid])))
             np.savez_compressed(os.path.join(OUTDIR, f"ocl_case_{variant}_{steps}.npz"), ours=ours, ref=f_ref, flags=flags)
     log.close()
+    for f in ("ref_in.bin", "ref_out.bin"):  # up to 285 MB each: not for the 64 MiB that travels back
+        if os.path.exists(os.path.join(OUTDIR, f)): os.remove(os.path.join(OUTDIR, f))
     report["all_ok"] = all(e.get("ok") for e in report["parity"])
     json.dump(report, open(os.path.join(OUTDIR, "r02_reference_opencl.json"), "w"), indent=1)
     print("ALL PARITY CASES OK" if report["all_ok"] else "SOME PARITY CASES FAILED")
