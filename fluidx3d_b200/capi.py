@@ -69,6 +69,8 @@ _SIGS = {
     "fx3d_stream_collide_launches": (_I, [_I, C.POINTER(_U64)], True),
     "fx3d_set_interior_reserve": (_I, [_I], True),
     "fx3d_stream_collide": (_I, [_LP, _U64, _F, _F, _F, _I, _VP], True),
+    "fx3d_stream_collide_fused": (_I, [_LP, _U64, _F, _F, _F, C.POINTER(_VP), _VP], True),
+    "fx3d_fused_halo_supported": (_I, [_LP], False),
     "fx3d_update_fields": (_I, [_LP, _U64, _F, _F, _F, _VP], True),
     "fx3d_run_steps": (_I, [_LP, _U64, _U64, _F, _F, _F, _VP], True),
     "fx3d_set_kernel_variant": (_I, [_I], True),
@@ -134,12 +136,12 @@ class Lib:
         self.launch_count(C.byref(v))
         return v.value
 
-    KERNEL_KINDS = ("k_stream_collide_v1", "k_stream_collide_vec", "k_stream_collide_pipe", "k_stream_collide_tma", "k_stream_collide_tma_seg", "k_stream_collide_hyb")
+    KERNEL_KINDS = ("k_stream_collide_v1", "k_stream_collide_vec", "k_stream_collide_pipe", "k_stream_collide_tma", "k_stream_collide_tma_seg", "k_stream_collide_hyb", "k_stream_collide_occ", "k_stream_collide_row")
 
     def kernel_kind_counts(self):
         """stream_collide launches so far per kernel kind (same order as KERNEL_KINDS)"""
         out = []
-        for k in range(6):
+        for k in range(len(self.KERNEL_KINDS)):
             v = C.c_uint64(0)
             self.stream_collide_launches(k, C.byref(v))
             out.append(v.value)

@@ -54,8 +54,8 @@ inline bool make_lattice(const fx3d_lattice* in, uint64_t t, float fx, float fy,
 inline size_t elem_bytes(uint32_t storage) { return storage==FX3D_FP32 ? 4u : 2u; }
 
 // stream_collide instantiations live in one translation unit per (velocity set, storage), see sc_inst.cu
-extern std::atomic<uint64_t> g_kind_launches[6]; // stream_collide launches by kernel kind: 0 general, 1 vector, 2 cp.async ring, 3 bulk copies (rows), 4 bulk copies (segments), 5 bulk loads + direct stores
+extern std::atomic<uint64_t> g_kind_launches[8]; // stream_collide launches by kernel kind: 0 general, 1 vector, 2 cp.async ring, 3 bulk copies (rows), 4 bulk copies (segments), 5 bulk loads + direct stores, 6 one cell per thread at high occupancy, 7 bulk copies (rows, shared ring)
 inline uint32_t pipe_cells_of(uint32_t velocity_set, uint32_t storage) { return (storage==FX3D_FP32 && velocity_set>19u) ? 2u : 4u; } // = pipe_cells<Q,ST>()
-template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, int cells_per_thread, int collision, bool volume_force, void* stream, int reserve=0, int ext=0); // cells_per_thread 0: persistent kernel chosen automatically (-1: cp.async ring, -2: whole-row bulk copies or nothing, -3: bulk copies wherever eligible), leaving `reserve` resident-block slots free
+template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, int cells_per_thread, int collision, bool volume_force, void* stream, int reserve=0, int ext=0, const RowPeers* fused=nullptr); // cells_per_thread 0: persistent kernel chosen automatically (-1: cp.async ring, -2: whole-row bulk copies or nothing, -3: bulk copies wherever eligible), leaving `reserve` resident-block slots free
 
 } // namespace fx3d

@@ -14,7 +14,7 @@ void set_error(const std::string& msg) { t_error = msg; }
 std::atomic<uint64_t> g_launches{0ull};
 std::atomic<int> g_variant{0};
 std::atomic<int> g_interior_reserve{8};
-std::atomic<uint64_t> g_kind_launches[6];
+std::atomic<uint64_t> g_kind_launches[8];
 
 // Non-halo extent and the shell / interior split used to overlap the halo exchange with computation, in CELLS. The shell is
 // every non-halo cell within one cell of a halo layer in y and z, and within XS cells in x, where XS (4, 2 or 1) is the largest
@@ -63,7 +63,7 @@ static bool default_pipelined(int region) { return region!=FX3D_REGION_SHELL; } 
 // One region, one kernel. Kernel forms are tried in order of preference; a form that is not eligible for this region's shape
 // launches nothing (launch_stream_collide returns 1) and the next one is tried, so a multi-slab SHELL can mix forms safely:
 // every cell of the region list is advanced by exactly one launch.
-static int stream_collide_region(const fx3d_lattice* lat, const Lattice& L, const CellRegion& c, int region, void* stream) {
+static int stream_collide_region(const fx3d_lattice* lat, const Lattice& L, const CellRegion& c, int region, void* stream, const RowPeers* fused=nullptr, bool query=false) {
 	const uint32_t width = c.x1-c.x0; // every x bound is a multiple of x_shell_width() cells from the first non-halo cell
 	const int want = g_variant.load();
 	const bool vf = (lat->features&FX3D_VOLUME_FORCE)!=0u;
@@ -71,15 +71,21 @@ static int stream_collide_region(const fx3d_lattice* lat, const Lattice& L, cons
 	auto launch = [&](uint32_t K, int mode, int ext) -> int {
 		const Region R = to_groups(L, c, K);
 		int rc;
-		FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, mode, (int)lat->collision, vf, stream, reserve, ext); })
+		FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { rc = (launch_stream_collide<Q, ST>)(L, R, query ? -100 : mode, (int)lat->collision, vf, stream, reserve, ext, fused); })
 		return rc;
 	};
 	const bool div4 = width%4u==0u && (c.x0-L.Hx)%4u==0u, div2 = width%2u==0u && (c.x0-L.Hx)%2u==0u;
+	if(fused || query) { // fused y/z halo delivery exists in the whole-row bulk-copy kernel only (4 cells per thread)
+		if(!div4 || want==1 || want==2 || want==4 || want==8 || want==32) return 1;
+		const int ext = ((lat->features&FX3D_SUBGRID) ? 1 : 0)|((lat->features&FX3D_MOVING_BOUNDARIES) ? 2 : 0);
+		return launch(4u, ext ? 0 : -2, ext);
+	}
 	if(lat->features&(FX3D_SUBGRID|FX3D_MOVING_BOUNDARIES)) { // widenings: bulk-copy / hybrid kernel where eligible, else the general kernel (any size)
 		const int ext = ((lat->features&FX3D_SUBGRID) ? 1 : 0)|((lat->features&FX3D_MOVING_BOUNDARIES) ? 2 : 0);
 		if(want!=1 && div4) { const int rc = launch(4u, 0, ext); if(rc!=1) return rc; }
 		return launch(1u, 1, ext);
 	}
+	if(want==32) return launch(1u, 32, 0);
 	const uint32_t pk = pipe_cells_of(lat->velocity_set, lat->storage);
 	const bool pipelined = (want==8 || want==16 || (want==0 && default_pipelined(region))) && (pk==4u ? div4 : div2);
 	if(pipelined) {
@@ -105,15 +111,29 @@ static int stream_collide_impl(const fx3d_lattice* lat, const Lattice& L, int re
 	return FX3D_OK;
 }
 
+static int stream_collide_fused_impl(const fx3d_lattice* lat, const Lattice& L, void* const* fi_neighbours, void* stream, bool query) {
+	std::vector<CellRegion> regs;
+	regions_of(L, FX3D_REGION_ALL, regs);
+	RowPeers peers;
+	for(int k=0; k<9; k++) peers.fi[k] = fi_neighbours ? fi_neighbours[k] : nullptr;
+	if(!query) for(int dz=-1; dz<=1; dz++) for(int dy=-1; dy<=1; dy++) { // every neighbour the kernel can route a row to must be there
+		const bool needed = (dy==0 || L.Hy) && (dz==0 || L.Hz) && (dy!=0 || dz!=0);
+		if(needed && !peers.fi[(dy+1)+3*(dz+1)]) { set_error("stream_collide_fused: a y/z neighbour's DDF buffer is null"); return FX3D_ERR_INVALID; }
+	}
+	const int rc = stream_collide_region(lat, L, regs[0], FX3D_REGION_ALL, stream, &peers, query);
+	if(rc==1) { if(!query) set_error("stream_collide_fused: this lattice shape is not taken by the whole-row bulk-copy kernel (see fx3d_fused_halo_supported)"); return query ? 1 : FX3D_ERR_INVALID; }
+	return rc;
+}
+
 } // namespace fx3d
 using namespace fx3d;
 
 extern "C" {
 
 const char* fx3d_last_error(void) { return t_error.c_str(); }
-int fx3d_set_kernel_variant(int variant) { if(variant!=0&&variant!=1&&variant!=2&&variant!=4&&variant!=8&&variant!=16) { set_error("variant must be 0 (auto), 1 (general), 2 or 4 (cells per thread), 8 (pipelined, cp.async), 16 (pipelined, bulk copies where eligible)"); return FX3D_ERR_INVALID; } g_variant = variant; return FX3D_OK; }
+int fx3d_set_kernel_variant(int variant) { if(variant!=0&&variant!=1&&variant!=2&&variant!=4&&variant!=8&&variant!=16&&variant!=32) { set_error("variant must be 0 (auto), 1 (general), 2 or 4 (cells per thread), 8 (pipelined, cp.async), 16 (pipelined, bulk copies where eligible), 32 (one cell per thread at high occupancy)"); return FX3D_ERR_INVALID; } g_variant = variant; return FX3D_OK; }
 int fx3d_set_interior_reserve(int blocks) { if(blocks<0||blocks>1024) { set_error("reserve must be 0..1024 blocks"); return FX3D_ERR_INVALID; } g_interior_reserve = blocks; return FX3D_OK; }
-int fx3d_stream_collide_launches(int kind, uint64_t* launches) { if(kind<0||kind>5||!launches) { set_error("kind must be 0..5"); return FX3D_ERR_INVALID; } *launches = g_kind_launches[kind].load(); return FX3D_OK; }
+int fx3d_stream_collide_launches(int kind, uint64_t* launches) { if(kind<0||kind>7||!launches) { set_error("kind must be 0..7"); return FX3D_ERR_INVALID; } *launches = g_kind_launches[kind].load(); return FX3D_OK; }
 int fx3d_launch_count(uint64_t* launches) { if(!launches) return FX3D_ERR_INVALID; *launches = g_launches.load(); return FX3D_OK; }
 
 size_t fx3d_fi_bytes(const fx3d_lattice* lat) {
@@ -164,6 +184,18 @@ int fx3d_stream_collide(const fx3d_lattice* lat, uint64_t t, float fx, float fy,
 	if(region<0||region>2) { set_error("invalid region"); return FX3D_ERR_INVALID; }
 	if(int rc = use_device(lat->device)) return rc;
 	return stream_collide_impl(lat, L, region, stream);
+}
+int fx3d_stream_collide_fused(const fx3d_lattice* lat, uint64_t t, float fx, float fy, float fz, void* const* fi_neighbours, fx3d_stream stream) {
+	Lattice L;
+	if(!make_lattice(lat, t, fx, fy, fz, L)) return FX3D_ERR_INVALID;
+	if(int rc = use_device(lat->device)) return rc;
+	return stream_collide_fused_impl(lat, L, fi_neighbours, stream, false);
+}
+int fx3d_fused_halo_supported(const fx3d_lattice* lat) {
+	Lattice L;
+	if(!make_lattice(lat, 0ull, 0.0f, 0.0f, 0.0f, L)) return 0;
+	if(!(L.Hy|L.Hz)) return 0; // nothing to fuse
+	return stream_collide_fused_impl(lat, L, nullptr, nullptr, true)==FX3D_OK ? 1 : 0;
 }
 int fx3d_run_steps(const fx3d_lattice* lat, uint64_t t0, uint64_t steps, float fx, float fy, float fz, fx3d_stream stream) {
 	Lattice L;

@@ -56,6 +56,30 @@ FX3D_HD uint64_t row(const Lattice& L, uint32_t y, uint32_t z) { return (uint64_
 FX3D_HD uint64_t phys(const Lattice& L, uint32_t x, uint32_t y, uint32_t z) { return row(L, y, z)+(uint64_t)(x+L.xo); }
 FX3D_HD uint32_t inc(uint32_t v, uint32_t n) { return v+1u==n ? 0u : v+1u; }
 FX3D_HD uint32_t dec(uint32_t v, uint32_t n) { return v==0u ? n-1u : v-1u; }
+FX3D_HD char* mad_wide_again(uint32_t a, uint32_t b, char* c) { // the same, but never merged with an earlier identical computation: recomputing an address costs one instruction, keeping it live across the collision costs two registers
+#if defined(FX3D_HOST_EMULATION)
+	return c+(uint64_t)a*(uint64_t)b;
+#else
+	unsigned long long r; asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"((unsigned long long)c)); return reinterpret_cast<char*>(r);
+#endif
+}
+// typed global-memory accesses for addresses that come out of the asm above (the compiler would otherwise use generic LD/ST)
+template<class E> FX3D_HD E load_global(const E* p) {
+#if defined(FX3D_HOST_EMULATION)
+	return *p;
+#else
+	if constexpr(sizeof(E)==4) { uint32_t v; asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return __uint_as_float(v); }
+	else { unsigned short v; asm volatile("ld.global.b16 %0, [%1];" : "=h"(v) : "l"(p) : "memory"); return (E)v; }
+#endif
+}
+template<class E> FX3D_HD void store_global(E* p, E v) {
+#if defined(FX3D_HOST_EMULATION)
+	*p = v;
+#else
+	if constexpr(sizeof(E)==4) asm volatile("st.global.b32 [%0], %1;" :: "l"(p), "r"(__float_as_uint(v)) : "memory");
+	else asm volatile("st.global.b16 [%0], %1;" :: "l"(p), "h"((unsigned short)v) : "memory");
+#endif
+}
 template<int E> FX3D_HD uint32_t step(uint32_t v, uint32_t n) { if constexpr(E>0) return inc(v, n); else if constexpr(E<0) return dec(v, n); else return v; }
 FX3D_HD uint32_t step_rt(int e, uint32_t v, uint32_t n) { return e>0 ? inc(v, n) : e<0 ? dec(v, n) : v; }
 
@@ -627,15 +651,30 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_col
 }
 
 // ================================================================================================================
-// stream_collide, bulk-copy form: the same z-marching persistent blocks, but the DDF rows move between HBM and shared memory
-// with TMA bulk copies (cp.async.bulk, completion on an mbarrier), one thread per row buffer, dealt evenly to the warps, and
-// the results go back the same way. Measured on B200 (tools/microbench/ubench3.cu): with 8-16 warps per SM, per-thread cp.async
-// loads + STG stores saturate at 5.2 TB/s however deep the ring is, bulk copies reach 6.4 TB/s. A tile row (all x of one (y,z))
-// is one contiguous segment per slot, so: one copy per (slot, tile row) in, one out; the x-shifted directions are read and
-// written at shifted positions of the periodic row buffer (no shuffles, no edge accesses). Requires the tile to span the
-// whole row: no x halo, Nx = 4*blockDim.x <= 512, 16-byte multiples (see tma_eligible()).
-// Per tile: wait(full[stage]) -> registers <- stage -> barrier -> collide -> stage <- registers -> proxy fence + barrier ->
-// bulk stores. A stage is refilled only after the bulk stores issued from it have finished reading it.
+// stream_collide, bulk-copy form: persistent blocks march through (row group, plane) tiles; the DDF rows of a tile move between
+// HBM and shared memory with TMA bulk copies (cp.async.bulk, completion on an mbarrier) and the results go back the same way.
+// Measured on B200 (tools/microbench/ubench3.cu, ubench4.cu): with 8-16 heavy warps per SM, per-thread cp.async loads + STG stores
+// saturate at 5.2 TB/s however deep the ring is, bulk copies reach 6.2 TB/s.
+//
+// Tile = 128/bx whole x-rows of W = 4*bx non-halo cells (bx threads per row, 4 cells per thread). A row of one slot is one
+// contiguous segment, so: one copy per (slot, tile row) in, one out. A row buffer is [16-byte pad | W elements | 16-byte pad]:
+//   * periodic rows (no x halo): the copy fills the middle; the x-shifted directions read and write at wrapped positions
+//   * rows with x halos (x-decomposed domains): the copy covers the pads too -- the halo cell x=0 is the last element of the
+//     head pad, x=Nx-1 the first of the tail pad (the DDF layout puts cell x=1 on a 128-byte line) -- and nothing wraps
+// so there are no shuffles, no edge accesses and no per-thread global addresses for the DDFs at all.
+//
+// A block is G compute groups of 128 threads sharing ONE ring of S stages (S > G): tile k of the block's contiguous share goes to
+// group k%G and stage k%S, i.e. S-G stages are loading while G are being worked on. Per tile and group: wait(full[stage]) ->
+// registers <- stage -> group barrier -> refill the stage of the group's previous tile -> collide -> stage <- registers (in place)
+// -> proxy fence + group barrier -> bulk stores. Every row buffer is loaded and stored by the same thread, which waits only for
+// the bulk stores it issued itself before it refills; groups synchronise with named barriers, never block-wide.
+//
+// Fused y/z halo delivery (replaces LBM::communicate_fi for those axes, src/lbm.cpp:1355-1387): under Esoteric-Pull every
+// (slot, row) written in step t has exactly one reader in step t+1 -- the tile at the same row for what was written through the
+// neighbour side, the tile at row-e_i for what was written locally. The bulk store of a row therefore goes straight to the
+// domain that owns the READER's row as a non-halo row (own memory, or the y/z/diagonal neighbour's over NVLink, P.fi[]), at that
+// domain's coordinates; no copy is made anywhere else, and no tile of any domain touches that (slot, row) during the same step.
+// Loads always come from own memory. x halos are elements inside a row and stay with the exchange kernels.
 // ================================================================================================================
 #ifndef FX3D_TMA_STAGES
 #define FX3D_TMA_STAGES 2
@@ -676,337 +715,193 @@ FX3D_HD void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "m
 FX3D_HD void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); } // my shared-memory writes become visible to the bulk-copy engine
 #endif
 
+// y/z neighbours of a domain for the fused halo delivery: fi[(dy+1)+3*(dz+1)], [4] = the domain itself; unused entries null
+struct RowPeers { void* fi[9]; };
+#ifndef FX3D_ROW_GROUPS_16
+#define FX3D_ROW_GROUPS_16 4 // compute groups per block, D3Q19 with 16-bit storage (512 threads, 128 registers)
+#endif
+#ifndef FX3D_ROW_GROUPS_32
+#define FX3D_ROW_GROUPS_32 2 // D3Q19 FP32 (256 threads, 255 registers)
+#endif
+#ifndef FX3D_ROW_GROUPS_27
+#define FX3D_ROW_GROUPS_27 3 // D3Q27 with 16-bit storage (384 threads, 168 registers); D3Q27 FP32 always runs 2
+#endif
+template<int Q, int ST> FX3D_HDC constexpr int row_groups() { return ST==ST_FP32 ? (Q>19 ? 2 : FX3D_ROW_GROUPS_32) : (Q>19 ? FX3D_ROW_GROUPS_27 : FX3D_ROW_GROUPS_16); }
+constexpr uint32_t ROW_PAD = 16u, ROW_MAX_STAGES = 15u;
+FX3D_HDC constexpr uint32_t row_stage_bytes(uint32_t Q, uint32_t esz, uint32_t bx, uint32_t by) { return Q*by*(bx*4u*esz+2u*ROW_PAD); }
+#if defined(FX3D_HOST_EMULATION)
+// emulation of an mbarrier with an arrival count: bits 0-31 completed phases, 32-47 pending arrivals, 48-63 arrivals per phase.
+// Copies happen at issue, so a copying thread arrives after its copies (mbar_copies_issued), not before them.
+FX3D_HD void mbar_init_n(uint64_t* b, uint32_t n) { __atomic_store_n(b, ((uint64_t)n<<48)|((uint64_t)n<<32), __ATOMIC_SEQ_CST); }
+FX3D_HD void mbar_arrive_expect_tx(uint64_t*, uint32_t) {}
+FX3D_HD void mbar_copies_issued(uint64_t* b) {
+	uint64_t v = __atomic_load_n(b, __ATOMIC_SEQ_CST);
+	for(;;) {
+		const uint64_t n = v>>48, pending = ((v>>32)&0xFFFFull)-1ull, phase = v&0xFFFFFFFFull;
+		const uint64_t nv = pending==0ull ? (n<<48)|(n<<32)|((phase+1ull)&0xFFFFFFFFull) : (n<<48)|(pending<<32)|phase;
+		if(__atomic_compare_exchange_n(b, &v, nv, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) break;
+	}
+}
+FX3D_HD void mbar_wait_n(uint64_t* b, uint32_t parity) { while((__atomic_load_n(b, __ATOMIC_SEQ_CST)&1ull)==(uint64_t)parity) std::this_thread::yield(); }
+FX3D_HD void group_sync(uint32_t g) { emul::group_barrier(g); }
+#else
+FX3D_HD void mbar_init_n(uint64_t* b, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(b)), "r"(n) : "memory"); }
+FX3D_HD void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) { mbar_expect_tx(b, bytes); } // one arrival, `bytes` more to wait for
+FX3D_HD void mbar_copies_issued(uint64_t*) {}
+FX3D_HD void mbar_wait_n(uint64_t* b, uint32_t parity) { mbar_wait(b, parity); }
+FX3D_HD void group_sync(uint32_t g) { asm volatile("bar.sync %0, 128;" :: "r"(g+1u) : "memory"); } // named barrier of one compute group
+#endif
+
 template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false>
-__global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_collide_tma(const Lattice L, const Region R, const uint32_t tiles_y) {
-	constexpr int K = 4, S = FX3D_TMA_STAGES;
-	constexpr uint32_t odd = (uint32_t)ODD;
+__global__ void __launch_bounds__(128*row_groups<Q, ST>(), 1) k_stream_collide_tma(const Lattice L, const Region R, const uint32_t tiles_y, const uint32_t S, const RowPeers P) {
+	constexpr int K = 4;
+	constexpr uint32_t G = (uint32_t)row_groups<Q, ST>(), PAD = ROW_PAD;
 	typedef Codec<ST> C;
 	typedef typename C::elem_t E;
-	typedef Pack<ST, K> P;
-	constexpr uint32_t VB = (uint32_t)(sizeof(E)*K), SET = 128u*VB, STAGE = tma_stage_bytes<Q, ST>(); // SET: one row-buffer set (all rows of the tile) of one slot
+	typedef Pack<ST, K> PK;
+	constexpr uint32_t VB = (uint32_t)(sizeof(E)*K), ESZ = (uint32_t)sizeof(E);
 	unsigned char* const smem = dynamic_smem();
 	uint64_t* const full = reinterpret_cast<uint64_t*>(smem); // full[stage]: the bulk loads of the tile in this stage have landed
 	unsigned char* const ring = smem+128;
-	const uint32_t tid = threadIdx.x+threadIdx.y*blockDim.x;
-	const uint32_t W = blockDim.x*(uint32_t)K, row_bytes = blockDim.x*VB; // W == L.Nx
-	const uint32_t ncopies = (uint32_t)(Q+1)*blockDim.y; // per tile: Q slot rows + one flag row for every tile row
-	if(tid==0u) { for(int s=0; s<S; s++) mbar_init(full+s); }
+	const uint32_t bx = blockDim.x, by = blockDim.y, g = threadIdx.z;
+	const uint32_t t = threadIdx.x+threadIdx.y*bx, lane = t&31u;
+	const uint32_t warp = __shfl_sync(0xFFFFFFFFu, t>>5, 0); // warp within the group, uniform
+	const uint32_t W = bx*(uint32_t)K, row_bytes = bx*VB, RB = row_bytes+2u*PAD, SET = by*RB, STAGE = (uint32_t)Q*SET;
+	const bool hx = L.Hx!=0u, hy = L.Hy!=0u, hz = L.Hz!=0u;
+	// where a row buffer starts in its pitch row (bytes), how much of it the copies cover, and where that lands in the buffer
+	const uint32_t g_off = hx ? (L.xo+1u)*ESZ-PAD : 0u, copy_bytes = hx ? RB : row_bytes, s_off = hx ? 0u : PAD;
+	const uint32_t ncopies = (uint32_t)Q*by;
+	const bool one_row = by==1u;
+	const uint32_t first_copy = warp+4u*lane; // multi-row tiles: copy c = ty*Q+j belongs to lane c/4 of warp c%4 (then every 128th)
+	const bool copier = one_row ? lane==0u : first_copy<ncopies;
+	if(t==0u && g==0u) { for(uint32_t s=0u; s<S; s++) mbar_init_n(full+s, one_row ? 4u : (ncopies<128u ? ncopies : 128u)); }
 	fence_async_smem();
 	__syncthreads();
 
-	// global address of copy c of the tile (rows R.y0+yb*by.., plane z): c = ty*(Q+1)+j; j<Q: slot buffer j, j==Q: flags
-	auto copy_src = [&](uint32_t c, uint32_t yb, uint32_t z, uint32_t& smem_off, uint32_t& bytes) -> char* {
-		const uint32_t ty = c/(uint32_t)(Q+1), j = c%(uint32_t)(Q+1), y = R.y0+yb*blockDim.y+ty;
-		if(j==(uint32_t)Q) { smem_off = (uint32_t)Q*SET+ty*W; bytes = W; return reinterpret_cast<char*>(L.flags)+((uint64_t)y+(uint64_t)z*L.Ny)*L.Nx; }
-		smem_off = j*SET+ty*row_bytes; bytes = row_bytes;
-		uint32_t slot = j, yr = y, zr = z;
-		if(j>0u) {
-			const uint32_t i = (j&1u) ? j : j-1u; // odd member of the direction pair
-			if(j&1u) slot = odd ? i : i+1u;
-			else { slot = odd ? i+1u : i; yr = step_rt(dir_rt(1, i), y, L.Ny); zr = step_rt(dir_rt(2, i), z, L.Nz); }
+	// ---- addresses: buffer j of a tile row at (y, z); for stores the row may belong to a y/z neighbour (see the header) ----
+	auto row_address = [&](bool store, uint32_t slot, bool local, int ey, int ez, uint32_t y, uint32_t z) -> char* {
+		uint32_t yr = y, zr = z;
+		int dy = 0, dz = 0;
+		if(!local) { yr = step_rt(ey, y, L.Ny); zr = step_rt(ez, z, L.Nz); }
+		if(store) {
+			// the reader's cell row: the row itself for neighbour-side buffers, row-e for local ones
+			const uint32_t ry = local ? (uint32_t)((int)y-ey) : yr, rz = local ? (uint32_t)((int)z-ez) : zr;
+			if(hy) dy = ry==0u ? -1 : ry==L.Ny-1u ? 1 : 0;
+			if(hz) dz = rz==0u ? -1 : rz==L.Nz-1u ? 1 : 0;
+			yr = (uint32_t)((int)yr-dy*(int)(L.Ny-2u)); zr = (uint32_t)((int)zr-dz*(int)(L.Nz-2u));
 		}
-		return reinterpret_cast<char*>(L.fi)+((uint64_t)slot*L.slot+row(L, yr, zr))*sizeof(E);
+		char* base = reinterpret_cast<char*>(L.fi);
+		if(dy!=0 || dz!=0) base = reinterpret_cast<char*>(P.fi[(dy+1)+3*(dz+1)]);
+		return base+((uint64_t)slot*L.slot+row(L, yr, zr))*ESZ+g_off;
 	};
-	// The copies of a tile are dealt round-robin to the warps (copy c belongs to lane c/4 of warp c%4), so that no warp arrives
-	// late at the block barriers because it alone feeds the copy engine; a thread waits only for the bulk stores it issued itself,
-	// and buffer c is always loaded and stored by the same thread.
-	const uint32_t first_copy = (tid>>5)+4u*(tid&31u);
-	// One-row tiles (blockDim.y==1, e.g. Nx=512): everything about a copy but y and z is known at compile time once the warp is
-	// known, so lane 0 of warp w issues buffers w, w+4, .. from an unrolled list with warp-uniform address arithmetic.
-	const bool one_row = blockDim.y==1u;
-	const uint32_t warp = __shfl_sync(0xFFFFFFFFu, tid>>5, 0);
-	auto copy_rows = [&](auto LOAD, uint32_t yb, uint32_t z, uint32_t stage) {
+	auto copy_one_row = [&](auto LOAD, uint32_t y, uint32_t z, uint32_t stage) { // lane 0 of every warp: its share of the Q copies, everything but y and z known at compile time
 		constexpr bool load = decltype(LOAD)::value;
-		const uint32_t y = R.y0+yb;
-		const uint32_t yv[3] = { dec(y, L.Ny), y, inc(y, L.Ny) }, zv[3] = { dec(z, L.Nz), z, inc(z, L.Nz) };
-		unsigned char* const sb = ring+(size_t)stage*STAGE;
+		unsigned char* const sb = ring+(size_t)stage*STAGE+s_off;
 		auto one = [&](auto J) {
 			constexpr int j = J;
-			if constexpr(j==Q) { if constexpr(load) bulk_load(sb+(size_t)Q*SET, reinterpret_cast<char*>(L.flags)+((uint64_t)y+(uint64_t)z*L.Ny)*L.Nx, W, full+stage); }
-			else {
-				constexpr int i = j==0 ? 0 : (j&1) ? j : j-1; // odd member of the direction pair
-				constexpr uint32_t slot = j==0 ? 0u : (j&1) ? (ODD ? (uint32_t)i : (uint32_t)i+1u) : (ODD ? (uint32_t)i+1u : (uint32_t)i);
-				constexpr int ey = (j==0 || (j&1)) ? 0 : dir_y(i), ez = (j==0 || (j&1)) ? 0 : dir_z(i);
-				char* g = reinterpret_cast<char*>(L.fi)+((uint64_t)slot*L.slot+row(L, yv[ey+1], zv[ez+1]))*sizeof(E);
-				if constexpr(load) bulk_load(sb+(size_t)j*SET, g, row_bytes, full+stage); else bulk_store(g, sb+(size_t)j*SET, row_bytes);
-			}
-		};
-		if(warp==0u) static_for<0, Q+1, 4>(one); else if(warp==1u) static_for<1, Q+1, 4>(one); else if(warp==2u) static_for<2, Q+1, 4>(one); else static_for<3, Q+1, 4>(one);
-	};
-	auto load_tile = [&](uint32_t yb, uint32_t z, uint32_t stage) { // every thread calls it
-		if(tid==0u) mbar_expect_tx(full+stage, blockDim.y*((uint32_t)Q*row_bytes+W));
-		if(one_row) { if((tid&31u)==0u) copy_rows(std::true_type{}, yb, z, stage); }
-		else for(uint32_t c=first_copy; c<ncopies; c+=128u) { uint32_t off, bytes; char* src = copy_src(c, yb, z, off, bytes); bulk_load(ring+(size_t)stage*STAGE+off, src, bytes, full+stage); }
-#if defined(FX3D_HOST_EMULATION)
-		__syncthreads(); // (emulation: copies happen at issue; the phase completes once every thread has made its copies)
-		if(tid==0u) mbar_phase_done_emulated(full+stage);
-#endif
-	};
-	auto store_tile = [&](uint32_t yb, uint32_t z, uint32_t stage) {
-		if(one_row) { if((tid&31u)==0u) { copy_rows(std::false_type{}, yb, z, stage); bulk_commit(); } return; }
-		bool any = false;
-		for(uint32_t c=first_copy; c<ncopies; c+=128u) { uint32_t off, bytes; char* dst = copy_src(c, yb, z, off, bytes); if(c%(uint32_t)(Q+1)!=(uint32_t)Q) { bulk_store(dst, ring+(size_t)stage*STAGE+off, bytes); any = true; } }
-		if(any) bulk_commit();
-	};
-	const bool copier = one_row ? (tid&31u)==0u : first_copy<ncopies;
-
-	const uint32_t nz = R.z1-R.z0;
-	const uint64_t ntiles = (uint64_t)tiles_y*nz;
-	uint64_t tile = ntiles*blockIdx.x/gridDim.x;
-	const uint64_t tile_end = ntiles*(blockIdx.x+1u)/gridDim.x;
-	uint32_t it = 0u; // tiles this block has consumed: stage = it%S, barrier parity = (it/S)&1
-	const uint32_t x0 = (uint32_t)K*threadIdx.x;
-	while(tile<tile_end) {
-		const uint32_t yb = (uint32_t)(tile/nz), zoff = (uint32_t)(tile%nz);
-		const uint32_t zs = R.z0+zoff, ze = (uint64_t)(nz-zoff)<=tile_end-tile ? R.z1 : zs+(uint32_t)(tile_end-tile);
-		tile += ze-zs;
-		const uint32_t y = R.y0+yb*blockDim.y+threadIdx.y;
-		if(copier) bulk_wait_read(); // prologue: the first S-1 planes of this run
-		for(uint32_t k=0u; k<(uint32_t)(S-1); k++) if(zs+k<ze) load_tile(yb, zs+k, (it+k)%(uint32_t)S);
-		for(uint32_t z=zs; z<ze; z++, it++) {
-			const uint32_t stage = it%(uint32_t)S;
-			mbar_wait(full+stage, (it/(uint32_t)S)&1u);
-			unsigned char* const sb = ring+(size_t)stage*STAGE;
-			const uint32_t flags4 = *reinterpret_cast<const uint32_t*>(sb+(size_t)Q*SET+tid*(uint32_t)K);
-			// ---- stream in from the stage: my vectors, and for the x-shifted directions the element beyond them in the periodic row ----
-			P A[Q];
-			static_for<0, Q, 1>([&](auto I) { A[I].load(reinterpret_cast<const E*>(sb+(size_t)I.value*SET+tid*VB)); });
-			static_for<1, Q, 2>([&](auto I) {
-				constexpr int i = I;
-				const E* rowp = reinterpret_cast<const E*>(sb+(size_t)(i+1)*SET+threadIdx.y*row_bytes);
-				if constexpr(dir_x(i)>0) A[i+1].push_back(P::bits(rowp[x0+(uint32_t)K==W ? 0u : x0+(uint32_t)K]));
-				else if constexpr(dir_x(i)<0) A[i+1].push_front(P::bits(rowp[x0==0u ? W-1u : x0-1u]));
-			});
-			__syncthreads(); // everybody has read the stage before anybody writes results into it
-			// refill the other stage(s) now rather than at the top of the iteration: the bulk stores issued from it at the end of the
-			// previous iteration have had the stream-in to finish reading it, so the copying threads rarely wait here
-			if(z+(uint32_t)(S-1)<ze) { if(copier) bulk_wait_read(); load_tile(yb, z+(uint32_t)(S-1), (it+(uint32_t)(S-1))%(uint32_t)S); }
-			collide_tile<Q, COLL, ST, VF, K, SG, MB>(L, A, flags4, x0, y, z);
-			// ---- stream out into the same row buffers ----
-			A[0].store(reinterpret_cast<E*>(sb+tid*VB));
-			static_for<1, Q, 2>([&](auto I) {
-				constexpr int i = I;
-				A[i].store(reinterpret_cast<E*>(sb+(size_t)i*SET+tid*VB));
-				E* rowp = reinterpret_cast<E*>(sb+(size_t)(i+1)*SET+threadIdx.y*row_bytes);
-				if constexpr(dir_x(i)==0) A[i+1].store(rowp+x0);
-				else if constexpr(dir_x(i)>0) A[i+1].store_row_up(rowp, x0, W);
-				else A[i+1].store_row_down(rowp, x0, W);
-			});
-			fence_async_smem();
-			__syncthreads();
-			store_tile(yb, z, stage);
-		}
-	}
-	if(copier) bulk_wait_all();
-}
-
-// ---- bulk-copy form for tiles that are a segment of a longer row, and for rows with x halos ----
-// Same pipeline as k_stream_collide_tma; what changes is the row ends. A slot buffer whose direction has an x component holds
-// elements that other tiles own: of the positions a tile writes for ex>0 (x+1 .. x+W) the first 16-byte chunk of its segment
-// contains the left neighbour's element, and its own last element lies one past the segment (mirrored for ex<0). So every row
-// buffer has a 16-byte pad on either side: the pad on the side the direction reaches into is loaded along with the segment
-// (one longer copy; a separate 16-byte copy where the row wraps periodically), threads read and write at shifted positions
-// without any wrap logic, the bulk store covers the fully owned chunks only, and the remaining <= 16/sizeof(E) owned elements per
-// shifted buffer are written by single threads with plain stores. Flags are read per thread (their rows are not 16-byte aligned).
-template<int Q, int ST> FX3D_HDC constexpr uint32_t tmaseg_set_bytes() { return 128u*4u*(ST==ST_FP32 ? 4u : 2u)+4u*32u; } // up to 4 tile rows, each padded by 2x16 bytes
-template<int Q, int ST> FX3D_HDC constexpr uint32_t tmaseg_smem_bytes() { return 128u+(uint32_t)FX3D_TMA_STAGES*(uint32_t)Q*tmaseg_set_bytes<Q, ST>(); }
-template<int Q> FX3D_HDC constexpr unsigned long long pack_x_dirs() { unsigned long long m = 0ull; int n = 0; for(int i=1; i<Q; i+=2) if(dir_x(i)!=0) { m |= (unsigned long long)i<<(5*n); n++; } return m; } // the odd directions with an x component, 5 bits each
-
-template<int Q, int COLL, int ST, bool VF, int ODD>
-__global__ void __launch_bounds__(128, tma_blocks_per_sm<Q, ST>()) k_stream_collide_tma_seg(const Lattice L, const Region R, const uint32_t tiles_x, const uint32_t tiles_y) {
-	constexpr int K = 4, S = FX3D_TMA_STAGES, NXD = x_dirs<Q>();
-	constexpr uint32_t odd = (uint32_t)ODD;
-	typedef Codec<ST> C;
-	typedef typename C::elem_t E;
-	typedef Pack<ST, K> P;
-	constexpr uint32_t VB = (uint32_t)(sizeof(E)*K), PAD = 16u, CH = PAD/(uint32_t)sizeof(E), SET = tmaseg_set_bytes<Q, ST>(), STAGE = (uint32_t)Q*SET;
-	unsigned char* const smem = dynamic_smem();
-	uint64_t* const full = reinterpret_cast<uint64_t*>(smem);
-	unsigned char* const ring = smem+128;
-	const uint32_t tid = threadIdx.x+threadIdx.y*blockDim.x;
-	const uint32_t W = blockDim.x*(uint32_t)K, row_bytes = blockDim.x*VB, ROWB = row_bytes+2u*PAD; // a row buffer: [pad | W elements | pad]
-	const uint32_t nbuf = (uint32_t)Q*blockDim.y, nfix = (uint32_t)NXD*blockDim.y*CH;
-	if(tid==0u) { for(int s=0; s<S; s++) mbar_init(full+s); }
-	fence_async_smem();
-	__syncthreads();
-
-	// buffer c = ty*Q+j of the tile at (X0, rows R.y0+yb*by.., plane z): global address of the segment start, x shift of its direction
-	auto buffer_row = [&](uint32_t c, uint32_t X0, uint32_t yb, uint32_t z, uint32_t& smem_off, int& ex) -> char* {
-		const uint32_t ty = c/(uint32_t)Q, j = c%(uint32_t)Q, y = R.y0+yb*blockDim.y+ty;
-		smem_off = j*SET+ty*ROWB;
-		uint32_t slot = j, yr = y, zr = z;
-		ex = 0;
-		if(j>0u) {
-			const uint32_t i = (j&1u) ? j : j-1u;
-			if(j&1u) slot = odd ? i : i+1u;
-			else { slot = odd ? i+1u : i; yr = step_rt(dir_rt(1, i), y, L.Ny); zr = step_rt(dir_rt(2, i), z, L.Nz); ex = dir_rt(0, i); }
-		}
-		return reinterpret_cast<char*>(L.fi)+((uint64_t)slot*L.slot+row(L, yr, zr)+(uint64_t)(X0+L.xo))*sizeof(E);
-	};
-	const uint32_t first_copy = (tid>>5)+4u*(tid&31u);
-	// One-row tiles (blockDim.y==1, i.e. segments of 512 cells): lane 0 of warp w issues buffers w, w+4, .. from an unrolled list
-	// in which everything but X0, y and z is a compile-time constant; the end-chunk elements are stored by threads n*CH+k.
-	const bool one_row = blockDim.y==1u;
-	const uint32_t warp = __shfl_sync(0xFFFFFFFFu, tid>>5, 0);
-	const bool copier = one_row ? (tid&31u)==0u : first_copy<nbuf;
-	auto row_ptr = [&](auto J, uint32_t X0, uint32_t y, uint32_t z) -> char* { // segment start of buffer J (compile time) in row y of plane z
-		constexpr int j = decltype(J)::value;
-		constexpr int i = j==0 ? 0 : (j&1) ? j : j-1;
-		constexpr uint32_t slot = j==0 ? 0u : (j&1) ? (ODD ? (uint32_t)i : (uint32_t)i+1u) : (ODD ? (uint32_t)i+1u : (uint32_t)i);
-		constexpr int ey = (j==0 || (j&1)) ? 0 : dir_y(i), ez = (j==0 || (j&1)) ? 0 : dir_z(i);
-		return reinterpret_cast<char*>(L.fi)+((uint64_t)slot*L.slot+row(L, step<ey>(y, L.Ny), step<ez>(z, L.Nz))+(uint64_t)(X0+L.xo))*sizeof(E);
-	};
-	auto copy_rows = [&](auto LOAD, uint32_t X0, uint32_t yb, uint32_t z, uint32_t stage) {
-		constexpr bool load = decltype(LOAD)::value;
-		const uint32_t y = R.y0+yb;
-		unsigned char* const sb = ring+(size_t)stage*STAGE;
-		auto one = [&](auto J) {
-			constexpr int j = J;
-			constexpr int ex = (j==0 || (j&1)) ? 0 : dir_x(j-1);
-			char* g = row_ptr(J, X0, y, z);
-			unsigned char* b = sb+(size_t)j*SET;
-			if constexpr(load) {
-				if constexpr(ex>0) {
-					if(X0+W<L.Nx) bulk_load(b+PAD, g, row_bytes+PAD, full+stage);
-					else { bulk_load(b+PAD, g, row_bytes, full+stage); bulk_load(b+PAD+row_bytes, g-(size_t)X0*sizeof(E), PAD, full+stage); }
-				} else if constexpr(ex<0) {
-					if(X0>0u) bulk_load(b, g-PAD, row_bytes+PAD, full+stage);
-					else { bulk_load(b+PAD, g, row_bytes, full+stage); bulk_load(b, g+(size_t)(L.Nx-CH)*sizeof(E), PAD, full+stage); }
-				} else bulk_load(b+PAD, g, row_bytes, full+stage);
-			} else {
-				if constexpr(ex>0) bulk_store(g+PAD, b+2u*PAD, row_bytes-PAD); else if constexpr(ex<0) bulk_store(g, b+PAD, row_bytes-PAD); else bulk_store(g, b+PAD, row_bytes);
-			}
+			constexpr int i = j==0 ? 0 : (j&1) ? j : j-1; // odd member of the direction pair
+			constexpr uint32_t slot = j==0 ? 0u : (j&1) ? (ODD ? (uint32_t)i : (uint32_t)i+1u) : (ODD ? (uint32_t)i+1u : (uint32_t)i);
+			constexpr bool local = j==0 || (j&1);
+			constexpr int ey = j==0 ? 0 : dir_y(i), ez = j==0 ? 0 : dir_z(i);
+			char* gp = row_address(!load && j!=0, slot, local, ey, ez, y, z);
+			if constexpr(load) bulk_load(sb+(size_t)j*SET, gp, copy_bytes, full+stage); else bulk_store(gp, sb+(size_t)j*SET, copy_bytes);
 		};
 		if(warp==0u) static_for<0, Q, 4>(one); else if(warp==1u) static_for<1, Q, 4>(one); else if(warp==2u) static_for<2, Q, 4>(one); else static_for<3, Q, 4>(one);
 	};
-	auto fix_rows = [&](uint32_t X0, uint32_t yb, uint32_t z, uint32_t stage) { // one-row tiles: thread n*CH+k stores end-chunk element k of the n-th shifted buffer
-		const uint32_t y = R.y0+yb, k = tid%CH;
-		int n = 0;
-		static_for<1, Q, 2>([&](auto I) {
-			constexpr int i = I;
-			if constexpr(dir_x(i)!=0) {
-				if(tid/CH==(uint32_t)n) {
-					char* g = row_ptr(std::integral_constant<int, i+1>{}, X0, y, z);
-					const E* seg = reinterpret_cast<const E*>(ring+(size_t)stage*STAGE+(size_t)(i+1)*SET+PAD);
-					const int pos = dir_x(i)>0 ? (k+1u<CH ? (int)k+1 : (int)W) : (k==0u ? -1 : (int)(W-CH+k-1u));
-					int64_t gp = pos;
-					if(pos<0 && X0==0u) gp = (int64_t)L.Nx-1; else if(pos>=(int)W && X0+W>=L.Nx) gp = -(int64_t)X0;
-					reinterpret_cast<E*>(g)[gp] = seg[pos];
-				}
-				n++;
-			}
-		});
-	};
-	auto load_tile = [&](uint32_t X0, uint32_t yb, uint32_t z, uint32_t stage) {
-		if(tid==0u) mbar_expect_tx(full+stage, blockDim.y*((uint32_t)Q*row_bytes+(uint32_t)NXD*PAD));
-		if(one_row) { if((tid&31u)==0u) copy_rows(std::true_type{}, X0, yb, z, stage); }
-		else for(uint32_t c=first_copy; c<nbuf; c+=128u) {
-			uint32_t off; int ex;
-			char* g = buffer_row(c, X0, yb, z, off, ex);
-			unsigned char* b = ring+(size_t)stage*STAGE+off;
-			if(ex>0) { // segment + the element one past it
-				if(X0+W<L.Nx) bulk_load(b+PAD, g, row_bytes+PAD, full+stage);
-				else { bulk_load(b+PAD, g, row_bytes, full+stage); bulk_load(b+PAD+row_bytes, g-(size_t)X0*sizeof(E), PAD, full+stage); } // periodic: the row's first chunk
-			} else if(ex<0) { // the element before the segment + segment
-				if(X0>0u) bulk_load(b, g-PAD, row_bytes+PAD, full+stage);
-				else { bulk_load(b+PAD, g, row_bytes, full+stage); bulk_load(b, g+(size_t)(L.Nx-CH)*sizeof(E), PAD, full+stage); } // periodic: the row's last chunk
-			} else bulk_load(b+PAD, g, row_bytes, full+stage);
+	auto copy_any = [&](bool load, uint32_t c, uint32_t y0, uint32_t z, uint32_t stage) { // multi-row tiles: copy c, decoded at run time
+		const uint32_t ty = c/(uint32_t)Q, j = c%(uint32_t)Q;
+		uint32_t slot = 0u; bool local = true; int ey = 0, ez = 0;
+		if(j>0u) {
+			const uint32_t i = (j&1u) ? j : j-1u;
+			local = (j&1u)!=0u;
+			slot = local ? (ODD ? i : i+1u) : (ODD ? i+1u : i);
+			ey = dir_rt(1, i); ez = dir_rt(2, i);
 		}
-#if defined(FX3D_HOST_EMULATION)
-		__syncthreads();
-		if(tid==0u) mbar_phase_done_emulated(full+stage);
-#endif
+		char* gp = row_address(!load && j!=0u, slot, local, ey, ez, y0+ty, z);
+		unsigned char* sp = ring+(size_t)stage*STAGE+(size_t)j*SET+ty*RB+s_off;
+		if(load) bulk_load(sp, gp, copy_bytes, full+stage); else bulk_store(gp, sp, copy_bytes);
 	};
-	auto store_tile = [&](uint32_t X0, uint32_t yb, uint32_t z, uint32_t stage) {
+	auto load_tile = [&](uint32_t y0, uint32_t z, uint32_t stage) { // every thread of the group calls it
+		if(!copier) return;
 		if(one_row) {
-			if((tid&31u)==0u) { copy_rows(std::false_type{}, X0, yb, z, stage); bulk_commit(); }
-			if(tid<(uint32_t)NXD*CH) fix_rows(X0, yb, z, stage);
-			return;
+			uint32_t n = 0u; for(uint32_t j=warp; j<(uint32_t)Q; j+=4u) n++;
+			mbar_arrive_expect_tx(full+stage, n*copy_bytes);
+			copy_one_row(std::true_type{}, y0, z, stage);
+		} else {
+			uint32_t n = 0u; for(uint32_t c=first_copy; c<ncopies; c+=128u) n++;
+			mbar_arrive_expect_tx(full+stage, n*copy_bytes);
+			for(uint32_t c=first_copy; c<ncopies; c+=128u) copy_any(true, c, y0, z, stage);
 		}
-		for(uint32_t c=first_copy; c<nbuf; c+=128u) { // the fully owned 16-byte chunks, in bulk
-			uint32_t off; int ex;
-			char* g = buffer_row(c, X0, yb, z, off, ex);
-			unsigned char* b = ring+(size_t)stage*STAGE+off+PAD;
-			if(ex>0) bulk_store(g+PAD, b+PAD, row_bytes-PAD); else if(ex<0) bulk_store(g, b, row_bytes-PAD); else bulk_store(g, b, row_bytes);
-		}
-		if(copier) bulk_commit();
-		for(uint32_t f=tid; f<nfix; f+=128u) { // the owned elements of the two end chunks, one by one
-			const uint32_t k = f%CH, ty = (f/CH)%blockDim.y, n = f/(CH*blockDim.y);
-			const uint32_t i = (uint32_t)((pack_x_dirs<Q>()>>(5u*n))&31ull);
-			uint32_t off; int ex;
-			char* g = buffer_row(ty*(uint32_t)Q+i+1u, X0, yb, z, off, ex);
-			const E* seg = reinterpret_cast<const E*>(ring+(size_t)stage*STAGE+off+PAD);
-			// ex>0: positions 1..CH-1 and W; ex<0: positions -1 and W-CH..W-2 (position p of the segment is cell X0+p)
-			const int pos = ex>0 ? (k+1u<CH ? (int)k+1 : (int)W) : (k==0u ? -1 : (int)(W-CH+k-1u));
-			int64_t gp = pos;
-			if(pos<0 && X0==0u) gp = (int64_t)L.Nx-1; else if(pos>=(int)W && X0+W>=L.Nx) gp = -(int64_t)X0; // periodic wrap inside the row
-			reinterpret_cast<E*>(g)[gp] = seg[pos];
-		}
+		mbar_copies_issued(full+stage);
+	};
+	auto store_tile = [&](uint32_t y0, uint32_t z, uint32_t stage) {
+		if(!copier) return;
+		if(one_row) copy_one_row(std::false_type{}, y0, z, stage);
+		else for(uint32_t c=first_copy; c<ncopies; c+=128u) copy_any(false, c, y0, z, stage);
+		bulk_commit();
 	};
 
+	// ---- this block's contiguous share of the (row group, plane) tiles; tile k of the share: group k%G, stage k%S ----
 	const uint32_t nz = R.z1-R.z0;
-	const uint64_t ntiles = (uint64_t)tiles_x*tiles_y*nz;
-	uint64_t tile = ntiles*blockIdx.x/gridDim.x;
-	const uint64_t tile_end = ntiles*(blockIdx.x+1u)/gridDim.x;
-	uint32_t it = 0u;
-	const uint32_t x0 = (uint32_t)K*threadIdx.x; // my first cell within the segment
-	while(tile<tile_end) {
-		const uint32_t col = (uint32_t)(tile/nz), zoff = (uint32_t)(tile%nz), xb = col%tiles_x, yb = col/tiles_x;
-		const uint32_t zs = R.z0+zoff, ze = (uint64_t)(nz-zoff)<=tile_end-tile ? R.z1 : zs+(uint32_t)(tile_end-tile);
-		tile += ze-zs;
-		const uint32_t X0 = L.Hx+(R.g0+xb*blockDim.x)*(uint32_t)K, y = R.y0+yb*blockDim.y+threadIdx.y;
-		const uint8_t* const my_flags = L.flags+((uint64_t)(X0+x0)+(uint64_t)y*L.Nx);
-		const uint64_t flag_plane = (uint64_t)L.Nx*L.Ny;
-		// my 4 flag bytes come from two aligned words; the words of the next plane are requested a whole tile ahead and only
-		// combined when they are needed (combining at the load would wait for them on the spot)
-		uint32_t fw0, fw1;
-		auto request_flags = [&](uint32_t z) {
-			const uintptr_t a = reinterpret_cast<uintptr_t>(my_flags+(uint64_t)z*flag_plane);
-			fw0 = *reinterpret_cast<const uint32_t*>(a&~(uintptr_t)3u);
-			fw1 = (a&3u) ? *reinterpret_cast<const uint32_t*>((a&~(uintptr_t)3u)+4u) : 0u;
-		};
-		auto combine_flags = [&](uint32_t z) -> uint32_t {
-			const uint32_t sh = 8u*(uint32_t)(reinterpret_cast<uintptr_t>(my_flags+(uint64_t)z*flag_plane)&3u);
-			return sh==0u ? fw0 : (fw0>>sh)|(fw1<<(32u-sh));
-		};
-		if(copier) bulk_wait_read();
-		for(uint32_t k=0u; k<(uint32_t)(S-1); k++) if(zs+k<ze) load_tile(X0, yb, zs+k, (it+k)%(uint32_t)S);
-		request_flags(zs);
-		for(uint32_t z=zs; z<ze; z++, it++) {
-			const uint32_t stage = it%(uint32_t)S;
-			const uint32_t flags4 = combine_flags(z);
-			mbar_wait(full+stage, (it/(uint32_t)S)&1u);
-			unsigned char* const sb = ring+(size_t)stage*STAGE+threadIdx.y*ROWB+PAD;
-			P A[Q];
-			static_for<0, Q, 1>([&](auto I) { A[I].load(reinterpret_cast<const E*>(sb+(size_t)I.value*SET)+x0); });
-			static_for<1, Q, 2>([&](auto I) {
-				constexpr int i = I;
-				const E* rowp = reinterpret_cast<const E*>(sb+(size_t)(i+1)*SET);
-				if constexpr(dir_x(i)>0) A[i+1].push_back(P::bits(rowp[x0+(uint32_t)K]));
-				else if constexpr(dir_x(i)<0) A[i+1].push_front(P::bits(*(rowp+x0-1)));
-			});
-			__syncthreads();
-			if(z+(uint32_t)(S-1)<ze) { if(copier) bulk_wait_read(); load_tile(X0, yb, z+(uint32_t)(S-1), (it+(uint32_t)(S-1))%(uint32_t)S); }
-			if(z+1u<ze) request_flags(z+1u);
-			collide_tile<Q, COLL, ST, VF, K>(L, A, flags4, X0+x0, y, z);
-			A[0].store(reinterpret_cast<E*>(sb)+x0);
-			static_for<1, Q, 2>([&](auto I) {
-				constexpr int i = I;
-				A[i].store(reinterpret_cast<E*>(sb+(size_t)i*SET)+x0);
-				E* rowp = reinterpret_cast<E*>(sb+(size_t)(i+1)*SET);
-				if constexpr(dir_x(i)==0) A[i+1].store(rowp+x0);
-				else if constexpr(dir_x(i)>0) A[i+1].store_seg_up(rowp, x0);
-				else A[i+1].store_seg_down(rowp, x0);
-			});
-			fence_async_smem();
-			__syncthreads();
-			store_tile(X0, yb, z, stage);
-		}
+	const uint64_t ntiles = (uint64_t)tiles_y*nz, T0 = ntiles*blockIdx.x/gridDim.x, T1 = ntiles*(blockIdx.x+1u)/gridDim.x;
+	const uint32_t n = (uint32_t)(T1-T0);
+	struct Pos { uint32_t yb, zo; }; // tile row group and plane offset
+	auto advance = [&](Pos p, uint32_t d) -> Pos { p.zo += d; while(p.zo>=nz) { p.zo -= nz; p.yb++; } return p; };
+	const Pos first = advance(Pos{ (uint32_t)(T0/nz), (uint32_t)(T0%nz) }, 0u);
+	for(uint32_t j=g; j<S && j<n; j+=G) { const Pos p = advance(first, j); load_tile(R.y0+p.yb*by, R.z0+p.zo, j); } // prologue: group j%G loads tile j
+	const uint32_t x0 = (uint32_t)K*threadIdx.x;
+	// my 4 flag bytes: two aligned words, requested one tile ahead and only combined when needed
+	const uint64_t flag_plane = (uint64_t)L.Nx*L.Ny;
+	uint32_t fw0 = 0u, fw1 = 0u;
+	auto flag_address = [&](Pos p) -> uintptr_t { return reinterpret_cast<uintptr_t>(L.flags+((uint64_t)(L.Hx+x0)+(uint64_t)(R.y0+p.yb*by+threadIdx.y)*L.Nx+(uint64_t)(R.z0+p.zo)*flag_plane)); };
+	auto request_flags = [&](Pos p) { const uintptr_t a = flag_address(p); fw0 = *reinterpret_cast<const uint32_t*>(a&~(uintptr_t)3u); fw1 = (a&3u) ? *reinterpret_cast<const uint32_t*>((a&~(uintptr_t)3u)+4u) : 0u; };
+	auto combine_flags = [&](Pos p) -> uint32_t { const uint32_t sh = 8u*(uint32_t)(flag_address(p)&3u); return sh==0u ? fw0 : (fw0>>sh)|(fw1<<(32u-sh)); };
+	Pos cur = advance(first, g);
+	if(g<n) request_flags(cur);
+	for(uint32_t k=g; k<n; k+=G, cur = advance(cur, G)) {
+		const uint32_t stage = k%S, y0 = R.y0+cur.yb*by, y = y0+threadIdx.y, z = R.z0+cur.zo;
+		if(k>=S && k<S+G) mbar_wait_n(full+stage, 0u); // early tiles: the stage's first fill (a prologue load issued by another group) must be complete before its second can be awaited
+		mbar_wait_n(full+stage, (k/S)&1u);
+		const uint32_t flags4 = combine_flags(cur);
+		unsigned char* const sb = ring+(size_t)stage*STAGE+threadIdx.y*RB+PAD; // element 0 of my row in buffer 0
+		// ---- stream in from the stage: my vectors, and for the x-shifted directions the element beyond them ----
+		PK A[Q];
+		static_for<0, Q, 1>([&](auto I) { A[I].load(reinterpret_cast<const E*>(sb+(size_t)I.value*SET)+x0); });
+		static_for<1, Q, 2>([&](auto I) {
+			constexpr int i = I;
+			const E* rowp = reinterpret_cast<const E*>(sb+(size_t)(i+1)*SET);
+			if constexpr(dir_x(i)>0) A[i+1].push_back(PK::bits(hx ? rowp[x0+(uint32_t)K] : rowp[x0+(uint32_t)K==W ? 0u : x0+(uint32_t)K]));
+			else if constexpr(dir_x(i)<0) A[i+1].push_front(PK::bits(hx ? *(rowp+x0-1) : rowp[x0==0u ? W-1u : x0-1u]));
+		});
+		group_sync(g); // the whole group has read the stage before anybody writes results into it
+		// refill the stage of this group's previous tile now rather than right after its stores: they have had the stream-in above
+		// to finish reading it, so the copying threads rarely wait here
+		if(k>=G && k-G+S<n) { const Pos p = advance(cur, S-G); if(copier) bulk_wait_read(); load_tile(R.y0+p.yb*by, R.z0+p.zo, (k-G)%S); }
+		if(k+G<n) request_flags(advance(cur, G));
+		collide_tile<Q, COLL, ST, VF, K, SG, MB>(L, A, flags4, L.Hx+x0, y, z);
+		// ---- stream out into the same row buffers ----
+		A[0].store(reinterpret_cast<E*>(sb)+x0);
+		static_for<1, Q, 2>([&](auto I) {
+			constexpr int i = I;
+			A[i].store(reinterpret_cast<E*>(sb+(size_t)i*SET)+x0);
+			E* rowp = reinterpret_cast<E*>(sb+(size_t)(i+1)*SET);
+			if constexpr(dir_x(i)==0) A[i+1].store(rowp+x0);
+			else if constexpr(dir_x(i)>0) { if(hx) A[i+1].store_seg_up(rowp, x0); else A[i+1].store_row_up(rowp, x0, W); }
+			else { if(hx) A[i+1].store_seg_down(rowp, x0); else A[i+1].store_row_down(rowp, x0, W); }
+		});
+		fence_async_smem();
+		group_sync(g);
+		store_tile(y0, z, stage);
 	}
 	if(copier) bulk_wait_all();
 }
 
-// ---- hybrid: bulk loads as in k_stream_collide_tma_seg, stream-out straight from registers as in k_stream_collide_pipe ----
+// ---- row-segment tiles (rows longer than a tile, or shapes the whole-row kernel does not take) ----
+template<int Q, int ST> FX3D_HDC constexpr uint32_t tmaseg_set_bytes() { return 128u*4u*(ST==ST_FP32 ? 4u : 2u)+4u*32u; } // up to 4 tile rows, each padded by 2x16 bytes
+template<int Q, int ST> FX3D_HDC constexpr uint32_t tmaseg_smem_bytes() { return 128u+(uint32_t)FX3D_TMA_STAGES*(uint32_t)Q*tmaseg_set_bytes<Q, ST>(); }
+
+
+// ---- hybrid: bulk loads of row segments into padded row buffers, stream-out straight from registers as in k_stream_collide_pipe ----
 // tools/microbench/ubench3.cu: it is the *load* half of the LSU path that saturates at low occupancy (bulk loads + STG stores reach
 // the same 6.2 TB/s as bulk loads + bulk stores). Per-thread stores settle the ownership of the row ends by themselves (shuffles
 // inside a warp, one scalar store at warp / segment ends), so there is no write-back into the stage, no second barrier, no fix-up.
@@ -1249,6 +1144,60 @@ __global__ void __launch_bounds__(128) k_stream_collide_v1(const Lattice L, cons
 	collide_cell<Q, COLL, VF, float, SG>(f, 1.0f, 1.0f, is_e, false, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
 	if(L.upd!=0u && !is_e) { L.rho[n] = rhon; L.u[n] = uxn; L.u[N+n] = uyn; L.u[2ull*N+n] = uzn; }
 	io.push(L, L.odd, f);
+}
+
+// ---- stream_collide, occupancy form: one cell per thread like the general kernel, but built to stay within 64 registers
+// (32 warps per SM) -- 32-bit element offsets formed from three x, three row and three plane terms at the point of use, slot
+// numbers as immediates (step parity is a template parameter), the pairwise-fused collision. The reference's own OpenCL kernel
+// has this shape (56 registers, 36 warps per SM on the B200's driver compiler) and reaches the full copy bandwidth in FP32, where
+// the low-occupancy bulk-copy pipeline tops out at about 6.2 TB/s; for 16-bit storage the bulk-copy kernels are far ahead.
+#ifndef FX3D_OCC_MINBLOCKS
+#define FX3D_OCC_MINBLOCKS 8
+#endif
+template<int Q, int COLL, int ST, bool VF, int ODD>
+__global__ void __launch_bounds__(128, FX3D_OCC_MINBLOCKS) k_stream_collide_occ(const Lattice L, const Region R) {
+	typedef Codec<ST> C;
+	typedef typename C::elem_t E;
+	uint32_t x, y, z;
+	if(!region_cell(R, x, y, z)) return;
+	const uint32_t n = x+(y+z*L.Ny)*L.Nx; // the reference's uxx=uint index: N < 2^32 (checked on the host)
+	const uint32_t fb = L.flags[n]&TYPE_BO;
+	if(fb==TYPE_S) return;
+	// element offsets inside one slot: ox[ex+1]+oy[ey+1]+oz[ez+1], each < 2^32 in sum (the padded slot holds < 2^32 elements)
+	const uint32_t ox[3] = { dec(x, L.Nx)+L.xo, x+L.xo, inc(x, L.Nx)+L.xo };
+	const uint32_t oy[3] = { dec(y, L.Ny)*L.px, y*L.px, inc(y, L.Ny)*L.px };
+	const uint32_t pz = L.px*L.Ny;
+	const uint32_t oz[3] = { dec(z, L.Nz)*pz, z*pz, inc(z, L.Nz)*pz };
+	char* const base = reinterpret_cast<char*>(L.fi);
+	auto at = [&](auto EX, auto EY, auto EZ, uint32_t slot) -> E* { // one IADD3 + one IMAD.WIDE pair
+		const uint32_t off = ox[EX.value+1]+oy[EY.value+1]+oz[EZ.value+1];
+		return reinterpret_cast<E*>(mad_wide(off, (uint32_t)sizeof(E), mad_wide(L.slot32, slot*(uint32_t)sizeof(E), base)));
+	};
+	typedef std::integral_constant<int, 0> Z0;
+	float f[Q];
+	f[0] = C::decode(load_global<E>(at(Z0{}, Z0{}, Z0{}, 0u)));
+	static_for<1, Q, 2>([&](auto I) { // load_f, src/kernel.cpp:1326-1332
+		constexpr int i = I;
+		f[i  ] = C::decode(load_global<E>(at(Z0{}, Z0{}, Z0{}, ODD ? (uint32_t)i : (uint32_t)i+1u)));
+		f[i+1] = C::decode(load_global<E>(at(std::integral_constant<int, dir_x(i)>{}, std::integral_constant<int, dir_y(i)>{}, std::integral_constant<int, dir_z(i)>{}, ODD ? (uint32_t)i+1u : (uint32_t)i)));
+	});
+	const bool is_e = L.eb!=0u && fb==TYPE_E;
+	float rho_e = 1.0f, ux_e = 0.0f, uy_e = 0.0f, uz_e = 0.0f;
+	const uint64_t N = cells(L);
+	if(is_e) { rho_e = L.rho[n]; ux_e = L.u[n]; uy_e = L.u[N+n]; uz_e = L.u[2ull*N+n]; }
+	float rhon, uxn, uyn, uzn;
+	collide_cell_fused<Q, COLL, VF, float>(f, 1.0f, 1.0f, is_e, false, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+	if(L.upd!=0u && !is_e) { L.rho[n] = rhon; L.u[n] = uxn; L.u[N+n] = uyn; L.u[2ull*N+n] = uzn; }
+	auto at_again = [&](auto EX, auto EY, auto EZ, uint32_t slot) -> E* {
+		const uint32_t off = ox[EX.value+1]+oy[EY.value+1]+oz[EZ.value+1];
+		return reinterpret_cast<E*>(mad_wide_again(off, (uint32_t)sizeof(E), mad_wide_again(L.slot32, slot*(uint32_t)sizeof(E), base)));
+	};
+	store_global<E>(at_again(Z0{}, Z0{}, Z0{}, 0u), C::encode(f[0]));
+	static_for<1, Q, 2>([&](auto I) { // store_f, src/kernel.cpp:1333-1339
+		constexpr int i = I;
+		store_global<E>(at_again(std::integral_constant<int, dir_x(i)>{}, std::integral_constant<int, dir_y(i)>{}, std::integral_constant<int, dir_z(i)>{}, ODD ? (uint32_t)i+1u : (uint32_t)i), C::encode(f[i]));
+		store_global<E>(at_again(Z0{}, Z0{}, Z0{}, ODD ? (uint32_t)i : (uint32_t)i+1u), C::encode(f[i+1]));
+	});
 }
 
 // initialize, src/kernel.cpp:1358-1430 (build without MOVING_BOUNDARIES / SURFACE / TEMPERATURE)

@@ -42,34 +42,46 @@ template<int Q, int COLL, int ST, bool VF> static int launch_pipe(const Lattice&
 	return L.odd ? launch_pipe_parity<Q, COLL, ST, VF, 1>(L, R, block, stream, reserve) : launch_pipe_parity<Q, COLL, ST, VF, 0>(L, R, block, stream, reserve);
 }
 
-// bulk-copy (TMA) kernel: the tile must span whole rows -- see the kernel's header comment
-static bool tma_eligible(const Lattice& L, const Region& R, const dim3& block) {
-	return L.Hx==0u && L.xo==0u && R.g0==0u && R.g1*4u==L.Nx && block.x*4u==L.Nx && L.Nx%16u==0u && block.x*block.y==128u && (R.y1-R.y0)%block.y==0u;
+// bulk-copy (TMA) kernel: the tile must span whole rows -- see the kernel's header comment. Block = (bx, 128/bx, G); the ring depth
+// S is whatever fits the shared memory of one SM (one block per SM), at least G+1.
+template<int Q, int ST> static uint32_t row_stages(const dim3& block) {
+	const uint32_t stage = row_stage_bytes((uint32_t)Q, ST==ST_FP32 ? 4u : 2u, block.x, block.y);
+	return std::min<uint32_t>(ROW_MAX_STAGES, (227u*1024u-1024u-128u)/stage);
 }
-template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false> static int launch_tma_parity(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
+template<int Q, int ST> static bool tma_eligible(const Lattice& L, const Region& R, const dim3& block) {
+	const uint32_t esz = ST==ST_FP32 ? 4u : 2u, inner = L.Nx-2u*L.Hx;
+	if(R.g0!=0u || R.g1*4u!=inner || block.x*4u!=inner || block.x*block.y!=128u || (inner*esz)%16u!=0u || (R.y1-R.y0)%block.y!=0u) return false;
+	if(L.Hx ? ((L.xo+1u)*esz)%16u!=0u : L.xo!=0u) return false; // the first non-halo cell of a row starts a 16-byte chunk
+	return row_stages<Q, ST>(block)>=(uint32_t)row_groups<Q, ST>()+1u;
+}
+// stand-in for the emulation's one-tile-per-call pacing and for regions that are only a few tiles: fewer groups than the kernel was
+// built for would need another instantiation, so small regions simply leave some groups idle
+template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false> static int launch_tma_parity(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve, const RowPeers& peers) {
 	const uint32_t tiles_y = (R.y1-R.y0)/block.y, nz = R.z1-R.z0;
-	constexpr uint32_t smem = tma_smem_bytes<Q, ST>();
-	int sms = 148, per_sm = tma_blocks_per_sm<Q, ST>();
+	constexpr uint32_t G = (uint32_t)row_groups<Q, ST>();
+	const uint32_t S = row_stages<Q, ST>(block);
+	const uint32_t smem = 128u+S*row_stage_bytes((uint32_t)Q, ST==ST_FP32 ? 4u : 2u, block.x, block.y);
+	int sms = 148;
 #if !defined(FX3D_HOST_EMULATION)
 	static std::atomic<uint64_t> configured{0ull};
 	int dev = 0; cudaGetDevice(&dev);
 	if(dev>=64 || !((configured.load()>>dev)&1ull)) {
-		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024-1024);
 		if(e!=cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stream_collide_tma)");
 		if(dev<64) configured.fetch_or(1ull<<dev);
 	}
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 #else
-	sms = 2; per_sm = 1;
+	sms = 2;
 #endif
-	const uint64_t all_blocks = (uint64_t)sms*(uint64_t)per_sm, blocks = all_blocks>2ull*(uint64_t)std::max(reserve, 0) ? all_blocks-(uint64_t)std::max(reserve, 0) : all_blocks, ntiles = (uint64_t)tiles_y*nz;
+	const uint64_t all_blocks = (uint64_t)sms, take = (uint64_t)std::max(reserve, 0)/4ull, blocks = all_blocks>2ull*take ? all_blocks-take : all_blocks, ntiles = (uint64_t)tiles_y*nz;
 	if(ntiles==0ull) return FX3D_OK;
-	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, blocks), 1u, 1u);
+	const dim3 grid((uint32_t)std::min<uint64_t>((ntiles+G-1u)/G, blocks), 1u, 1u);
 	g_kind_launches[3]++;
-	FX3D_LAUNCH_SMEM((k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG, MB>), grid, block, smem, stream, L, R, tiles_y);
+	FX3D_LAUNCH_SMEM((k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG, MB>), grid, dim3(block.x, block.y, G), smem, stream, L, R, tiles_y, S, peers);
 	return check_launch("stream_collide (bulk copies)");
 }
-// segment form: tiles are full 4*block.x-cell segments of longer rows, or rows with x halos
+// row segments (rows longer than 512 cells, shapes the whole-row kernel does not take): bulk loads, direct stores
 template<int Q, int ST> static bool tmaseg_eligible(const Lattice& L, const Region& R, const dim3& block) {
 	const uint32_t esz = ST==ST_FP32 ? 4u : 2u, groups = R.g1-R.g0;
 	if((uint64_t)tmaseg_smem_bytes<Q, ST>()*tma_blocks_per_sm<Q, ST>()+2048u>227u*1024u) return false; // D3Q27 FP32
@@ -77,33 +89,6 @@ template<int Q, int ST> static bool tmaseg_eligible(const Lattice& L, const Regi
 	if(((uint64_t)(L.Hx+R.g0*4u+L.xo)*esz)%16u!=0u) return false; // segment starts on a 16-byte boundary of its row
 	if(L.Hx==0u && (L.Nx*esz)%16u!=0u) return false;               // so does the periodic wrap chunk
 	return true;
-}
-template<int Q, int COLL, int ST, bool VF, int ODD> static int launch_tmaseg_parity(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
-	const uint32_t tiles_x = (R.g1-R.g0)/block.x, tiles_y = (R.y1-R.y0)/block.y, nz = R.z1-R.z0;
-	constexpr uint32_t smem = tmaseg_smem_bytes<Q, ST>();
-	int sms = 148, per_sm = tma_blocks_per_sm<Q, ST>();
-#if !defined(FX3D_HOST_EMULATION)
-	static std::atomic<uint64_t> configured{0ull};
-	int dev = 0; cudaGetDevice(&dev);
-	if(dev>=64 || !((configured.load()>>dev)&1ull)) {
-		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_tma_seg<Q, COLL, ST, VF, ODD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if(e!=cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stream_collide_tma_seg)");
-		if(dev<64) configured.fetch_or(1ull<<dev);
-	}
-	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-#else
-	sms = 2; per_sm = 1;
-#endif
-	const uint64_t all_blocks = (uint64_t)sms*(uint64_t)per_sm, blocks = all_blocks>2ull*(uint64_t)std::max(reserve, 0) ? all_blocks-(uint64_t)std::max(reserve, 0) : all_blocks, ntiles = (uint64_t)tiles_x*tiles_y*nz;
-	if(ntiles==0ull) return FX3D_OK;
-	if((uint64_t)tiles_x*tiles_y>0xFFFFFFFFull) { set_error("region has too many tile columns"); return FX3D_ERR_INVALID; }
-	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, blocks), 1u, 1u);
-	g_kind_launches[4]++;
-	FX3D_LAUNCH_SMEM((k_stream_collide_tma_seg<Q, COLL, ST, VF, ODD>), grid, block, smem, stream, L, R, tiles_x, tiles_y);
-	return check_launch("stream_collide (bulk copies, row segments)");
-}
-template<int Q, int COLL, int ST, bool VF> static int launch_tmaseg(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
-	return L.odd ? launch_tmaseg_parity<Q, COLL, ST, VF, 1>(L, R, block, stream, reserve) : launch_tmaseg_parity<Q, COLL, ST, VF, 0>(L, R, block, stream, reserve);
 }
 template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false> static int launch_hyb_parity(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
 	const uint32_t tiles_x = (R.g1-R.g0)/block.x, tiles_y = (R.y1-R.y0)/block.y, nz = R.z1-R.z0;
@@ -132,17 +117,23 @@ template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = f
 template<int Q, int COLL, int ST, bool VF, bool SG = false, bool MB = false> static int launch_hyb(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
 	return L.odd ? launch_hyb_parity<Q, COLL, ST, VF, 1, SG, MB>(L, R, block, stream, reserve) : launch_hyb_parity<Q, COLL, ST, VF, 0, SG, MB>(L, R, block, stream, reserve);
 }
-template<int Q, int COLL, int ST, bool VF, bool SG = false, bool MB = false> static int launch_tma(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
-	return L.odd ? launch_tma_parity<Q, COLL, ST, VF, 1, SG, MB>(L, R, block, stream, reserve) : launch_tma_parity<Q, COLL, ST, VF, 0, SG, MB>(L, R, block, stream, reserve);
+template<int Q, int COLL, int ST, bool VF, bool SG = false, bool MB = false> static int launch_tma(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve, const RowPeers& peers) {
+	return L.odd ? launch_tma_parity<Q, COLL, ST, VF, 1, SG, MB>(L, R, block, stream, reserve, peers) : launch_tma_parity<Q, COLL, ST, VF, 0, SG, MB>(L, R, block, stream, reserve, peers);
 }
 
-template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, int cells_per_thread, int collision, bool volume_force, void* stream, int reserve, int ext) {
+template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, int cells_per_thread, int collision, bool volume_force, void* stream, int reserve, int ext, const RowPeers* fused) {
 	if(R.g1<=R.g0||R.y1<=R.y0||R.z1<=R.z0) return FX3D_OK;
+	RowPeers peers; // the y/z neighbours whose rows this launch delivers itself; without them every row stays in this domain's memory
+	for(int k=0; k<9; k++) peers.fi[k] = fused ? fused->fi[k] : nullptr;
+	peers.fi[4] = L.fi;
+	Lattice Lk = L; // the whole-row kernel routes halo rows by Hy/Hz: unfused launches see no y/z halos (rows then stay where the general rule puts them: here)
+	if(!fused) { Lk.Hy = 0u; Lk.Hz = 0u; }
+	if(cells_per_thread==-100) return tma_eligible<Q, ST>(L, R, block_shape(R.g1-R.g0)) ? FX3D_OK : 1; // query: would the whole-row kernel take this region?
 	if(ext!=0) { // SUBGRID (bit 0) and/or MOVING_BOUNDARIES (bit 1): the whole-row bulk-copy kernel (cells_per_thread 0, regions in groups of 4) or the general kernel (1)
 		const dim3 block = block_shape(R.g1-R.g0);
 		const bool sg = (ext&1)!=0, mb = (ext&2)!=0;
 		if(cells_per_thread==0) {
-			if(!tma_eligible(L, R, block)) { // row segments / x halos: bulk loads + direct stores; else nothing launched, the caller falls back to the general kernel
+			if(!tma_eligible<Q, ST>(L, R, block)) { // row segments: bulk loads + direct stores; else nothing launched, the caller falls back to the general kernel
 				if(!tmaseg_eligible<Q, ST>(L, R, block)) return 1;
 #define FX3D_HYB_EXT(COLL, VF) (sg ? (mb ? launch_hyb<Q, COLL, ST, VF, true, true>(L, R, block, stream, reserve) : launch_hyb<Q, COLL, ST, VF, true, false>(L, R, block, stream, reserve)) \
                                    : launch_hyb<Q, COLL, ST, VF, false, true>(L, R, block, stream, reserve))
@@ -150,8 +141,8 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 				return volume_force ? FX3D_HYB_EXT(COLL_TRT, true) : FX3D_HYB_EXT(COLL_TRT, false);
 #undef FX3D_HYB_EXT
 			}
-#define FX3D_TMA_EXT(COLL, VF) (sg ? (mb ? launch_tma<Q, COLL, ST, VF, true, true>(L, R, block, stream, reserve) : launch_tma<Q, COLL, ST, VF, true, false>(L, R, block, stream, reserve)) \
-                                   : launch_tma<Q, COLL, ST, VF, false, true>(L, R, block, stream, reserve))
+#define FX3D_TMA_EXT(COLL, VF) (sg ? (mb ? launch_tma<Q, COLL, ST, VF, true, true>(Lk, R, block, stream, reserve, peers) : launch_tma<Q, COLL, ST, VF, true, false>(Lk, R, block, stream, reserve, peers)) \
+                                   : launch_tma<Q, COLL, ST, VF, false, true>(Lk, R, block, stream, reserve, peers))
 			if(collision==COLL_SRT) return volume_force ? FX3D_TMA_EXT(COLL_SRT, true) : FX3D_TMA_EXT(COLL_SRT, false);
 			return volume_force ? FX3D_TMA_EXT(COLL_TRT, true) : FX3D_TMA_EXT(COLL_TRT, false);
 #undef FX3D_TMA_EXT
@@ -166,24 +157,31 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 	}
 	if(cells_per_thread<=0) { // persistent kernels; R.g0/g1 are in groups of pipe_cells<Q,ST>() cells. 0: bulk copies where the tile spans the row, else cp.async; -1: cp.async
 		const dim3 block = block_shape(R.g1-R.g0);
-		if(cells_per_thread==0 && pipe_cells<Q, ST>()==4 && !tma_eligible(L, R, block) && tmaseg_eligible<Q, ST>(L, R, block)) { // row segments / x halos: bulk loads, direct stores
+		const bool rows = tma_eligible<Q, ST>(L, R, block);
+		if(cells_per_thread==-2 && !rows) return 1; // -2: bulk copies of whole rows or nothing (regions in groups of 4 cells); 1 = "not eligible", no launch
+		if(rows && (cells_per_thread==-2 || ((cells_per_thread==0 || cells_per_thread==-3) && pipe_cells<Q, ST>()==4))) {
+			if(collision==COLL_SRT) return volume_force ? launch_tma<Q, COLL_SRT, ST, true>(Lk, R, block, stream, reserve, peers) : launch_tma<Q, COLL_SRT, ST, false>(Lk, R, block, stream, reserve, peers);
+			return volume_force ? launch_tma<Q, COLL_TRT, ST, true>(Lk, R, block, stream, reserve, peers) : launch_tma<Q, COLL_TRT, ST, false>(Lk, R, block, stream, reserve, peers);
+		}
+		if(fused) return 1; // the caller asked for fused halo delivery, which only the whole-row kernel provides
+		if((cells_per_thread==0 || cells_per_thread==-3) && pipe_cells<Q, ST>()==4 && tmaseg_eligible<Q, ST>(L, R, block)) { // row segments: bulk loads, direct stores
 			if(collision==COLL_SRT) return volume_force ? launch_hyb<Q, COLL_SRT, ST, true>(L, R, block, stream, reserve) : launch_hyb<Q, COLL_SRT, ST, false>(L, R, block, stream, reserve);
 			return volume_force ? launch_hyb<Q, COLL_TRT, ST, true>(L, R, block, stream, reserve) : launch_hyb<Q, COLL_TRT, ST, false>(L, R, block, stream, reserve);
-		}
-		if(cells_per_thread==-3 && pipe_cells<Q, ST>()==4 && !tma_eligible(L, R, block) && tmaseg_eligible<Q, ST>(L, R, block)) { // variant 16: bulk stores as well
-			if(collision==COLL_SRT) return volume_force ? launch_tmaseg<Q, COLL_SRT, ST, true>(L, R, block, stream, reserve) : launch_tmaseg<Q, COLL_SRT, ST, false>(L, R, block, stream, reserve);
-			return volume_force ? launch_tmaseg<Q, COLL_TRT, ST, true>(L, R, block, stream, reserve) : launch_tmaseg<Q, COLL_TRT, ST, false>(L, R, block, stream, reserve);
-		}
-		if(cells_per_thread==-2 && !tma_eligible(L, R, block)) return 1; // -2: bulk copies or nothing (regions in groups of 4 cells); 1 = "not eligible", no launch
-		if((cells_per_thread==-2 || ((cells_per_thread==0 || cells_per_thread==-3) && pipe_cells<Q, ST>()==4)) && tma_eligible(L, R, block)) {
-			if(collision==COLL_SRT) return volume_force ? launch_tma<Q, COLL_SRT, ST, true>(L, R, block, stream, reserve) : launch_tma<Q, COLL_SRT, ST, false>(L, R, block, stream, reserve);
-			return volume_force ? launch_tma<Q, COLL_TRT, ST, true>(L, R, block, stream, reserve) : launch_tma<Q, COLL_TRT, ST, false>(L, R, block, stream, reserve);
 		}
 		if(collision==COLL_SRT) return volume_force ? launch_pipe<Q, COLL_SRT, ST, true>(L, R, block, stream, reserve) : launch_pipe<Q, COLL_SRT, ST, false>(L, R, block, stream, reserve);
 		return volume_force ? launch_pipe<Q, COLL_TRT, ST, true>(L, R, block, stream, reserve) : launch_pipe<Q, COLL_TRT, ST, false>(L, R, block, stream, reserve);
 	}
 	const dim3 block = block_shape(R.g1-R.g0);
 	const dim3 grid((R.g1-R.g0+block.x-1u)/block.x, (R.y1-R.y0+block.y-1u)/block.y, R.z1-R.z0);
+	if(cells_per_thread==32) { // one cell per thread at high occupancy (R in cells)
+		if((uint64_t)L.Nx*L.Ny*L.Nz>0xFFFFFFFFull) { set_error("the occupancy kernel indexes cells with 32 bits"); return FX3D_ERR_INVALID; }
+		g_kind_launches[6]++;
+#define FX3D_OCC(COLL, VF) do { if(L.odd) FX3D_LAUNCH((k_stream_collide_occ<Q, COLL, ST, VF, 1>), grid, block, stream, L, R); else FX3D_LAUNCH((k_stream_collide_occ<Q, COLL, ST, VF, 0>), grid, block, stream, L, R); } while(0)
+		if(collision==COLL_SRT) { if(volume_force) FX3D_OCC(COLL_SRT, true); else FX3D_OCC(COLL_SRT, false); }
+		else { if(volume_force) FX3D_OCC(COLL_TRT, true); else FX3D_OCC(COLL_TRT, false); }
+#undef FX3D_OCC
+		return check_launch("stream_collide (one cell per thread, high occupancy)");
+	}
 #define FX3D_SC(KERNEL, COLL, VF) FX3D_LAUNCH((KERNEL<Q, COLL, ST, VF>), grid, block, stream, L, R)
 #define FX3D_SCV(K, COLL, VF) do { if(L.odd) FX3D_LAUNCH((k_stream_collide_vec<Q, COLL, ST, VF, K, 1>), grid, block, stream, L, R); else FX3D_LAUNCH((k_stream_collide_vec<Q, COLL, ST, VF, K, 0>), grid, block, stream, L, R); } while(0)
 #define FX3D_SC_ALL(MACRO, ARG) \
@@ -198,6 +196,6 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 #undef FX3D_SC
 	return check_launch("stream_collide");
 }
-template int launch_stream_collide<FX3D_Q, FX3D_ST>(const Lattice&, const Region&, int, int, bool, void*, int, int);
+template int launch_stream_collide<FX3D_Q, FX3D_ST>(const Lattice&, const Region&, int, int, bool, void*, int, int, const RowPeers*);
 
 } // namespace fx3d

@@ -90,6 +90,7 @@ LBM_Domain::LBM_Domain(const Device_Info& device_info, fx3d_stream shared_stream
 uint LBM_Domain::get_velocity_set() const { return velocity_set; }
 
 void LBM_Domain::enqueue_initialize() { fx3d_check(fx3d_initialize(&lattice, device.get_stream()), "initialize"); }
+void LBM_Domain::enqueue_stream_collide_fused(void* const* fi_neighbours) { fx3d_check(fx3d_stream_collide_fused(&lattice, t, fx, fy, fz, fi_neighbours, device.get_stream()), "stream_collide_fused"); }
 void LBM_Domain::enqueue_stream_collide(const int region) { fx3d_check(fx3d_stream_collide(&lattice, t, fx, fy, fz, region, device.get_stream()), "stream_collide"); }
 void LBM_Domain::enqueue_run_steps(const ulong steps) { fx3d_check(fx3d_run_steps(&lattice, t, steps, fx, fy, fz, device.get_stream()), "stream_collide"); }
 #ifdef MOVING_BOUNDARIES
@@ -187,6 +188,8 @@ void LBM::construct(const uint Nx_, const uint Ny_, const uint Nz_, const uint D
 	rho = Memory_Container<float>(this, b_rho, "rho");
 	u = Memory_Container<float>(this, b_u, "u");
 	flags = Memory_Container<uchar>(this, b_flags, "flags");
+	fused_halo = Dy*Dz>1u;
+	for(uint d=0u; d<D && fused_halo; d++) fused_halo = fx3d_fused_halo_supported(&lbm_domain[d]->get_lattice())==1;
 }
 LBM::LBM(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx, const float fy, const float fz, const float sigma, const float alpha, const float beta, const uint particles_N, const float particles_rho) {
 	construct(Nx, Ny, Nz, Dx, Dy, Dz, nu, fx, fy, fz, sigma, alpha, beta, particles_N, particles_rho);
@@ -266,6 +269,10 @@ uint LBM::neighbour(const uint d, const uint axis, const int sign) const {
 	c[axis] = (c[axis]+Dn[axis]+(uint)sign)%Dn[axis];
 	return c[0]+(c[1]+c[2]*Dy)*Dx;
 }
+uint LBM::neighbour_yz(const uint d, const int dy, const int dz) const {
+	const uint x = (d%(Dx*Dy))%Dx, y = (d%(Dx*Dy))/Dx, z = d/(Dx*Dy);
+	return x+((y+Dy+(uint)dy)%Dy+((z+Dz+(uint)dz)%Dz)*Dy)*Dx;
+}
 void LBM::rendezvous() { // every domain tells its face neighbours "I am here" and waits for theirs, on the device
 	rendezvous_count++;
 	const uint Dn[3] = { Dx, Dy, Dz };
@@ -275,6 +282,10 @@ void LBM::rendezvous() { // every domain tells its face neighbours "I am here" a
 			const uint n = neighbour(d, axis, sign);
 			if(n!=d && std::find(nb[d].begin(), nb[d].end(), n)==nb[d].end()) nb[d].push_back(n);
 		}
+		if(Dy>1u && Dz>1u) for(int dy=-1; dy<=1; dy+=2) for(int dz=-1; dz<=1; dz+=2) { // with fused y/z halo delivery the diagonal neighbours write into this domain too
+			const uint n = neighbour_yz(d, dy, dz);
+			if(n!=d && std::find(nb[d].begin(), nb[d].end(), n)==nb[d].end()) nb[d].push_back(n);
+		}
 		std::sort(nb[d].begin(), nb[d].end());
 		vector<LBM_Domain*> peers;
 		for(uint n : nb[d]) peers.push_back(lbm_domain[n]);
@@ -282,9 +293,9 @@ void LBM::rendezvous() { // every domain tells its face neighbours "I am here" a
 	}
 	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_rendezvous_wait(nb[d], rendezvous_count);
 }
-void LBM::communicate_field(const bool ddfs) { // x, then y, then z, so that edges and corners travel with later faces
+void LBM::communicate_field(const bool ddfs, const uint axes) { // x, then y, then z, so that edges and corners travel with later faces
 	const uint Dn[3] = { Dx, Dy, Dz };
-	for(uint axis=0u; axis<3u; axis++) if(Dn[axis]>1u) {
+	for(uint axis=0u; axis<3u; axis++) if(Dn[axis]>1u && ((axes>>axis)&1u)) {
 		if(ddfs && axis==0u) for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_pack_x_faces();
 		rendezvous(); // what this phase reads (stream_collide output, or the previous axis' halos) is complete everywhere
 		for(uint d=0u; d<get_D(); d++) {
@@ -320,6 +331,17 @@ void LBM::initialize() {
 	initialized = true;
 }
 void LBM::do_time_step() {
+	if(fused_halo) { // the kernel delivers the y/z halo rows itself: one rendezvous, then only the x faces remain (see fx3d_stream_collide_fused)
+		for(uint d=0u; d<get_D(); d++) {
+			void* table[9] = { nullptr };
+			for(int dz=-1; dz<=1; dz++) for(int dy=-1; dy<=1; dy++) if((dy==0||Dy>1u) && (dz==0||Dz>1u)) table[(dy+1)+3*(dz+1)] = lbm_domain[neighbour_yz(d, dy, dz)]->get_lattice().fi;
+			lbm_domain[d]->enqueue_stream_collide_fused(table);
+		}
+		rendezvous();
+		if(Dx>1u) communicate_field(true, 1u);
+		for(uint d=0u; d<get_D(); d++) lbm_domain[d]->increment_time_step();
+		return;
+	}
 	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_stream_collide();
 	if(get_D()>1u) communicate_fi();
 	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->increment_time_step();

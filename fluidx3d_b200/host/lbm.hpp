@@ -39,6 +39,7 @@ public:
 
 	void enqueue_initialize();
 	void enqueue_stream_collide(const int region=FX3D_REGION_ALL);
+	void enqueue_stream_collide_fused(void* const* fi_neighbours); // with the y/z halo rows delivered by the kernel itself
 	void enqueue_run_steps(const ulong steps); // D==1 only: `steps` stream_collide launches without host work in between
 	void enqueue_update_fields();
 #ifdef MOVING_BOUNDARIES
@@ -88,8 +89,10 @@ class LBM {
 	void initialize();
 	void do_time_step();
 	uint neighbour(const uint d, const uint axis, const int sign) const;
+	uint neighbour_yz(const uint d, const int dy, const int dz) const;
+	bool fused_halo = false;           // every domain's shape qualifies for fx3d_stream_collide_fused
 	void rendezvous();                 // all domains meet their face neighbours on the device
-	void communicate_field(const bool ddfs);
+	void communicate_field(const bool ddfs, const uint axes=7u); // axes: bit per axis
 	void communicate_fi();
 	void communicate_rho_u_flags();
 	void construct(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx, const float fy, const float fz, const float sigma, const float alpha, const float beta, const uint particles_N, const float particles_rho);

@@ -232,7 +232,7 @@ class LBM:
     (src/lbm.hpp:428-435): pass Dx,Dy,Dz by keyword."""
 
     def __init__(self, Nx, Ny, Nz, nu, fx=0.0, fy=0.0, fz=0.0, *, Dx=1, Dy=1, Dz=1, velocity_set=19, collision=SRT, storage=FP32,
-                 features=0, devices=None, comm=None, lib=None, host_fields=True, overlap=False, benchmark=False):
+                 features=0, devices=None, comm=None, lib=None, host_fields=True, overlap=False, benchmark=False, fuse_halo=True):
         self.lib = lib or capi.lib()
         NDx, NDy, NDz = (Nx // Dx) * Dx if Dx else 0, (Ny // Dy) * Dy if Dy else 0, (Nz // Dz) * Dz if Dz else 0
         self._sanity_checks_constructor(Nx, Ny, Nz, Dx, Dy, Dz, nu, fx, fy, fz, velocity_set, collision, storage, features)
@@ -242,7 +242,8 @@ class LBM:
         self.Hx, self.Hy, self.Hz = int(Dx > 1), int(Dy > 1), int(Dz > 1)
         self.velocity_set, self.collision, self.storage, self.features = velocity_set, collision, storage, features
         self.initialized = False
-        self.comm, self.overlap, self.benchmark = comm, overlap, benchmark
+        self.comm, self.overlap, self.benchmark, self.fuse_halo = comm, overlap, benchmark, fuse_halo
+        self._fused = {}
         D = self.get_D()
         if comm is not None and comm.world_size != D:
             raise ValueError(f"{D} domains need {D} processes, got {comm.world_size}")
@@ -323,6 +324,18 @@ class LBM:
         c[axis] = (c[axis] + sign) % Dn
         return c[0] + (c[1] + c[2] * self.Dy) * self.Dx
 
+    def _neighbour_yz(self, d, dy, dz):
+        x, y, z = _domain_xyz(d, self.Dx, self.Dy)
+        return x + ((y + dy) % self.Dy + ((z + dz) % self.Dz) * self.Dy) * self.Dx
+
+    def _sync_neighbours(self, d):
+        """domains whose kernels read or write this domain's memory within a step: the face neighbours, plus -- with the y/z halo
+        delivery fused into stream_collide -- the diagonal neighbours in the y-z plane"""
+        nb = {self._neighbour(d, a, s) for a in range(3) for s in (1, -1) if (self.Dx, self.Dy, self.Dz)[a] > 1}
+        if self.Dy > 1 and self.Dz > 1:
+            nb |= {self._neighbour_yz(d, dy, dz) for dy in (-1, 1) for dz in (-1, 1)}
+        return sorted(nb - {d})
+
     def _connect_peers(self):
         """table d -> {fi, rho, u, flags, sync} device pointers for every domain this process needs to read or signal"""
         peers = {d: dict(fi=dom.fi.device_ptr, rho=dom.rho.device_ptr, u=dom.u.device_ptr, flags=dom.flags.device_ptr, sync=dom.sync_array, xfer=dom.xfer, device=dom.device)
@@ -341,7 +354,7 @@ class LBM:
                 self.lib.ipc_get_handle(dom.device, peers[d][k], h)
                 mine[k] = h.raw
             everyone = self.comm.allgather(mine)
-            needed = {self._neighbour(d, a, s) for a in range(3) for s in (1, -1) if (self.Dx, self.Dy, self.Dz)[a] > 1} - {d}
+            needed = set(self._sync_neighbours(d))
             for r in needed:
                 entry = {"device": dom.device}
                 for k in shared:
@@ -351,23 +364,34 @@ class LBM:
                 peers[r] = entry
             self._ipc_opened = {r: peers[r] for r in needed}
         self._peers = peers
+        # fused y/z halo delivery: per owned domain the 3x3 table of y/z neighbours' DDF buffers (include/fx3d.h: fx3d_stream_collide_fused)
+        self._fused = {}
+        if (self.Dy > 1 or self.Dz > 1) and not self.overlap and self.fuse_halo:
+            for d, dom in self.lbm_domain.items():
+                if self.lib.fused_halo_supported(C.byref(dom.lat)):
+                    table = (C.c_void_p * 9)()
+                    for dz in (-1, 0, 1):
+                        for dy in (-1, 0, 1):
+                            if (dy and self.Dy == 1) or (dz and self.Dz == 1): continue
+                            table[(dy + 1) + 3 * (dz + 1)] = peers[self._neighbour_yz(d, dy, dz)]["fi"]
+                    self._fused[d] = table
 
     # ---- halo exchange: replaces communicate_field, src/lbm.cpp:1355-1383 ----
     def _barrier(self, axis_or_all):
         """device-side rendezvous of every owned domain with its face neighbours (replaces the finish_queue barriers)"""
         self._seq += 1
         for d, dom in self.local_domains():
-            nb = sorted({self._neighbour(d, a, s) for a in range(3) for s in (1, -1) if (self.Dx, self.Dy, self.Dz)[a] > 1} - {d})
+            nb = self._sync_neighbours(d)
             arr = (C.c_void_p * len(nb))(*[self._peers[r]["sync"] for r in nb])
             self.lib.rendezvous_signal(dom.device, arr, len(nb), d, self._seq, dom.stream)
         for d, dom in self.local_domains():
-            nb = sorted({self._neighbour(d, a, s) for a in range(3) for s in (1, -1) if (self.Dx, self.Dy, self.Dz)[a] > 1} - {d})
+            nb = self._sync_neighbours(d)
             idx = (C.c_int * len(nb))(*nb)
             self.lib.rendezvous_wait(dom.device, dom.sync_array, idx, len(nb), self._seq, 20000, dom.stream)
 
-    def _communicate(self, field):
+    def _communicate(self, field, axes=(0, 1, 2)):
         for axis, Dn in enumerate((self.Dx, self.Dy, self.Dz)):
-            if Dn <= 1: continue
+            if Dn <= 1 or axis not in axes: continue
             staged = axis == 0 and field == "fi"
             if staged:  # x faces: pack my two outgoing layers into my linear buffers first, so that the peer reads below are coalesced
                 for d, dom in self.local_domains():
@@ -417,6 +441,15 @@ class LBM:
                 self.lib.stream_wait_event(dev, self._streams2[dev], self._events[dev][0])
             for _, dom in self.local_domains(): dom.enqueue_stream_collide(REGION_INTERIOR, stream=self._streams2[dom.device])
             for dev in devs: self.lib.event_record(dev, self._events[dev][1], self._streams2[dev])
+        elif self._fused and len(self._fused) == len(self.lbm_domain):
+            # y/z halo rows are delivered by the kernel itself (every stored row goes to the domain that reads it next); what remains is
+            # one rendezvous -- nobody starts step t+1 before its neighbours have finished step t -- and, for x-decomposed grids, the x faces
+            for d, dom in self.local_domains():
+                self.lib.stream_collide_fused(C.byref(dom.lat), dom.t, dom.fx, dom.fy, dom.fz, self._fused[d], dom.stream)
+            self._barrier(None)
+            if self.Dx > 1: self._communicate("fi", axes=(0,))
+            for _, dom in self.local_domains(): dom.increment_time_step()
+            return
         else:
             for _, dom in self.local_domains(): dom.enqueue_stream_collide()
         if self.get_D() > 1: self.communicate_fi()

@@ -108,19 +108,30 @@ int fx3d_update_fields(const fx3d_lattice* lattice, uint64_t t, float fx, float 
 /* MOVING_BOUNDARIES: re-mark the cells next to TYPE_S cells with non-zero velocity as TYPE_MS after the boundary velocities
  * changed (kernel update_moving_boundaries, kernel.cpp:1432-1450; LBM::update_moving_boundaries, lbm.cpp:1018-1027) */
 int fx3d_update_moving_boundaries(const fx3d_lattice* lattice, fx3d_stream stream);
+/* stream_collide over every non-halo cell WITH the y/z part of the halo exchange fused into it (replaces communicate_fi for those axes,
+ * lbm.cpp:1355-1387): each DDF row a step writes goes straight to the memory of the domain that reads it in the next step -- this domain's,
+ * or a y/z/diagonal neighbour's over NVLink. fi_neighbours[(dy+1)+3*(dz+1)] = DDF buffer of the domain at offset (dy,dz) in the domain grid
+ * (periodic), identical geometry; entries for undecomposed axes and [4] (self) are ignored. The neighbours must not run step t+1 before this
+ * call has finished and vice versa (one fx3d_rendezvous per step); x halos still travel with fx3d_transfer_* / fx3d_exchange_fi afterwards.
+ * Only the whole-row bulk-copy kernel does this: fx3d_fused_halo_supported() tells whether a lattice qualifies (non-halo row length a multiple
+ * of 4 and at most 512 cells, rows 16-byte multiples, y extent a multiple of the rows per tile). */
+int fx3d_stream_collide_fused(const fx3d_lattice* lattice, uint64_t t, float fx, float fy, float fz, void* const* fi_neighbours, fx3d_stream stream);
+int fx3d_fused_halo_supported(const fx3d_lattice* lattice); /* 1 or 0 */
 /* n consecutive stream_collide steps t0..t0+n-1 of a single (non-decomposed) domain, no host work in between */
 int fx3d_run_steps(const fx3d_lattice* lattice, uint64_t t0, uint64_t steps, float fx, float fy, float fz, fx3d_stream stream);
 /* kernel choice for tests and profiling: 0 library default (persistent kernels: TMA bulk copies where the tile spans whole rows,
  * or -- FP32 -- row segments; else a cp.async ring), 1 general one-cell-per-thread kernel, 2 or 4 vector kernel with that many
  * cells per thread (falls back when the row length does not divide), 8 persistent kernel with the cp.async ring only,
- * 16 persistent kernel with bulk copies wherever they are eligible. Results are bit-identical for every choice. */
+ * 16 persistent kernel with bulk copies wherever they are eligible, 32 one cell per thread at high occupancy (64 registers, any grid
+ * size; the reference kernel's own shape). Results are bit-identical for every choice. */
 int fx3d_set_kernel_variant(int variant);
 /* FX3D_REGION_INTERIOR launches of the persistent kernel leave this many resident-block slots free, so that the halo exchange
  * kernels enqueued on another stream find room beside it (default 8; 0 = occupy every slot) */
 int fx3d_set_interior_reserve(int blocks);
 /* stream_collide launches so far by kernel kind: 0 general (1 cell/thread), 1 vector (2/4 cells/thread), 2 persistent with a
  * cp.async ring, 3 persistent with bulk copies of whole rows, 4 persistent with bulk copies of row segments, 5 persistent with bulk loads
- * of row segments and direct stores */
+ * of row segments and direct stores, 6 one cell per thread at high occupancy, 7 bulk copies of whole rows through a ring shared by
+ * several compute groups (with fused y/z halo delivery) */
 int fx3d_stream_collide_launches(int kind, uint64_t* launches);
 int fx3d_launch_count(uint64_t* launches);                            /* kernels launched by this library so far */
 

@@ -44,7 +44,7 @@ struct WarpCtx {
 	int pred[32];
 	unsigned lanes;
 };
-struct ThreadCtx { WarpCtx* warp; unsigned lane; unsigned char* smem; std::barrier<>* block_bar; };
+struct ThreadCtx { WarpCtx* warp; unsigned lane; unsigned char* smem; std::barrier<>* block_bar; std::barrier<>* group_bar; };
 inline thread_local ThreadCtx tctx;
 }
 inline thread_local uint3_ threadIdx, blockIdx;
@@ -69,6 +69,7 @@ inline unsigned ballot(int p) {
 	return m;
 }
 inline unsigned char* block_smem() { return tctx.smem; }
+inline void group_barrier(unsigned) { tctx.group_bar->arrive_and_wait(); } // the calling thread's 128-thread group (groups are consecutive thread ranges)
 template<class F> void launch(dim3 grid, dim3 block, F&& body, size_t smem_bytes=0) {
 	const unsigned nthreads = block.x*block.y*block.z, nwarps = (nthreads+31u)/32u;
 	for(unsigned bz=0u; bz<grid.z; bz++) for(unsigned by=0u; by<grid.y; by++) for(unsigned bx=0u; bx<grid.x; bx++) {
@@ -79,6 +80,8 @@ template<class F> void launch(dim3 grid, dim3 block, F&& body, size_t smem_bytes
 		}
 		std::vector<unsigned char> smem(smem_bytes+128);
 		std::barrier<> block_bar((std::ptrdiff_t)nthreads);
+		std::vector<std::unique_ptr<std::barrier<>>> group_bars; // named barriers of 128-thread groups (bar.sync id, 128)
+		for(unsigned gi=0u; gi<(nthreads+127u)/128u; gi++) group_bars.push_back(std::make_unique<std::barrier<>>((std::ptrdiff_t)std::min(128u, nthreads-128u*gi)));
 		std::vector<std::thread> th;
 		th.reserve(nthreads);
 		for(unsigned tid=0u; tid<nthreads; tid++) th.emplace_back([&, tid]() {
@@ -86,8 +89,9 @@ template<class F> void launch(dim3 grid, dim3 block, F&& body, size_t smem_bytes
 			blockIdx = uint3_{ bx, by, bz };
 			blockDim = block; gridDim = grid;
 			tctx.warp = &warps[tid/32u]; tctx.lane = tid%32u; tctx.smem = smem.data()+((128-reinterpret_cast<uintptr_t>(smem.data())%128)%128);
-			tctx.block_bar = &block_bar;
+			tctx.block_bar = &block_bar; tctx.group_bar = group_bars[tid/128u].get();
 			body();
+			tctx.group_bar->arrive_and_drop();
 			tctx.warp->bar->arrive_and_drop(); // a thread that has returned no longer takes part in warp collectives
 			block_bar.arrive_and_drop();       // ... nor in block barriers
 		});

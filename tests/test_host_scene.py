@@ -27,7 +27,9 @@ CASES = [((19, SRT, FP32, 0), (16, 8, 6), (1, 1, 1), 4, None, None),
          ((19, SRT, FP16C, 0), (24, 6, 6), (2, 1, 1), 4, None, None),        # x decomposition on one device
          ((27, TRT, FP32, 3), (16, 8, 6), (1, 2, 2), 4, (1e-4, -2e-4, 3e-4), None),
          ((19, SRT, FP32, 16), (16, 8, 6), (1, 1, 2), 6, None, "1,0.05"),    # MOVING_BOUNDARIES with update_moving_boundaries() after 3 steps
-         ((19, SRT, FP16S, 8), (16, 8, 6), (1, 1, 1), 4, None, None)]        # SUBGRID
+         ((19, SRT, FP16S, 8), (16, 8, 6), (1, 1, 1), 4, None, None),        # SUBGRID
+         ((19, SRT, FP16S, 0), (64, 32, 8), (2, 2, 2), 5, None, None),       # whole-row tiles on every domain: y/z halo delivery fused into the kernel, x faces exchanged
+         ((19, TRT, FP32, 3), (32, 32, 8), (1, 2, 2), 4, (1e-4, -2e-4, 3e-4), None)]
 GPU_CASES = CASES + [((19, SRT, FP16S, 0), (512, 8, 8), (1, 1, 1), 6, None, None), ((19, SRT, FP32, 0), (128, 64, 32), (2, 2, 2), 10, None, None),
                      ((19, SRT, FP32, 16), (64, 64, 64), (1, 1, 1), 20, None, "63,0.1")]  # lid-driven cavity mechanism at a realistic size
 

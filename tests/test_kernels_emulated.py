@@ -52,7 +52,7 @@ CASES = [((19, SRT, FP32, 0), (16, 6, 4), (1, 1, 1)), ((19, SRT, FP16S, 0), (16,
 
 
 @pytest.mark.parametrize("v,dims,D", CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in CASES])
-@pytest.mark.parametrize("variant", [1, 2, 4, 8], ids=["general", "vector2", "vector4", "pipelined"])
+@pytest.mark.parametrize("variant", [1, 2, 4, 8, 32], ids=["general", "vector2", "vector4", "pipelined", "occupancy"])
 def test_emulated_kernels_match_oracle(emul, v, dims, D, variant):
     f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
     for steps in (1, 4):
@@ -85,20 +85,6 @@ SEG_CASES = [((19, SRT, FP16S, 0), (1024, 2, 2), (1, 1, 1)), ((19, SRT, FP16S, 0
 
 
 @pytest.mark.parametrize("v,dims,D", SEG_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in SEG_CASES])
-def test_emulated_bulk_copy_segments_match_oracle(emul, v, dims, D):
-    """the bulk-copy kernel on tiles that are segments of longer rows (periodic wrap across tiles) and on x-decomposed domains
-    (halo cells at the row ends): padded row buffers, partial bulk stores, single-element stores for the end chunks"""
-    f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
-    before = emul.kernel_kind_counts()
-    for steps in (1, 2, 5):
-        got, want = product(emul, v, dims, D, steps, f, 16), oracle(v, dims, D, steps, f)
-        for a, b in zip(got, want):
-            assert np.array_equal(bits(a), bits(b))
-    after = emul.kernel_kind_counts()
-    assert after[4] > before[4] and after[:3] == before[:3], "the segment bulk-copy kernel must be the one that ran"
-
-
-@pytest.mark.parametrize("v,dims,D", SEG_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in SEG_CASES])
 def test_emulated_hybrid_kernel_matches_oracle(emul, v, dims, D):
     """the default choice for row segments and x-decomposed domains: bulk loads into padded row buffers, stream-out straight
     from registers with the vector kernel's ownership rules (shuffles inside a warp, scalar stores at warp and segment ends)"""
@@ -109,7 +95,30 @@ def test_emulated_hybrid_kernel_matches_oracle(emul, v, dims, D):
         for a, b in zip(got, want):
             assert np.array_equal(bits(a), bits(b))
     after = emul.kernel_kind_counts()
-    assert after[5] > before[5] and after[:5] == before[:5], "the hybrid kernel must be the one that ran"
+    if (dims[0] // D[0]) > 512:
+        assert after[5] > before[5] and after[:5] == before[:5], "the hybrid kernel must be the one that ran"
+    else:  # x-decomposed domains whose rows fit one tile: the whole-row kernel takes them (halo cells in the row-buffer pads)
+        assert after[3] > before[3] and after[:3] == before[:3] and after[5] == before[5], "the whole-row bulk-copy kernel must be the one that ran"
+
+
+XROW_CASES = [((19, SRT, FP16S, 0), (64, 16, 4), (2, 1, 1)), ((19, TRT, FP32, 3), (128, 16, 6), (2, 2, 1)), ((27, SRT, FP16C, 2), (64, 64, 8), (2, 2, 2)),
+              ((19, SRT, FP16S, 1), (1024, 4, 4), (2, 1, 2)), ((27, TRT, FP32, 3), (64, 16, 6), (2, 1, 1)), ((19, SRT, FP32, 0), (32, 32, 8), (1, 2, 2)),
+              ((19, SRT, FP16S, 24), (64, 32, 8), (2, 2, 2)), ((19, TRT, FP16C, 11), (32, 32, 6), (1, 2, 1))]  # (rows per domain: a multiple of the rows per tile)
+
+
+@pytest.mark.parametrize("v,dims,D", XROW_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in XROW_CASES])
+def test_emulated_row_kernel_with_halos_and_fused_delivery(emul, v, dims, D):
+    """the whole-row bulk-copy kernel on decomposed domains: x halos live in the pads of the row buffers (no periodic wrap), and the y/z
+    part of the halo exchange is fused into the kernel -- every stored row goes to the domain that reads it next (LBM.do_time_step picks
+    fx3d_stream_collide_fused where fx3d_fused_halo_supported says so); several compute groups share one ring of stages"""
+    f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
+    before = emul.kernel_kind_counts()
+    for steps in (1, 2, 5):
+        got, want = product(emul, v, dims, D, steps, f, 0), oracle(v, dims, D, steps, f)
+        for a, b in zip(got, want):
+            assert np.array_equal(bits(a), bits(b))
+    after = emul.kernel_kind_counts()
+    assert after[3] > before[3] and all(after[k] == before[k] for k in (0, 1, 2, 4, 5, 6)), "the whole-row bulk-copy kernel must be the one that ran"
 
 
 SG_CASES = [((19, SRT, FP32, 8), (9, 7, 5), (1, 1, 1)), ((19, TRT, FP16S, 11), (12, 6, 6), (2, 1, 2)), ((27, SRT, FP16C, 8), (10, 6, 4), (1, 1, 1)),  # general kernel
@@ -259,7 +268,7 @@ def test_c_abi_error_behaviour(emul):
     from fluidx3d_b200.capi import Fx3dError
     for bad in (3, 5, 7, -1, 64):
         with pytest.raises(Fx3dError, match="variant must be"): emul.set_kernel_variant(bad)
-    for ok in (0, 1, 2, 4, 8, 16, 0): emul.set_kernel_variant(ok)
+    for ok in (0, 1, 2, 4, 8, 16, 32, 0): emul.set_kernel_variant(ok)
     with pytest.raises(Fx3dError, match="reserve"): emul.set_interior_reserve(-1)
     emul.set_interior_reserve(8)
     n = C.c_uint64(0)
