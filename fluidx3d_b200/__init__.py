@@ -3,3 +3,4 @@ reference's host API. The compute path is libfx3d_cuda.so (C ABI in include/fx3d
 binding (capi) and the Python mirror of the LBM host classes (lbm). The C++ host surface is in fluidx3d_b200/host/."""
 from .capi import (FP32, FP16S, FP16C, SRT, TRT, VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID, MOVING_BOUNDARIES, TYPE_S, TYPE_E, Fx3dError)  # noqa: F401
 from .lbm import LBM, LBM_Domain, Memory_Container, TorchComm  # noqa: F401
+from .mesh import Mesh, read_stl  # noqa: F401

@@ -72,6 +72,8 @@ _SIGS = {
     "fx3d_stream_collide_fused": (_I, [_LP, _U64, _F, _F, _F, C.POINTER(_VP), _VP], True),
     "fx3d_fused_halo_supported": (_I, [_LP], False),
     "fx3d_update_fields": (_I, [_LP, _U64, _F, _F, _F, _VP], True),
+    "fx3d_voxelize_mesh": (_I, [_LP, _I, _I, _I, _U32, _U64, C.c_uint8, _VP, _VP, _VP, _VP, _VP], True),
+    "fx3d_unvoxelize_mesh": (_I, [_LP, _I, _I, _I, C.c_uint8, _F, _F, _F, _F, _F, _F, _VP], True),
     "fx3d_run_steps": (_I, [_LP, _U64, _U64, _F, _F, _F, _VP], True),
     "fx3d_set_kernel_variant": (_I, [_I], True),
     "fx3d_launch_count": (_I, [C.POINTER(_U64)], True),

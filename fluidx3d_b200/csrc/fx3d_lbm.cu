@@ -230,6 +230,31 @@ int fx3d_update_moving_boundaries(const fx3d_lattice* lat, fx3d_stream stream) {
 	return check_launch("update_moving_boundaries");
 }
 
+int fx3d_voxelize_mesh(const fx3d_lattice* lat, int Ox, int Oy, int Oz, uint32_t direction, uint64_t t, uint8_t flag, const float* p0, const float* p1, const float* p2, const float* bbu, fx3d_stream stream) {
+	Lattice L;
+	if(!make_lattice(lat, t, 0.0f, 0.0f, 0.0f, L)) return FX3D_ERR_INVALID;
+	if(direction>2u || !p0 || !p1 || !p2 || !bbu) { set_error("voxelize_mesh: direction must be 0, 1 or 2 and the triangle buffers must not be null"); return FX3D_ERR_INVALID; }
+	if(int rc = use_device(lat->device)) return rc;
+	VoxelizeArgs V;
+	std::memcpy(&V.triangle_number, &bbu[0], 4);
+	V.x0 = bbu[1]; V.y0 = bbu[2]; V.z0 = bbu[3]; V.x1 = bbu[4]; V.y1 = bbu[5]; V.z1 = bbu[6]; V.cx = bbu[7]; V.cy = bbu[8]; V.cz = bbu[9];
+	V.ux = bbu[10]; V.uy = bbu[11]; V.uz = bbu[12]; V.rx = bbu[13]; V.ry = bbu[14]; V.rz = bbu[15]; V.Ox = Ox; V.Oy = Oy; V.Oz = Oz;
+	const uint64_t A = direction==0u ? (uint64_t)L.Ny*L.Nz : direction==1u ? (uint64_t)L.Nz*L.Nx : (uint64_t)L.Nx*L.Ny;
+	if(A>0xFFFFFFFFull) { set_error("face too large"); return FX3D_ERR_INVALID; }
+	const dim3 b(128u), g((uint32_t)((A+127ull)/128ull));
+	const uint32_t smem = VOX_CHUNK*9u*4u, t_odd = (uint32_t)(t&1ull);
+	FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { FX3D_LAUNCH_SMEM((k_voxelize_mesh<Q, ST>), g, b, smem, stream, L, direction, t_odd, flag, p0, p1, p2, V); })
+	return check_launch("voxelize_mesh");
+}
+int fx3d_unvoxelize_mesh(const fx3d_lattice* lat, int Ox, int Oy, int Oz, uint8_t flag, float x0, float y0, float z0, float x1, float y1, float z1, fx3d_stream stream) {
+	Lattice L;
+	if(!make_lattice(lat, 0ull, 0.0f, 0.0f, 0.0f, L)) return FX3D_ERR_INVALID;
+	if(int rc = use_device(lat->device)) return rc;
+	const uint64_t N = (uint64_t)L.Nx*L.Ny*L.Nz;
+	FX3D_LAUNCH(k_unvoxelize_mesh, dim3((uint32_t)((N+127ull)/128ull)), dim3(128u), stream, L, flag, x0, y0, z0, x1, y1, z1, Ox, Oy, Oz);
+	return check_launch("unvoxelize_mesh");
+}
+
 static bool face_setup(const fx3d_lattice* lat, uint32_t axis, uint64_t t, Lattice& L, dim3& g, dim3& b) {
 	if(!make_lattice(lat, t, 0.0f, 0.0f, 0.0f, L)) return false;
 	if(axis>2u) { set_error("axis must be 0, 1 or 2"); return false; }

@@ -1238,6 +1238,112 @@ __global__ void __launch_bounds__(128) k_update_fields(const Lattice L, const Re
 }
 
 // ================================================================================================================
+// voxelize_mesh / unvoxelize_mesh, src/kernel.cpp:2267-2357: one thread per cell of the face normal to
+// `direction` casts a ray through its column, intersects it with every triangle (bidirectional Moeller-Trumbore, the reference's
+// operation order: the flags must come out identical), sorts the hit distances and walks the column toggling inside/outside.
+// The triangles are staged through shared memory a chunk at a time -- every thread of the block reads the same triangle at the
+// same moment -- together with the two edge vectors p1-p0 and p2-p0, which do not depend on the thread.
+// ================================================================================================================
+struct Float3 { float x, y, z; };
+FX3D_HD Float3 f3(float x, float y, float z) { return Float3{ x, y, z }; }
+FX3D_HD Float3 operator+(Float3 a, Float3 b) { return Float3{ a.x+b.x, a.y+b.y, a.z+b.z }; }
+FX3D_HD Float3 operator-(Float3 a, Float3 b) { return Float3{ a.x-b.x, a.y-b.y, a.z-b.z }; }
+FX3D_HD Float3 cross3(Float3 a, Float3 b) { return Float3{ a.y*b.z-a.z*b.y, a.z*b.x-a.x*b.z, a.x*b.y-a.y*b.x }; }
+FX3D_HD float dot3(Float3 a, Float3 b) { return a.x*b.x+a.y*b.y+a.z*b.z; }
+FX3D_HD Float3 cell_position(const Lattice& L, uint32_t x, uint32_t y, uint32_t z) { return f3((float)x+0.5f-0.5f*(float)L.Nx, (float)y+0.5f-0.5f*(float)L.Ny, (float)z+0.5f-0.5f*(float)L.Nz); } // :828-830
+FX3D_HD int clamp_int(int v, int lo, int hi) { return v<lo ? lo : v>hi ? hi : v; }
+struct VoxelizeArgs { // the 16-float block of LBM_Domain::voxelize_mesh_on_device (src/lbm.cpp:279-296) and the domain offset (def_Ox.., src/lbm.cpp:335)
+	uint32_t triangle_number; float x0, y0, z0, x1, y1, z1, cx, cy, cz, ux, uy, uz, rx, ry, rz; int Ox, Oy, Oz;
+};
+constexpr uint32_t VOX_CHUNK = 128u; // triangles staged per pass: 128 x 9 floats x 4 B x (vertices + edges) = 9 KB
+template<int Q, int ST>
+__global__ void __launch_bounds__(128) k_voxelize_mesh(const Lattice L, const uint32_t direction, const uint32_t t_odd, const uint8_t flag, const float* p0, const float* p1, const float* p2, const VoxelizeArgs V) {
+	typedef Codec<ST> C;
+	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x, A = direction==0u ? L.Ny*L.Nz : direction==1u ? L.Nz*L.Nx : L.Nx*L.Ny;
+	float* const tri = reinterpret_cast<float*>(dynamic_smem()); // [VOX_CHUNK][p0 | p1-p0 | p2-p0]
+	const uint32_t hmin = direction==0u ? (uint32_t)clamp_int((int)V.x0-V.Ox, 0, (int)L.Nx-1) : direction==1u ? (uint32_t)clamp_int((int)V.y0-V.Oy, 0, (int)L.Ny-1) : (uint32_t)clamp_int((int)V.z0-V.Oz, 0, (int)L.Nz-1);
+	const uint32_t hmax = direction==0u ? (uint32_t)clamp_int((int)V.x1-V.Ox, 0, (int)L.Nx-1) : direction==1u ? (uint32_t)clamp_int((int)V.y1-V.Oy, 0, (int)L.Ny-1) : (uint32_t)clamp_int((int)V.z1-V.Oz, 0, (int)L.Nz-1);
+	const uint32_t ac = a<A ? a : A-1u; // threads past the face keep the block's staging loop company
+	uint32_t X, Y, Z;
+	if(direction==0u) { X = hmin; Y = ac%L.Ny; Z = ac/L.Ny; } else if(direction==1u) { X = ac/L.Nz; Y = hmin; Z = ac%L.Nz; } else { X = ac%L.Nx; Y = ac/L.Nx; Z = hmin; }
+	const Float3 offset = f3(0.5f*(float)((int)L.Nx+2*V.Ox)-0.5f, 0.5f*(float)((int)L.Ny+2*V.Oy)-0.5f, 0.5f*(float)((int)L.Nz+2*V.Oz)-0.5f);
+	const Float3 r_origin = cell_position(L, X, Y, Z)+offset;
+	const Float3 r_direction = f3((float)(direction==0u), (float)(direction==1u), (float)(direction==2u));
+	const bool outside_box = direction==0u ? (r_origin.y<V.y0||r_origin.z<V.z0||r_origin.y>=V.y1||r_origin.z>=V.z1) : direction==1u ? (r_origin.x<V.x0||r_origin.z<V.z0||r_origin.x>=V.x1||r_origin.z>=V.z1) : (r_origin.x<V.x0||r_origin.y<V.y0||r_origin.x>=V.x1||r_origin.y>=V.y1);
+	const bool active = a<A && !outside_box;
+	uint32_t intersections = 0u, intersections_check = 0u;
+	uint16_t distances[64]; // up to 64 mesh intersections per column, as in the reference
+	for(uint32_t base=0u; base<V.triangle_number; base+=VOX_CHUNK) {
+		const uint32_t count = V.triangle_number-base<VOX_CHUNK ? V.triangle_number-base : VOX_CHUNK;
+		__syncthreads();
+		for(uint32_t k=threadIdx.x; k<count; k+=blockDim.x) {
+			const uint32_t i = 3u*(base+k);
+			const Float3 a0 = f3(p0[i], p0[i+1u], p0[i+2u]), eu = f3(p1[i], p1[i+1u], p1[i+2u])-a0, ev = f3(p2[i], p2[i+1u], p2[i+2u])-a0;
+			float* q = tri+9u*k;
+			q[0] = a0.x; q[1] = a0.y; q[2] = a0.z; q[3] = eu.x; q[4] = eu.y; q[5] = eu.z; q[6] = ev.x; q[7] = ev.y; q[8] = ev.z;
+		}
+		__syncthreads();
+		if(active) for(uint32_t k=0u; k<count; k++) {
+			const float* q = tri+9u*k;
+			const Float3 p0i = f3(q[0], q[1], q[2]), eu = f3(q[3], q[4], q[5]), ev = f3(q[6], q[7], q[8]);
+			const Float3 w = r_origin-p0i, h = cross3(r_direction, ev), qq = cross3(w, eu);
+			const float g = dot3(eu, h), f = 1.0f/g, s = f*dot3(w, h), tt = f*dot3(r_direction, qq), d = f*dot3(ev, qq);
+			if(g!=0.0f&&s>=0.0f&&s<1.0f&&tt>=0.0f&&s+tt<1.0f) {
+				if(d>0.0f) { if(intersections<64u&&d<65536.0f) distances[intersections] = (uint16_t)d; intersections++; }
+				else intersections_check++;
+			}
+		}
+	}
+	if(!active) return;
+	for(uint32_t i=1u; i<(intersections<64u ? intersections : 64u); i++) { // insertion sort
+		const uint16_t tv = distances[i];
+		uint32_t j = i;
+		while(j>0u&&distances[j-1u]>tv) { distances[j] = distances[j-1u]; j--; }
+		distances[j] = tv;
+	}
+	bool inside = (intersections%2u)&&(intersections_check%2u);
+	const bool set_u = V.ux*V.ux+V.uy*V.uy+V.uz*V.uz+V.rx*V.rx+V.ry*V.ry+V.rz*V.rz>0.0f;
+	uint32_t intersection = intersections%2u!=intersections_check%2u;
+	const uint32_t h0 = direction==0u ? X : direction==1u ? Y : Z;
+	const uint32_t hmesh = intersections>0u ? h0+(uint32_t)distances[intersections-1u<63u ? intersections-1u : 63u] : 0u; // unused without intersections: inside stays false
+	const uint64_t N = cells(L);
+	for(uint32_t hh=h0; hh<=hmax; hh++) {
+		while(intersection<intersections&&hh>h0+(uint32_t)distances[intersection<63u ? intersection : 63u]) { inside = !inside; intersection++; }
+		inside = inside&&(intersection<intersections&&hh<hmesh);
+		const uint32_t cx_ = direction==0u ? hh : X, cy_ = direction==1u ? hh : Y, cz_ = direction==2u ? hh : Z;
+		const uint64_t n = lin(L, cx_, cy_, cz_);
+		uint32_t flagsn = L.flags[n];
+		const Float3 p = cell_position(L, cx_, cy_, cz_)+offset;
+		const Float3 u_set = f3(V.ux, V.uy, V.uz)+cross3(f3(V.cx, V.cy, V.cz)-p, f3(V.rx, V.ry, V.rz));
+		if(inside) {
+			flagsn = (flagsn&~TYPE_BO)|flag;
+			if(set_u) { L.u[n] = u_set.x; L.u[N+n] = u_set.y; L.u[2ull*N+n] = u_set.z; }
+		} else if((flagsn&TYPE_BO)==TYPE_S&&(flagsn&0xC0u)==((uint32_t)flag&0xC0u)) { // the cell was solid, with the same TYPE_X/TYPE_Y marker
+			const float unx = L.u[n], uny = L.u[N+n], unz = L.u[2ull*N+n];
+			if(unx==u_set.x&&uny==u_set.y&&unz==u_set.z) { // it belonged to this geometry
+				if(set_u) { // a moving solid left the cell: its DDFs restart from equilibrium at rho=1 (no mass drift)
+					float feq[Q];
+					equilibrium<Q, float>(1.0f, unx, uny, unz, 1.0f, feq);
+					CellIO<Q, ST> io; io.locate(L, cx_, cy_, cz_);
+					io.push(L, t_odd, feq);
+				}
+				flagsn = (flagsn&TYPE_BO)==TYPE_MS ? flagsn&~TYPE_MS : flagsn&~(uint32_t)flag;
+			}
+		}
+		L.flags[n] = (uint8_t)flagsn;
+	}
+}
+#if defined(FX3D_TU_LBM)
+__global__ void __launch_bounds__(128) k_unvoxelize_mesh(const Lattice L, const uint8_t flag, const float x0, const float y0, const float z0, const float x1, const float y1, const float z1, const int Ox, const int Oy, const int Oz) { // :2351-2357
+	const uint64_t n = (uint64_t)blockIdx.x*blockDim.x+threadIdx.x;
+	if(n>=cells(L)) return;
+	const uint64_t plane = (uint64_t)L.Nx*L.Ny, r = n%plane;
+	const Float3 p = cell_position(L, (uint32_t)(r%L.Nx), (uint32_t)(r/L.Nx), (uint32_t)(n/plane))+f3(0.5f*(float)((int)L.Nx+2*Ox)-0.5f, 0.5f*(float)((int)L.Ny+2*Oy)-0.5f, 0.5f*(float)((int)L.Nz+2*Oz)-0.5f);
+	if(p.x>=x0-1.0f&&p.y>=y0-1.0f&&p.z>=z0-1.0f&&p.x<=x1+1.0f&&p.y<=y1+1.0f&&p.z<=z1+1.0f) L.flags[n] &= (uint8_t)~flag;
+}
+#endif
+
+// ================================================================================================================
 // halo transfer. Direction lists per face side (position b pairs opposite directions on the two sides),
 // src/kernel.cpp:2069-2101; face-cell decomposition of a per axis :2053-2068.
 // ================================================================================================================

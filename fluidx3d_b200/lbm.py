@@ -494,6 +494,42 @@ class LBM:
         if self.get_D() > 1: self.communicate_rho_u_flags()  # the reference exchanges the flags alone; rho and u halos are unchanged copies
         for _, dom in self.local_domains(): dom.finish_queue()
 
+    # ---- GPU voxeliser, src/lbm.cpp:1074-1145 ----
+    def voxelize_mesh_on_device(self, mesh, flag=TYPE_S, rotation_center=None, linear_velocity=(0.0, 0.0, 0.0), rotational_velocity=(0.0, 0.0, 0.0)):
+        """mark the cells inside the closed triangle mesh with `flag` on every domain (kernel voxelize_mesh, src/kernel.cpp:2267-2345)"""
+        from .mesh import voxelize_parameters
+        bbu, direction = voxelize_parameters(mesh, mesh.center if rotation_center is None else rotation_center, linear_velocity, rotational_velocity)
+        nbytes = mesh.triangle_number * 12
+        for d, dom in self.local_domains():
+            bufs = []
+            for arr in (mesh.p0, mesh.p1, mesh.p2):
+                p = C.c_void_p(); self.lib.malloc(dom.device, nbytes, C.byref(p))
+                self.lib.memcpy_h2d(dom.device, p, arr.ctypes.data, nbytes, dom.stream, 1)
+                bufs.append(p)
+            self.lib.voxelize_mesh(C.byref(dom.lat), dom.Ox, dom.Oy, dom.Oz, direction, dom.t + 1, flag, bufs[0], bufs[1], bufs[2], bbu.ctypes.data, dom.stream)
+            dom.finish_queue()
+            for p in bufs: self.lib.free(dom.device, p)
+        moving = any(v != 0.0 for v in linear_velocity) or any(v != 0.0 for v in rotational_velocity)
+        if (self.features & MOVING_BOUNDARIES) and (flag & (TYPE_S | TYPE_E)) == TYPE_S and moving: self.update_moving_boundaries()
+        if not self.initialized and self.host_fields:  # the host copies follow, so that initialize() does not overwrite the result
+            self.flags.read_from_device(); self.u.read_from_device()
+
+    def unvoxelize_mesh_on_device(self, mesh, flag=TYPE_S):
+        """clear `flag` in the bounding box of the mesh (only needed when the box changes size between re-voxelisations), src/lbm.cpp:1090-1093"""
+        for _, dom in self.local_domains():
+            self.lib.unvoxelize_mesh(C.byref(dom.lat), dom.Ox, dom.Oy, dom.Oz, flag, *[C.c_float(float(v)) for v in (*mesh.pmin, *mesh.pmax)], dom.stream)
+        for _, dom in self.local_domains(): dom.finish_queue()
+
+    def voxelize_stl(self, path, center=None, rotation=None, size=0.0, flag=TYPE_S):
+        """read a binary .stl file, fit it into the box (size 0), scale its longest side to `size` cells (size > 0) or by -size, and voxelise it
+        (LBM::voxelize_stl, src/lbm.cpp:1130-1145; flags travel host -> device -> host around the kernel like there)"""
+        from .mesh import read_stl
+        mesh = read_stl(path, self.size(), self.center() if center is None else center, size, rotation)
+        self.flags.write_to_device()
+        self.voxelize_mesh_on_device(mesh, flag)
+        self.flags.read_from_device()
+        return mesh
+
     def reset(self): self.initialized = False
 
     # ---- getters, src/lbm.hpp:448-535 ----

@@ -135,6 +135,16 @@ int fx3d_set_interior_reserve(int blocks);
 int fx3d_stream_collide_launches(int kind, uint64_t* launches);
 int fx3d_launch_count(uint64_t* launches);                            /* kernels launched by this library so far */
 
+/* GPU voxeliser (kernel voxelize_mesh / unvoxelize_mesh, kernel.cpp:2267-2357; LBM_Domain::voxelize_mesh_on_device, lbm.cpp:275-327): marks the
+ * cells inside a closed triangle mesh with `flag` (and gives them the velocity of the moving/rotating body), unmarks cells the body has left.
+ * p0,p1,p2: device buffers, 3 floats per triangle; bbu: HOST array of 16 floats laid out like the reference's bounding_box_and_velocity
+ * (triangle count as raw bits, bounding box min-2/max+2, rotation centre, linear velocity, rotational velocity); Ox,Oy,Oz: offset of this
+ * domain in the global grid (x*Nx/Dx-Hx, lbm.cpp:733); direction: axis the rays are cast along; t: the step the restarted DDFs are laid out for
+ * (the reference passes t+1). */
+int fx3d_voxelize_mesh(const fx3d_lattice* lattice, int Ox, int Oy, int Oz, uint32_t direction, uint64_t t, uint8_t flag,
+	const float* p0, const float* p1, const float* p2, const float* bbu, fx3d_stream stream);
+int fx3d_unvoxelize_mesh(const fx3d_lattice* lattice, int Ox, int Oy, int Oz, uint8_t flag, float x0, float y0, float z0, float x1, float y1, float z1, fx3d_stream stream);
+
 /* halo transfer through linear buffers, layout and semantics of transfer_extract_fi / transfer__insert_fi and
  * transfer_*_rho_u_flags (kernel.cpp:2049-2158, lbm.cpp:1308-1354). axis: 0 x, 1 y, 2 z. Buffers are device memory of
  * fx3d_transfer_bytes() each. */

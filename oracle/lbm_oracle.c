@@ -485,3 +485,105 @@ void orc_transfer_insert_rho_u_flags(const orc_grid* g, uint32_t axis, uint64_t 
 		insert_ruf(a, A, face_cell(g, axis, a, 0u   ), N, buf_m, rho, u, flags);
 	}
 }
+
+
+/* ================================================================================================================
+ * voxelize_mesh / unvoxelize_mesh -- src/kernel.cpp:2267-2357. One work item per cell of the face normal to
+ * `direction` casts a ray along the axis through the column, intersects it with every triangle (bidirectional Moeller-Trumbore),
+ * sorts the hit distances and walks the column toggling inside/outside. cross() and dot() are the plain expressions
+ * (a.y*b.z-a.z*b.y, ...; a.x*b.x+a.y*b.y+a.z*b.z, left to right), every operation separately rounded.
+ * Ox,Oy,Oz: offset of this domain in the global grid (def_Ox.., src/lbm.cpp:335); bbu: the 16 floats of
+ * LBM_Domain::voxelize_mesh_on_device (src/lbm.cpp:279-296): triangle count (as bits), bounding box, rotation centre, linear and
+ * rotational velocity.
+ * ================================================================================================================ */
+typedef struct { float x, y, z; } f3_t;
+static inline f3_t f3(float x, float y, float z) { f3_t r = { x, y, z }; return r; }
+static inline f3_t f3_sub(f3_t a, f3_t b) { return f3(a.x-b.x, a.y-b.y, a.z-b.z); }
+static inline f3_t f3_add(f3_t a, f3_t b) { return f3(a.x+b.x, a.y+b.y, a.z+b.z); }
+static inline f3_t f3_cross(f3_t a, f3_t b) { return f3(a.y*b.z-a.z*b.y, a.z*b.x-a.x*b.z, a.x*b.y-a.y*b.x); }
+static inline float f3_dot(f3_t a, f3_t b) { return a.x*b.x+a.y*b.y+a.z*b.z; }
+static inline int clampi(int v, int lo, int hi) { return v<lo ? lo : v>hi ? hi : v; }
+static inline f3_t position_of(const orc_grid* g, uint32_t x, uint32_t y, uint32_t z) { /* src/kernel.cpp:828-830 */
+	return f3((float)x+0.5f-0.5f*(float)g->Nx, (float)y+0.5f-0.5f*(float)g->Ny, (float)z+0.5f-0.5f*(float)g->Nz);
+}
+void orc_voxelize_mesh(const orc_grid* g, int Ox, int Oy, int Oz, uint32_t direction, void* fi, float* u, uint8_t* flags, uint64_t t, uint8_t flag,
+	const float* p0, const float* p1, const float* p2, const float* bbu) {
+	const uint64_t A = orc_area(g, direction), N = cells_of(g);
+	const uint32_t triangle_number = bits_of(bbu[0]);
+	const float x0 = bbu[1], y0 = bbu[2], z0 = bbu[3], x1 = bbu[4], y1 = bbu[5], z1 = bbu[6];
+	const float cx = bbu[7], cy = bbu[8], cz = bbu[9], ux = bbu[10], uy = bbu[11], uz = bbu[12], rx = bbu[13], ry = bbu[14], rz = bbu[15];
+	const f3_t offset = f3(0.5f*(float)((int)g->Nx+2*Ox)-0.5f, 0.5f*(float)((int)g->Ny+2*Oy)-0.5f, 0.5f*(float)((int)g->Nz+2*Oz)-0.5f);
+	ORC_PARALLEL_FOR
+	for(uint64_t a=0u; a<A; a++) {
+		const uint32_t hmin = direction==0u ? (uint32_t)clampi((int)x0-Ox, 0, (int)g->Nx-1) : direction==1u ? (uint32_t)clampi((int)y0-Oy, 0, (int)g->Ny-1) : (uint32_t)clampi((int)z0-Oz, 0, (int)g->Nz-1);
+		const uint32_t hmax = direction==0u ? (uint32_t)clampi((int)x1-Ox, 0, (int)g->Nx-1) : direction==1u ? (uint32_t)clampi((int)y1-Oy, 0, (int)g->Ny-1) : (uint32_t)clampi((int)z1-Oz, 0, (int)g->Nz-1);
+		uint32_t X, Y, Z;
+		if(direction==0u) { X = hmin; Y = (uint32_t)(a%g->Ny); Z = (uint32_t)(a/g->Ny); }
+		else if(direction==1u) { X = (uint32_t)(a/g->Nz); Y = hmin; Z = (uint32_t)(a%g->Nz); }
+		else { X = (uint32_t)(a%g->Nx); Y = (uint32_t)(a/g->Nx); Z = hmin; }
+		const f3_t r_origin = f3_add(position_of(g, X, Y, Z), offset);
+		const f3_t r_direction = f3((float)(direction==0u), (float)(direction==1u), (float)(direction==2u));
+		uint32_t intersections = 0u, intersections_check = 0u;
+		uint16_t distances[64];
+		const int outside_box = direction==0u ? (r_origin.y<y0||r_origin.z<z0||r_origin.y>=y1||r_origin.z>=z1) : direction==1u ? (r_origin.x<x0||r_origin.z<z0||r_origin.x>=x1||r_origin.z>=z1) : (r_origin.x<x0||r_origin.y<y0||r_origin.x>=x1||r_origin.y>=y1);
+		if(outside_box) continue;
+		for(uint32_t i=0u; i<triangle_number; i++) {
+			const f3_t p0i = f3(p0[3u*i], p0[3u*i+1u], p0[3u*i+2u]), p1i = f3(p1[3u*i], p1[3u*i+1u], p1[3u*i+2u]), p2i = f3(p2[3u*i], p2[3u*i+1u], p2[3u*i+2u]);
+			const f3_t eu = f3_sub(p1i, p0i), ev = f3_sub(p2i, p0i), ew = f3_sub(r_origin, p0i), h = f3_cross(r_direction, ev), q = f3_cross(ew, eu);
+			const float gdet = f3_dot(eu, h), f = 1.0f/gdet, s = f*f3_dot(ew, h), tt = f*f3_dot(r_direction, q), d = f*f3_dot(ev, q);
+			if(gdet!=0.0f&&s>=0.0f&&s<1.0f&&tt>=0.0f&&s+tt<1.0f) {
+				if(d>0.0f) {
+					if(intersections<64u&&d<65536.0f) distances[intersections] = (uint16_t)d;
+					intersections++;
+				} else intersections_check++;
+			}
+		}
+		for(uint32_t i=1u; i<(intersections<64u ? intersections : 64u); i++) { /* insertion sort */
+			const uint16_t tv = distances[i];
+			uint32_t j = i;
+			while(j>0u&&distances[j-1u]>tv) { distances[j] = distances[j-1u]; j--; }
+			distances[j] = tv;
+		}
+		int inside = (intersections%2u)&&(intersections_check%2u);
+		const int set_u = ux*ux+uy*uy+uz*uz+rx*rx+ry*ry+rz*rz>0.0f;
+		uint32_t intersection = intersections%2u!=intersections_check%2u;
+		const uint32_t h0 = direction==0u ? X : direction==1u ? Y : Z;
+		const uint32_t last = intersections-1u<63u ? intersections-1u : 63u; /* min(intersections-1u, 63u) with unsigned wrap for 0 */
+		const uint32_t hmesh = h0+(uint32_t)(intersections>0u ? distances[last] : distances[63]); /* (value unused when there are no intersections: inside stays 0) */
+		for(uint32_t hh=h0; hh<=hmax; hh++) {
+			while(intersection<intersections&&hh>h0+(uint32_t)distances[intersection<63u ? intersection : 63u]) { inside = !inside; intersection++; }
+			inside = inside&&(intersection<intersections&&hh<hmesh);
+			const uint64_t n = index_of(g, direction==0u ? hh : X, direction==1u ? hh : Y, direction==2u ? hh : Z);
+			uint8_t flagsn = flags[n];
+			const xyz_t c = coords_of(g, n);
+			const f3_t p = f3_add(position_of(g, c.x, c.y, c.z), offset);
+			const f3_t u_set = f3_add(f3(ux, uy, uz), f3_cross(f3_sub(f3(cx, cy, cz), p), f3(rx, ry, rz)));
+			if(inside) {
+				flagsn = (uint8_t)((flagsn&~TYPE_BO)|flag);
+				if(set_u) { u[n] = u_set.x; u[N+n] = u_set.y; u[2u*N+n] = u_set.z; }
+			} else if((flagsn&TYPE_BO)==TYPE_S&&(flagsn&0xC0u)==(flag&0xC0u)) { /* TYPE_XY = TYPE_X|TYPE_Y */
+				const float unx = u[n], uny = u[N+n], unz = u[2u*N+n];
+				if(unx==u_set.x&&uny==u_set.y&&unz==u_set.z) {
+					if(set_u) { /* the solid cell becomes fluid again: its DDFs restart from equilibrium at rho=1 */
+						uint64_t j[QMAX]; float feq[QMAX];
+						neighbours_of(g, n, j);
+						equilibrium(g, 1.0f, unx, uny, unz, feq);
+						push_ddfs(g, n, feq, fi, j, t);
+					}
+					flagsn = (flagsn&TYPE_BO)==TYPE_MS ? (uint8_t)(flagsn&~TYPE_MS) : (uint8_t)(flagsn&~flag);
+				}
+			}
+			flags[n] = flagsn;
+		}
+	}
+}
+void orc_unvoxelize_mesh(const orc_grid* g, int Ox, int Oy, int Oz, uint8_t* flags, uint8_t flag, float x0, float y0, float z0, float x1, float y1, float z1) { /* :2351-2357 */
+	const uint64_t N = cells_of(g);
+	const f3_t offset = f3(0.5f*(float)((int)g->Nx+2*Ox)-0.5f, 0.5f*(float)((int)g->Ny+2*Oy)-0.5f, 0.5f*(float)((int)g->Nz+2*Oz)-0.5f);
+	ORC_PARALLEL_FOR
+	for(uint64_t n=0u; n<N; n++) {
+		const xyz_t c = coords_of(g, n);
+		const f3_t p = f3_add(position_of(g, c.x, c.y, c.z), offset);
+		if(p.x>=x0-1.0f&&p.y>=y0-1.0f&&p.z>=z0-1.0f&&p.x<=x1+1.0f&&p.y<=y1+1.0f&&p.z<=z1+1.0f) flags[n] &= (uint8_t)~flag;
+	}
+}

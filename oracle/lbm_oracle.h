@@ -62,6 +62,12 @@ void orc_transfer_insert_fi(const orc_grid* g, uint32_t axis, uint64_t t, const 
 void orc_transfer_extract_rho_u_flags(const orc_grid* g, uint32_t axis, uint64_t t, void* buf_p, void* buf_m, const float* rho, const float* u, const uint8_t* flags);
 void orc_transfer_insert_rho_u_flags(const orc_grid* g, uint32_t axis, uint64_t t, const void* buf_p, const void* buf_m, float* rho, float* u, uint8_t* flags);
 
+/* GPU voxeliser: src/kernel.cpp:2267-2357; Ox,Oy,Oz = offset of the domain in the global grid; p0,p1,p2 = 3 floats per
+ * triangle; bbu = the 16-float parameter block of LBM_Domain::voxelize_mesh_on_device (src/lbm.cpp:279-296) */
+void orc_voxelize_mesh(const orc_grid* g, int Ox, int Oy, int Oz, uint32_t direction, void* fi, float* u, uint8_t* flags, uint64_t t, uint8_t flag,
+	const float* p0, const float* p1, const float* p2, const float* bbu);
+void orc_unvoxelize_mesh(const orc_grid* g, int Ox, int Oy, int Oz, uint8_t* flags, uint8_t flag, float x0, float y0, float z0, float x1, float y1, float z1);
+
 void orc_set_threads(int n); /* OpenMP threads used by the kernels above (0 = library default) */
 int  orc_get_threads(void);
 

@@ -36,6 +36,7 @@ WANTED = [
     "get_area", "index_extract_p", "index_extract_m", "index_insert_p", "index_insert_m", "index_transfer",
     "extract_fi", "insert_fi", "transfer_extract_fi", "transfer__insert_fi",
     "extract_rho_u_flags", "insert_rho_u_flags", "transfer_extract_rho_u_flags", "transfer__insert_rho_u_flags",
+    "position", "voxelize_mesh", "unvoxelize_mesh",
 ]
 
 
@@ -43,7 +44,7 @@ def prologue(q, coll, storage, mask):
     transfers = 5 if q == 19 else 9
     d = [
         "#define def_Nx g_Nx", "#define def_Ny g_Ny", "#define def_Nz g_Nz", "#define def_N g_N", "#define uxx uint",
-        "#define def_Dx g_Dx", "#define def_Dy g_Dy", "#define def_Dz g_Dz",
+        "#define def_Dx g_Dx", "#define def_Dy g_Dy", "#define def_Dz g_Dz", "#define def_Ox g_Ox", "#define def_Oy g_Oy", "#define def_Oz g_Oz",
         "#define def_Ax (g_Ny*g_Nz)", "#define def_Ay (g_Nz*g_Nx)", "#define def_Az (g_Nx*g_Ny)",
         f"#define D3Q{q}", f"#define def_velocity_set {q}u", "#define def_dimensions 3u", f"#define def_transfers {transfers}u",
         "#define def_c 0.57735027f", "#define def_w g_w",
@@ -113,6 +114,10 @@ void ref_transfer_insert_rho_u_flags(uint direction, ulong t, const void* bp, co
 #ifdef MOVING_BOUNDARIES
 void ref_update_moving_boundaries(const float* u, uchar* flags) { NDRANGE(g_N, update_moving_boundaries(u, flags)) }
 #endif
+void ref_set_offsets(int Ox, int Oy, int Oz) { g_Ox = Ox; g_Oy = Oy; g_Oz = Oz; }
+void ref_voxelize_mesh(uint direction, void* fi, float* u, uchar* flags, ulong t, uchar flag, const float* p0, const float* p1, const float* p2, const float* bbu) {
+	NDRANGE(get_area(direction), voxelize_mesh(direction, (fpxx*)fi, u, flags, t, flag, p0, p1, p2, bbu)) }
+void ref_unvoxelize_mesh(uchar* flags, uchar flag, float x0, float y0, float z0, float x1, float y1, float z1) { NDRANGE(g_N, unvoxelize_mesh(flags, flag, x0, y0, z0, x1, y1, z1)) }
 ushort ref_float_to_half_custom(float x) { return float_to_half_custom(x); }
 float ref_half_to_float_custom(ushort x) { return half_to_float_custom(x); }
 }

@@ -24,6 +24,15 @@ struct float3 { float x, y, z; };
 static inline uint3 make_uint3(uint x, uint y, uint z) { return uint3{ x, y, z }; }
 static inline float3 make_float3(float x, float y, float z) { return float3{ x, y, z }; }
 
+// float3 arithmetic of the voxeliser (src/kernel.cpp:2267-2357): component-wise, every operation separately rounded; cross() and dot() as the
+// plain expressions (the same ones the reference's host-side float3 uses, src/utilities.hpp:1020-1025)
+static inline float3 operator+(const float3 a, const float3 b) { return float3{ a.x+b.x, a.y+b.y, a.z+b.z }; }
+static inline float3 operator-(const float3 a, const float3 b) { return float3{ a.x-b.x, a.y-b.y, a.z-b.z }; }
+static inline float3 cross(const float3 a, const float3 b) { return float3{ a.y*b.z-a.z*b.y, a.z*b.x-a.x*b.z, a.x*b.y-a.y*b.x }; }
+static inline float dot(const float3 a, const float3 b) { return a.x*b.x+a.y*b.y+a.z*b.z; }
+static inline int clamp(const int x, const int lo, const int hi) { return x<lo ? lo : x>hi ? hi : x; }
+static inline uint min(const uint a, const uint b) { return a<b ? a : b; }
+
 static inline uint as_uint(const float x) { uint u; std::memcpy(&u, &x, 4); return u; }
 static inline float as_float(const uint u) { float x; std::memcpy(&x, &u, 4); return x; }
 static inline float fma(const float a, const float b, const float c) { return __builtin_fmaf(a, b, c); }
@@ -34,6 +43,7 @@ static inline void vstore_half_rte(const float x, const ulong offset, half* p) {
 
 // run-time stand-ins for the constants LBM_Domain::device_defines() bakes into the JIT source (src/lbm.cpp:334-425)
 static uint g_Nx=1u, g_Ny=1u, g_Nz=1u, g_Dx=1u, g_Dy=1u, g_Dz=1u;
+static int g_Ox=0, g_Oy=0, g_Oz=0; // def_Ox.. : offset of the domain in the global grid
 static ulong g_N=1ul;
 static float g_w=1.0f;
 static thread_local ulong g_gid=0ul;

@@ -79,6 +79,9 @@ class OracleBackend:
     def update_moving_boundaries(self, u, flags):
         self.lib.orc_update_moving_boundaries(C.byref(self.g), _p(u), _p(flags))
 
+    def voxelize_mesh(self, offsets, direction, fi, u, flags, t, flag, p0, p1, p2, bbu):
+        self.lib.orc_voxelize_mesh(C.byref(self.g), C.c_int(offsets[0]), C.c_int(offsets[1]), C.c_int(offsets[2]), C.c_uint32(direction), _p(fi), _p(u), _p(flags), C.c_uint64(t), C.c_uint8(flag), _p(p0), _p(p1), _p(p2), _p(bbu))
+
     def extract_fi(self, axis, t, bp, bm, fi):
         self.lib.orc_transfer_extract_fi(C.byref(self.g), C.c_uint32(axis), C.c_uint64(t), _p(bp), _p(bm), _p(fi))
 
@@ -129,6 +132,10 @@ class RefBackend:
 
     def update_moving_boundaries(self, u, flags):
         self.lib.ref_update_moving_boundaries(_p(u), _p(flags))
+
+    def voxelize_mesh(self, offsets, direction, fi, u, flags, t, flag, p0, p1, p2, bbu):
+        self.lib.ref_set_offsets(C.c_int(offsets[0]), C.c_int(offsets[1]), C.c_int(offsets[2]))
+        self.lib.ref_voxelize_mesh(C.c_uint32(direction), _p(fi), _p(u), _p(flags), C.c_uint64(t), C.c_uint8(flag), _p(p0), _p(p1), _p(p2), _p(bbu))
 
     def extract_fi(self, axis, t, bp, bm, fi):
         self.lib.ref_transfer_extract_fi(C.c_uint32(axis), C.c_uint64(t), _p(bp), _p(bm), _p(fi))
@@ -251,6 +258,18 @@ class HostSim:
             self.b.update_moving_boundaries(d.u, d.flags)
         self._communicate("ruf")
 
+    def voxelize_mesh(self, mesh, flag=TYPE_S, rotation_center=None, linear_velocity=(0.0, 0.0, 0.0), rotational_velocity=(0.0, 0.0, 0.0)):
+        """LBM::voxelize_mesh_on_device (src/lbm.cpp:1074-1089) over LBM_Domain::voxelize_mesh_on_device (:275-322) on every domain"""
+        bbu, direction = voxelize_parameters(mesh, rotation_center if rotation_center is not None else mesh.center, linear_velocity, rotational_velocity)
+        nx, ny, nz = self.Nx // self.Dx, self.Ny // self.Dy, self.Nz // self.Dz
+        for d in range(self.D):
+            x, y, z = (d % (self.Dx * self.Dy)) % self.Dx, (d % (self.Dx * self.Dy)) // self.Dx, d // (self.Dx * self.Dy)
+            off = (x * nx - self.Hx, y * ny - self.Hy, z * nz - self.Hz)  # src/lbm.cpp:733
+            dom = self.dom[d]
+            self.b.voxelize_mesh(off, direction, dom.fi, dom.u, dom.flags, self.t + 1, flag, mesh.p0, mesh.p1, mesh.p2, bbu)
+        if (self.b.features & MOVING_BOUNDARIES) and (flag & (TYPE_S | TYPE_E)) == TYPE_S and (any(v != 0.0 for v in linear_velocity) or any(v != 0.0 for v in rotational_velocity)):
+            self.update_moving_boundaries()
+
     def update_fields(self):  # src/lbm.cpp:977-980
         for d in self.dom:
             self.b.update_fields(d.fi, d.rho, d.u, d.flags, self.t, *self.f)
@@ -289,3 +308,88 @@ def load_scenario(sim, rho, u, flags):
     for a in range(3):
         sim.set_global("u", u[a], a)
     sim.set_global("flags", flags)
+
+
+# ---- triangle meshes: binary STL (src/utilities.hpp:4530-4581) and the parameter block of the voxeliser (src/lbm.cpp:275-322) ----
+class Mesh:
+    """p0, p1, p2: float32 arrays (triangles, 3), C-contiguous; center, pmin, pmax: float32[3] (src/utilities.hpp:4425-4528)"""
+
+    def __init__(self, p0, p1, p2, center):
+        self.p0, self.p1, self.p2 = (np.ascontiguousarray(a, dtype=np.float32) for a in (p0, p1, p2))
+        self.center = np.asarray(center, dtype=np.float32)
+        self.find_bounds()
+
+    @property
+    def triangle_number(self): return self.p0.shape[0]
+
+    def find_bounds(self):
+        allp = np.concatenate([self.p0, self.p1, self.p2])
+        self.pmin, self.pmax = allp.min(axis=0), allp.max(axis=0)
+
+
+def read_stl(path, box_size, center, size, rotation=None, reposition=True):
+    """read_stl_raw, src/utilities.hpp:4530-4571: all arithmetic in binary32 in the reference's order center+scale*(offset+p)"""
+    raw = open(path, "rb").read()
+    n = int(np.frombuffer(raw, np.uint32, 1, 80)[0])
+    assert n > 0 and len(raw) == 84 + 50 * n, "corrupt or non-binary STL"
+    rec = np.frombuffer(raw, np.uint8, 50 * n, 84).reshape(n, 50)[:, :48].copy().view(np.float32).reshape(n, 12)
+    p = [rec[:, 3:6].copy(), rec[:, 6:9].copy(), rec[:, 9:12].copy()]
+    if rotation is not None:
+        R = np.asarray(rotation, dtype=np.float32)
+        p = [np.stack([(R[r, 0] * a[:, 0] + R[r, 1] * a[:, 1] + R[r, 2] * a[:, 2]).astype(np.float32) for r in range(3)], axis=1) for a in p]
+    m = Mesh(*p, center)
+    f32 = np.float32
+    ext = (m.pmax - m.pmin).astype(f32)
+    box = np.asarray(box_size, dtype=f32)
+    if size == 0.0: scale = f32(min(box[0] / ext[0], box[1] / ext[1], box[2] / ext[2]))
+    elif size > 0.0: scale = f32(f32(size) / max(ext))
+    else: scale = f32(-size)
+    offset = (f32(-0.5) * (m.pmin + m.pmax)).astype(f32) if reposition else np.zeros(3, f32)
+    c = np.asarray(center, dtype=f32)
+    out = [(c + scale * (offset + a)).astype(f32) for a in p]
+    return Mesh(*out, c)
+
+
+def write_stl(path, p0, p1, p2):
+    n = p0.shape[0]
+    rec = np.zeros((n, 50), np.uint8)
+    body = np.zeros((n, 12), np.float32)
+    body[:, 3:6], body[:, 6:9], body[:, 9:12] = p0, p1, p2
+    rec[:, :48] = body.view(np.uint8).reshape(n, 48)
+    with open(path, "wb") as f:
+        f.write(b"fx3d test mesh".ljust(80, b" ")); f.write(np.uint32(n).tobytes()); f.write(rec.tobytes())
+
+
+def voxelize_parameters(mesh, rotation_center, linear_velocity, rotational_velocity):
+    """the 16-float block and the ray direction LBM_Domain::voxelize_mesh_on_device chooses (src/lbm.cpp:279-321)"""
+    f32 = np.float32
+    bbu = np.zeros(16, f32)
+    bbu[0] = np.array([mesh.triangle_number], np.uint32).view(f32)[0]
+    bbu[1:4] = mesh.pmin - f32(2.0); bbu[4:7] = mesh.pmax + f32(2.0)
+    bbu[7:10] = np.asarray(rotation_center, f32); bbu[10:13] = np.asarray(linear_velocity, f32); bbu[13:16] = np.asarray(rotational_velocity, f32)
+    x0, y0, z0, x1, y1, z1 = bbu[1:7]
+    rot = bbu[13:16]
+    if float(np.sqrt(f32(rot[0] * rot[0] + rot[1] * rot[1] + rot[2] * rot[2]))) == 0.0:  # direction of the smallest bounding-box cross-section
+        v = [f32((y1 - y0) * (z1 - z0)), f32((z1 - z0) * (x1 - x0)), f32((x1 - x0) * (y1 - y0))]
+        direction = 0
+        for i in (1, 2):
+            if v[i] < v[direction]: direction = i
+    else:  # direction closest to the rotation axis
+        v = [abs(float(r)) for r in rot]
+        direction = 0
+        for i in (1, 2):
+            if v[i] > v[direction]: direction = i
+    return bbu, direction
+
+
+def torus_mesh(R=1.0, r=0.4, nu=24, nv=12):
+    """a closed, non-convex test surface: torus around the z axis, nu x nv quads split into triangles"""
+    a = np.linspace(0, 2 * np.pi, nu, endpoint=False); b = np.linspace(0, 2 * np.pi, nv, endpoint=False)
+    A, B = np.meshgrid(a, b, indexing="ij")
+    P = np.stack([(R + r * np.cos(B)) * np.cos(A), (R + r * np.cos(B)) * np.sin(A), r * np.sin(B)], axis=-1).astype(np.float32)
+    p0, p1, p2 = [], [], []
+    for i in range(nu):
+        for j in range(nv):
+            q00, q10, q01, q11 = P[i, j], P[(i + 1) % nu, j], P[i, (j + 1) % nv], P[(i + 1) % nu, (j + 1) % nv]
+            p0 += [q00, q10]; p1 += [q10, q11]; p2 += [q01, q01]
+    return np.array(p0, np.float32), np.array(p1, np.float32), np.array(p2, np.float32)
