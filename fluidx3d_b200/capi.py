@@ -8,7 +8,7 @@ DEFAULT_LIB = os.environ.get("FX3D_LIB", os.path.join(HERE, "libfx3d_cuda.so")) 
 
 FP32, FP16S, FP16C = 0, 1, 2
 SRT, TRT = 0, 1
-VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID, MOVING_BOUNDARIES = 1, 2, 4, 8, 16
+VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID, MOVING_BOUNDARIES, FORCE_FIELD = 1, 2, 4, 8, 16, 32
 REGION_ALL, REGION_SHELL, REGION_INTERIOR = 0, 1, 2
 TYPE_S, TYPE_E = 0x01, 0x02  # src/defines.hpp:52-53
 OK, ERR_NO_DEVICE, ERR_INVALID, ERR_OUT_OF_MEMORY, ERR_CUDA, ERR_TIMEOUT = 0, -1, -2, -3, -4, -5
@@ -29,7 +29,7 @@ class Lattice(C.Structure):
     _fields_ = [("device", C.c_int), ("Nx", C.c_uint32), ("Ny", C.c_uint32), ("Nz", C.c_uint32),
                 ("Dx", C.c_uint32), ("Dy", C.c_uint32), ("Dz", C.c_uint32),
                 ("velocity_set", C.c_uint32), ("collision", C.c_uint32), ("storage", C.c_uint32), ("features", C.c_uint32),
-                ("w", C.c_float), ("fi", C.c_void_p), ("rho", C.c_void_p), ("u", C.c_void_p), ("flags", C.c_void_p)]
+                ("w", C.c_float), ("fi", C.c_void_p), ("rho", C.c_void_p), ("u", C.c_void_p), ("flags", C.c_void_p), ("F", C.c_void_p)]
 
 
 _VP, _U64, _U32, _F, _I, _SZ = C.c_void_p, C.c_uint64, C.c_uint32, C.c_float, C.c_int, C.c_size_t
@@ -72,6 +72,12 @@ _SIGS = {
     "fx3d_stream_collide_fused": (_I, [_LP, _U64, _F, _F, _F, C.POINTER(_VP), _VP], True),
     "fx3d_fused_halo_supported": (_I, [_LP], False),
     "fx3d_update_fields": (_I, [_LP, _U64, _F, _F, _F, _VP], True),
+    "fx3d_update_force_field": (_I, [_LP, _U64, _VP], True),
+    "fx3d_reset_force_field": (_I, [_LP, _VP], True),
+    "fx3d_object_scratch_bytes": (_SZ, [_LP], False),
+    "fx3d_object_center_of_mass": (_I, [_LP, C.c_uint8, _VP, _VP, _VP], True),
+    "fx3d_object_force": (_I, [_LP, C.c_uint8, _VP, _VP, _VP], True),
+    "fx3d_object_torque": (_I, [_LP, C.c_uint8, _F, _F, _F, _VP, _VP, _VP], True),
     "fx3d_voxelize_mesh": (_I, [_LP, _I, _I, _I, _U32, _U64, C.c_uint8, _VP, _VP, _VP, _VP, _VP], True),
     "fx3d_unvoxelize_mesh": (_I, [_LP, _I, _I, _I, C.c_uint8, _F, _F, _F, _F, _F, _F, _VP], True),
     "fx3d_run_steps": (_I, [_LP, _U64, _U64, _F, _F, _F, _VP], True),
@@ -82,6 +88,12 @@ _SIGS = {
     "fx3d_transfer_insert_fi": (_I, [_LP, _U32, _U64, _VP, _VP, _VP], True),
     "fx3d_transfer_extract_rho_u_flags": (_I, [_LP, _U32, _U64, _VP, _VP, _VP], True),
     "fx3d_transfer_insert_rho_u_flags": (_I, [_LP, _U32, _U64, _VP, _VP, _VP], True),
+    "fx3d_transfer_extract_flags": (_I, [_LP, _U32, _U64, _VP, _VP, _VP], True),
+    "fx3d_transfer_insert_flags": (_I, [_LP, _U32, _U64, _VP, _VP, _VP], True),
+    "fx3d_transfer_extract_F": (_I, [_LP, _U32, _U64, _VP, _VP, _VP], True),
+    "fx3d_transfer_insert_F": (_I, [_LP, _U32, _U64, _VP, _VP, _VP], True),
+    "fx3d_exchange_flags": (_I, [_LP, _U32, _VP, _VP, _VP], True),
+    "fx3d_exchange_F": (_I, [_LP, _U32, _VP, _VP, _VP], True),
     "fx3d_exchange_fi": (_I, [_LP, _U32, _U64, _VP, _VP, _VP], True),
     "fx3d_exchange_rho_u_flags": (_I, [_LP, _U32, _VP, _VP, _VP, _VP, _VP, _VP, _VP], True),
     "fx3d_rendezvous_signal": (_I, [_I, C.POINTER(_VP), _I, _I, _U64, _VP], True),

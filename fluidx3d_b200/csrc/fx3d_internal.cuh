@@ -49,6 +49,7 @@ inline bool make_lattice(const fx3d_lattice* in, uint64_t t, float fx, float fy,
 	L.eb = (in->features&FX3D_EQUILIBRIUM_BOUNDARIES) ? 1u : 0u;
 	L.upd = (in->features&FX3D_UPDATE_FIELDS) ? 1u : 0u;
 	L.mb = (in->features&FX3D_MOVING_BOUNDARIES) ? 1u : 0u;
+	L.F = (in->features&FX3D_FORCE_FIELD) ? in->F : nullptr; // entry points that dereference it check for null themselves (fx3d_fi_bytes etc. run before the buffers exist)
 	return true;
 }
 inline size_t elem_bytes(uint32_t storage) { return storage==FX3D_FP32 ? 4u : 2u; }

@@ -75,6 +75,13 @@ static int stream_collide_region(const fx3d_lattice* lat, const Lattice& L, cons
 		return rc;
 	};
 	const bool div4 = width%4u==0u && (c.x0-L.Hx)%4u==0u, div2 = width%2u==0u && (c.x0-L.Hx)%2u==0u;
+	const bool cell_force = (lat->features&FX3D_FORCE_FIELD) && vf; // FORCE_FIELD only enters stream_collide through the volume-force terms (kernel.cpp:1494-1503,1550-1563)
+	if(cell_force) { // per-cell force: the general kernel (one cell per thread) adds F[n] to (fx,fy,fz)
+		if(fused || query) return 1;
+		if(!L.F) { set_error("FORCE_FIELD lattice without a force field buffer (fx3d_lattice.F)"); return FX3D_ERR_INVALID; }
+		const int ext = ((lat->features&FX3D_SUBGRID) ? 1 : 0)|((lat->features&FX3D_MOVING_BOUNDARIES) ? 2 : 0);
+		return launch(1u, 1, ext ? ext : 4);
+	}
 	if(fused || query) { // fused y/z halo delivery exists in the whole-row bulk-copy kernel only (4 cells per thread)
 		if(!div4 || want==1 || want==2 || want==4 || want==8 || want==32) return 1;
 		const int ext = ((lat->features&FX3D_SUBGRID) ? 1 : 0)|((lat->features&FX3D_MOVING_BOUNDARIES) ? 2 : 0);
@@ -214,6 +221,7 @@ int fx3d_update_fields(const fx3d_lattice* lat, uint64_t t, float fx, float fy, 
 	if(int rc = use_device(lat->device)) return rc;
 	const Region R = all_cells(L);
 	const dim3 b = cell_block(R.g1-R.g0), g = cell_grid(R, b);
+	if((lat->features&FX3D_FORCE_FIELD) && (lat->features&FX3D_VOLUME_FORCE) && !L.F) { set_error("FORCE_FIELD lattice without a force field buffer (fx3d_lattice.F)"); return FX3D_ERR_INVALID; }
 	if(lat->features&FX3D_VOLUME_FORCE) { FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { FX3D_LAUNCH((k_update_fields<Q, ST, true>), g, b, stream, L, R); }) }
 	else { FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { FX3D_LAUNCH((k_update_fields<Q, ST, false>), g, b, stream, L, R); }) }
 	return check_launch("update_fields");
@@ -229,6 +237,52 @@ int fx3d_update_moving_boundaries(const fx3d_lattice* lat, fx3d_stream stream) {
 	if(lat->velocity_set==19u) FX3D_LAUNCH((k_update_moving_boundaries<19>), g, b, stream, L, R); else FX3D_LAUNCH((k_update_moving_boundaries<27>), g, b, stream, L, R);
 	return check_launch("update_moving_boundaries");
 }
+
+// ---- FORCE_FIELD ----
+static bool force_field_lattice(const fx3d_lattice* lat, uint64_t t, Lattice& L) {
+	if(!make_lattice(lat, t, 0.0f, 0.0f, 0.0f, L)) return false;
+	if(!(lat->features&FX3D_FORCE_FIELD)) { set_error("this call needs the FORCE_FIELD feature"); return false; }
+	if(!L.F) { set_error("FORCE_FIELD lattice without a force field buffer (fx3d_lattice.F)"); return false; }
+	return true;
+}
+int fx3d_update_force_field(const fx3d_lattice* lat, uint64_t t, fx3d_stream stream) {
+	Lattice L;
+	if(!force_field_lattice(lat, t, L)) return FX3D_ERR_INVALID;
+	if(int rc = use_device(lat->device)) return rc;
+	const Region R = all_cells(L);
+	const dim3 b = cell_block(R.g1-R.g0), g = cell_grid(R, b);
+	FX3D_DISPATCH_Q_ST(lat->velocity_set, lat->storage, { FX3D_LAUNCH((k_update_force_field<Q, ST>), g, b, stream, L, R); })
+	return check_launch("update_force_field");
+}
+int fx3d_reset_force_field(const fx3d_lattice* lat, fx3d_stream stream) { // kernel reset_force_field, kernel.cpp:1885-1889: halo included
+	Lattice L;
+	if(!force_field_lattice(lat, 0ull, L)) return FX3D_ERR_INVALID;
+	return fx3d_memset(lat->device, L.F, 0, (size_t)(3ull*(uint64_t)L.Nx*L.Ny*L.Nz*4ull), stream);
+}
+size_t fx3d_object_scratch_bytes(const fx3d_lattice* lat) {
+	if(!lat) return 0u;
+	const uint64_t N = (uint64_t)lat->Nx*lat->Ny*lat->Nz;
+	return (size_t)(((N+OBJECT_GROUP-1u)/OBJECT_GROUP)*sizeof(ObjectPartial));
+}
+static int object_sum_impl(const fx3d_lattice* lat, uint32_t kind, uint8_t flag_marker, float cx, float cy, float cz, float* object_sum, void* scratch, fx3d_stream stream) {
+	Lattice L;
+	if(!force_field_lattice(lat, 0ull, L)) return FX3D_ERR_INVALID;
+	if(!object_sum || !scratch) { set_error("object_sum / scratch buffer is null"); return FX3D_ERR_INVALID; }
+	if(int rc = use_device(lat->device)) return rc;
+	const uint64_t groups = ((uint64_t)L.Nx*L.Ny*L.Nz+OBJECT_GROUP-1u)/OBJECT_GROUP;
+	if(groups>0x7FFFFFFFull) { set_error("lattice too large for the object sums"); return FX3D_ERR_INVALID; }
+	ObjectPartial* partial = reinterpret_cast<ObjectPartial*>(scratch);
+	const dim3 g((uint32_t)groups), b(OBJECT_GROUP);
+	const uint32_t smem = 4u*OBJECT_GROUP*4u;
+	if(kind==0u) FX3D_LAUNCH_SMEM((k_object_partial<0>), g, b, smem, stream, L, flag_marker, cx, cy, cz, partial);
+	else if(kind==1u) FX3D_LAUNCH_SMEM((k_object_partial<1>), g, b, smem, stream, L, flag_marker, cx, cy, cz, partial);
+	else FX3D_LAUNCH_SMEM((k_object_partial<2>), g, b, smem, stream, L, flag_marker, cx, cy, cz, partial);
+	FX3D_LAUNCH(k_object_total, dim3(1u), dim3(32u), stream, partial, (uint32_t)groups, kind, object_sum);
+	return check_launch("object sum");
+}
+int fx3d_object_center_of_mass(const fx3d_lattice* lat, uint8_t flag_marker, float* object_sum, void* scratch, fx3d_stream stream) { return object_sum_impl(lat, 0u, flag_marker, 0.0f, 0.0f, 0.0f, object_sum, scratch, stream); }
+int fx3d_object_force(const fx3d_lattice* lat, uint8_t flag_marker, float* object_sum, void* scratch, fx3d_stream stream) { return object_sum_impl(lat, 1u, flag_marker, 0.0f, 0.0f, 0.0f, object_sum, scratch, stream); }
+int fx3d_object_torque(const fx3d_lattice* lat, uint8_t flag_marker, float cx, float cy, float cz, float* object_sum, void* scratch, fx3d_stream stream) { return object_sum_impl(lat, 2u, flag_marker, cx, cy, cz, object_sum, scratch, stream); }
 
 int fx3d_voxelize_mesh(const fx3d_lattice* lat, int Ox, int Oy, int Oz, uint32_t direction, uint64_t t, uint8_t flag, const float* p0, const float* p1, const float* p2, const float* bbu, fx3d_stream stream) {
 	Lattice L;
@@ -300,6 +354,54 @@ int fx3d_transfer_insert_rho_u_flags(const fx3d_lattice* lat, uint32_t axis, uin
 	if(int rc = use_device(lat->device)) return rc;
 	FX3D_LAUNCH((k_transfer_rho_u_flags<false>), g, b, stream, L, axis, const_cast<void*>(bp), const_cast<void*>(bm));
 	return check_launch("transfer_insert_rho_u_flags");
+}
+int fx3d_transfer_extract_flags(const fx3d_lattice* lat, uint32_t axis, uint64_t t, void* bp, void* bm, fx3d_stream stream) {
+	Lattice L; dim3 g, b;
+	if(!face_setup(lat, axis, t, L, g, b)) return FX3D_ERR_INVALID;
+	if(!bp||!bm) { set_error("transfer buffers are null"); return FX3D_ERR_INVALID; }
+	if(int rc = use_device(lat->device)) return rc;
+	FX3D_LAUNCH((k_transfer_flags<true>), g, b, stream, L, axis, reinterpret_cast<uint8_t*>(bp), reinterpret_cast<uint8_t*>(bm));
+	return check_launch("transfer_extract_flags");
+}
+int fx3d_transfer_insert_flags(const fx3d_lattice* lat, uint32_t axis, uint64_t t, const void* bp, const void* bm, fx3d_stream stream) {
+	Lattice L; dim3 g, b;
+	if(!face_setup(lat, axis, t, L, g, b)) return FX3D_ERR_INVALID;
+	if(!bp||!bm) { set_error("transfer buffers are null"); return FX3D_ERR_INVALID; }
+	if(int rc = use_device(lat->device)) return rc;
+	FX3D_LAUNCH((k_transfer_flags<false>), g, b, stream, L, axis, reinterpret_cast<uint8_t*>(const_cast<void*>(bp)), reinterpret_cast<uint8_t*>(const_cast<void*>(bm)));
+	return check_launch("transfer_insert_flags");
+}
+int fx3d_transfer_extract_F(const fx3d_lattice* lat, uint32_t axis, uint64_t t, void* bp, void* bm, fx3d_stream stream) {
+	Lattice L; dim3 g, b;
+	if(!face_setup(lat, axis, t, L, g, b)) return FX3D_ERR_INVALID;
+	if(!L.F||!bp||!bm) { set_error("transfer_extract_F needs a FORCE_FIELD lattice and two buffers"); return FX3D_ERR_INVALID; }
+	if(int rc = use_device(lat->device)) return rc;
+	FX3D_LAUNCH((k_transfer_F<true>), g, b, stream, L, axis, reinterpret_cast<float*>(bp), reinterpret_cast<float*>(bm));
+	return check_launch("transfer_extract_F");
+}
+int fx3d_transfer_insert_F(const fx3d_lattice* lat, uint32_t axis, uint64_t t, const void* bp, const void* bm, fx3d_stream stream) {
+	Lattice L; dim3 g, b;
+	if(!face_setup(lat, axis, t, L, g, b)) return FX3D_ERR_INVALID;
+	if(!L.F||!bp||!bm) { set_error("transfer_insert_F needs a FORCE_FIELD lattice and two buffers"); return FX3D_ERR_INVALID; }
+	if(int rc = use_device(lat->device)) return rc;
+	FX3D_LAUNCH((k_transfer_F<false>), g, b, stream, L, axis, reinterpret_cast<float*>(const_cast<void*>(bp)), reinterpret_cast<float*>(const_cast<void*>(bm)));
+	return check_launch("transfer_insert_F");
+}
+int fx3d_exchange_flags(const fx3d_lattice* lat, uint32_t axis, const uint8_t* flags_plus, const uint8_t* flags_minus, fx3d_stream stream) {
+	Lattice L; dim3 g, b;
+	if(!face_setup(lat, axis, 0ull, L, g, b)) return FX3D_ERR_INVALID;
+	if(!flags_plus||!flags_minus) { set_error("neighbour flag buffers are null"); return FX3D_ERR_INVALID; }
+	if(int rc = use_device(lat->device)) return rc;
+	FX3D_LAUNCH(k_exchange_flags, g, b, stream, L, axis, flags_plus, flags_minus);
+	return check_launch("exchange_flags");
+}
+int fx3d_exchange_F(const fx3d_lattice* lat, uint32_t axis, const float* F_plus, const float* F_minus, fx3d_stream stream) {
+	Lattice L; dim3 g, b;
+	if(!face_setup(lat, axis, 0ull, L, g, b)) return FX3D_ERR_INVALID;
+	if(!L.F||!F_plus||!F_minus) { set_error("exchange_F needs a FORCE_FIELD lattice and the neighbours' force fields"); return FX3D_ERR_INVALID; }
+	if(int rc = use_device(lat->device)) return rc;
+	FX3D_LAUNCH(k_exchange_F, g, b, stream, L, axis, F_plus, F_minus);
+	return check_launch("exchange_F");
 }
 int fx3d_exchange_fi(const fx3d_lattice* lat, uint32_t axis, uint64_t t, const void* fi_plus, const void* fi_minus, fx3d_stream stream) {
 	Lattice L; dim3 g, b;

@@ -47,6 +47,7 @@ struct Lattice { // one LBM_Domain as the device sees it (passed by value)
 	uint32_t eb;         // EQUILIBRIUM_BOUNDARIES enabled
 	uint32_t upd;        // UPDATE_FIELDS enabled
 	uint32_t mb;         // MOVING_BOUNDARIES enabled (general kernels only)
+	float* F;            // FORCE_FIELD: per-cell force [3N] SoA, or null (general kernels, update_fields, the force-field kernels)
 };
 struct Region { uint32_t g0, g1, y0, y1, z0, z1; }; // x-group range [g0,g1), cell ranges in y and z
 
@@ -717,17 +718,32 @@ FX3D_HD void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" 
 
 // y/z neighbours of a domain for the fused halo delivery: fi[(dy+1)+3*(dz+1)], [4] = the domain itself; unused entries null
 struct RowPeers { void* fi[9]; };
+// Block organisation of the whole-row kernel, measured on B200 (profiles/r02_row_kernel_tuning.txt): G compute groups of 128 threads per block sharing
+// one ring, B resident blocks per SM (also the register cap: 65536/(128*G*B)), ring depth = what fits (capped by FX3D_ROW_MAX_STAGES).
 #ifndef FX3D_ROW_GROUPS_16
-#define FX3D_ROW_GROUPS_16 4 // compute groups per block, D3Q19 with 16-bit storage (512 threads, 128 registers)
+#define FX3D_ROW_GROUPS_16 1 // D3Q19 with 16-bit storage
+#endif
+#ifndef FX3D_ROW_BLOCKS_16
+#define FX3D_ROW_BLOCKS_16 4
 #endif
 #ifndef FX3D_ROW_GROUPS_32
-#define FX3D_ROW_GROUPS_32 2 // D3Q19 FP32 (256 threads, 255 registers)
+#define FX3D_ROW_GROUPS_32 1 // FP32 (both velocity sets)
+#endif
+#ifndef FX3D_ROW_BLOCKS_32
+#define FX3D_ROW_BLOCKS_32 2
 #endif
 #ifndef FX3D_ROW_GROUPS_27
-#define FX3D_ROW_GROUPS_27 3 // D3Q27 with 16-bit storage (384 threads, 168 registers); D3Q27 FP32 always runs 2
+#define FX3D_ROW_GROUPS_27 1 // D3Q27 with 16-bit storage
 #endif
-template<int Q, int ST> FX3D_HDC constexpr int row_groups() { return ST==ST_FP32 ? (Q>19 ? 2 : FX3D_ROW_GROUPS_32) : (Q>19 ? FX3D_ROW_GROUPS_27 : FX3D_ROW_GROUPS_16); }
-constexpr uint32_t ROW_PAD = 16u, ROW_MAX_STAGES = 15u;
+#ifndef FX3D_ROW_BLOCKS_27
+#define FX3D_ROW_BLOCKS_27 3
+#endif
+#ifndef FX3D_ROW_MAX_STAGES
+#define FX3D_ROW_MAX_STAGES 15
+#endif
+template<int Q, int ST> FX3D_HDC constexpr int row_groups() { return ST==ST_FP32 ? FX3D_ROW_GROUPS_32 : (Q>19 ? FX3D_ROW_GROUPS_27 : FX3D_ROW_GROUPS_16); }
+template<int Q, int ST> FX3D_HDC constexpr int row_blocks() { return ST==ST_FP32 ? FX3D_ROW_BLOCKS_32 : (Q>19 ? FX3D_ROW_BLOCKS_27 : FX3D_ROW_BLOCKS_16); }
+constexpr uint32_t ROW_PAD = 16u, ROW_MAX_STAGES = FX3D_ROW_MAX_STAGES<15 ? FX3D_ROW_MAX_STAGES : 15u, ROW_HEADER = 256u; // header: full[16] | first[4] | unused
 FX3D_HDC constexpr uint32_t row_stage_bytes(uint32_t Q, uint32_t esz, uint32_t bx, uint32_t by) { return Q*by*(bx*4u*esz+2u*ROW_PAD); }
 #if defined(FX3D_HOST_EMULATION)
 // emulation of an mbarrier with an arrival count: bits 0-31 completed phases, 32-47 pending arrivals, 48-63 arrivals per phase.
@@ -743,17 +759,19 @@ FX3D_HD void mbar_copies_issued(uint64_t* b) {
 	}
 }
 FX3D_HD void mbar_wait_n(uint64_t* b, uint32_t parity) { while((__atomic_load_n(b, __ATOMIC_SEQ_CST)&1ull)==(uint64_t)parity) std::this_thread::yield(); }
+FX3D_HD void mbar_arrive(uint64_t* b) { mbar_copies_issued(b); } // a plain arrival
 FX3D_HD void group_sync(uint32_t g) { emul::group_barrier(g); }
 #else
 FX3D_HD void mbar_init_n(uint64_t* b, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(b)), "r"(n) : "memory"); }
 FX3D_HD void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) { mbar_expect_tx(b, bytes); } // one arrival, `bytes` more to wait for
 FX3D_HD void mbar_copies_issued(uint64_t*) {}
 FX3D_HD void mbar_wait_n(uint64_t* b, uint32_t parity) { mbar_wait(b, parity); }
+FX3D_HD void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(b)) : "memory"); }
 FX3D_HD void group_sync(uint32_t g) { asm volatile("bar.sync %0, 128;" :: "r"(g+1u) : "memory"); } // named barrier of one compute group
 #endif
 
 template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false>
-__global__ void __launch_bounds__(128*row_groups<Q, ST>(), 1) k_stream_collide_tma(const Lattice L, const Region R, const uint32_t tiles_y, const uint32_t S, const RowPeers P) {
+__global__ void __launch_bounds__(128*row_groups<Q, ST>(), row_blocks<Q, ST>()) k_stream_collide_tma(const Lattice L, const Region R, const uint32_t tiles_y, const uint32_t S, const RowPeers P) {
 	constexpr int K = 4;
 	constexpr uint32_t G = (uint32_t)row_groups<Q, ST>(), PAD = ROW_PAD;
 	typedef Codec<ST> C;
@@ -762,7 +780,8 @@ __global__ void __launch_bounds__(128*row_groups<Q, ST>(), 1) k_stream_collide_t
 	constexpr uint32_t VB = (uint32_t)(sizeof(E)*K), ESZ = (uint32_t)sizeof(E);
 	unsigned char* const smem = dynamic_smem();
 	uint64_t* const full = reinterpret_cast<uint64_t*>(smem); // full[stage]: the bulk loads of the tile in this stage have landed
-	unsigned char* const ring = smem+128;
+	uint64_t* const first_fill = full+16;                     // first_fill[stage], stage < G: one-shot, the FIRST fill of this stage has landed (see the main loop)
+	unsigned char* const ring = smem+ROW_HEADER;
 	const uint32_t bx = blockDim.x, by = blockDim.y, g = threadIdx.z;
 	const uint32_t t = threadIdx.x+threadIdx.y*bx, lane = t&31u;
 	const uint32_t warp = __shfl_sync(0xFFFFFFFFu, t>>5, 0); // warp within the group, uniform
@@ -774,7 +793,10 @@ __global__ void __launch_bounds__(128*row_groups<Q, ST>(), 1) k_stream_collide_t
 	const bool one_row = by==1u;
 	const uint32_t first_copy = warp+4u*lane; // multi-row tiles: copy c = ty*Q+j belongs to lane c/4 of warp c%4 (then every 128th)
 	const bool copier = one_row ? lane==0u : first_copy<ncopies;
-	if(t==0u && g==0u) { for(uint32_t s=0u; s<S; s++) mbar_init_n(full+s, one_row ? 4u : (ncopies<128u ? ncopies : 128u)); }
+	if(t==0u && g==0u) {
+		for(uint32_t s=0u; s<S; s++) mbar_init_n(full+s, one_row ? 4u : (ncopies<128u ? ncopies : 128u));
+		for(uint32_t s=0u; s<G; s++) mbar_init_n(first_fill+s, 1u);
+	}
 	fence_async_smem();
 	__syncthreads();
 
@@ -858,10 +880,16 @@ __global__ void __launch_bounds__(128*row_groups<Q, ST>(), 1) k_stream_collide_t
 	auto combine_flags = [&](Pos p) -> uint32_t { const uint32_t sh = 8u*(uint32_t)(flag_address(p)&3u); return sh==0u ? fw0 : (fw0>>sh)|(fw1<<(32u-sh)); };
 	Pos cur = advance(first, g);
 	if(g<n) request_flags(cur);
+	uint32_t stage = g, fill = 0u, prev_stage = 0u; // stage = k%S, fill = k/S (how often the stage has been filled before), prev_stage = (k-G)%S: kept incrementally, S is a run-time value
 	for(uint32_t k=g; k<n; k+=G, cur = advance(cur, G)) {
-		const uint32_t stage = k%S, y0 = R.y0+cur.yb*by, y = y0+threadIdx.y, z = R.z0+cur.zo;
-		if(k>=S && k<S+G) mbar_wait_n(full+stage, 0u); // early tiles: the stage's first fill (a prologue load issued by another group) must be complete before its second can be awaited
-		mbar_wait_n(full+stage, (k/S)&1u);
+		const uint32_t y0 = R.y0+cur.yb*by, y = y0+threadIdx.y, z = R.z0+cur.zo;
+		// A parity wait can only tell a phase from its neighbours: waiting for fill m of a stage is sound only once fill m-1 is known to be complete.
+		// From k = S+G on that follows from the schedule (this group's previous tile k-G was loaded by the group that had just consumed fill m-1 of
+		// this very stage). Tiles S..S+G-1 are second fills whose predecessors were prologue loads consumed by ANOTHER group at an unrelated time --
+		// waiting for "phase 0" on full[] would hang if fill 1 has already landed too -- so that group reports on a one-shot barrier of its own.
+		if(k>=S && k<S+G) mbar_wait_n(first_fill+stage, 0u);
+		mbar_wait_n(full+stage, fill&1u);
+		if(k<G && t==0u) mbar_arrive(first_fill+stage);
 		const uint32_t flags4 = combine_flags(cur);
 		unsigned char* const sb = ring+(size_t)stage*STAGE+threadIdx.y*RB+PAD; // element 0 of my row in buffer 0
 		// ---- stream in from the stage: my vectors, and for the x-shifted directions the element beyond them ----
@@ -876,7 +904,7 @@ __global__ void __launch_bounds__(128*row_groups<Q, ST>(), 1) k_stream_collide_t
 		group_sync(g); // the whole group has read the stage before anybody writes results into it
 		// refill the stage of this group's previous tile now rather than right after its stores: they have had the stream-in above
 		// to finish reading it, so the copying threads rarely wait here
-		if(k>=G && k-G+S<n) { const Pos p = advance(cur, S-G); if(copier) bulk_wait_read(); load_tile(R.y0+p.yb*by, R.z0+p.zo, (k-G)%S); }
+		if(k>=G && k-G+S<n) { const Pos p = advance(cur, S-G); if(copier) bulk_wait_read(); load_tile(R.y0+p.yb*by, R.z0+p.zo, prev_stage); }
 		if(k+G<n) request_flags(advance(cur, G));
 		collide_tile<Q, COLL, ST, VF, K, SG, MB>(L, A, flags4, L.Hx+x0, y, z);
 		// ---- stream out into the same row buffers ----
@@ -892,6 +920,8 @@ __global__ void __launch_bounds__(128*row_groups<Q, ST>(), 1) k_stream_collide_t
 		fence_async_smem();
 		group_sync(g);
 		store_tile(y0, z, stage);
+		prev_stage = stage; stage += G;
+		if(stage>=S) { stage -= S; fill++; }
 	}
 	if(copier) bulk_wait_all();
 }
@@ -1141,7 +1171,9 @@ __global__ void __launch_bounds__(128) k_stream_collide_v1(const Lattice L, cons
 	float rho_e = 1.0f, ux_e = 0.0f, uy_e = 0.0f, uz_e = 0.0f;
 	if(is_e) { rho_e = L.rho[n]; ux_e = L.u[n]; uy_e = L.u[N+n]; uz_e = L.u[2ull*N+n]; }
 	float rhon, uxn, uyn, uzn;
-	collide_cell<Q, COLL, VF, float, SG>(f, 1.0f, 1.0f, is_e, false, rho_e, ux_e, uy_e, uz_e, L.fx, L.fy, L.fz, L.w, rhon, uxn, uyn, uzn);
+	float fxn = L.fx, fyn = L.fy, fzn = L.fz; // :1494
+	if constexpr(VF) { if(L.F) { fxn += L.F[n]; fyn += L.F[N+n]; fzn += L.F[2ull*N+n]; } } // FORCE_FIELD, :1497-1503 (without VOLUME_FORCE the force is never used)
+	collide_cell<Q, COLL, VF, float, SG>(f, 1.0f, 1.0f, is_e, false, rho_e, ux_e, uy_e, uz_e, fxn, fyn, fzn, L.w, rhon, uxn, uyn, uzn);
 	if(L.upd!=0u && !is_e) { L.rho[n] = rhon; L.u[n] = uxn; L.u[N+n] = uyn; L.u[2ull*N+n] = uzn; }
 	io.push(L, L.odd, f);
 }
@@ -1232,7 +1264,9 @@ __global__ void __launch_bounds__(128) k_update_fields(const Lattice L, const Re
 	io.pull(L, L.odd, f);
 	if(L.mb!=0u && fb==TYPE_MS) apply_moving_boundaries<Q>(L, x, y, z, f); // :1813-1815
 	float rhon, uxn, uyn, uzn;
-	fields_of_cell<Q, VF>(f, L.fx, L.fy, L.fz, rhon, uxn, uyn, uzn);
+	float fxn = L.fx, fyn = L.fy, fzn = L.fz;
+	if constexpr(VF) { if(L.F) { fxn += L.F[n]; fyn += L.F[N+n]; fzn += L.F[2ull*N+n]; } } // FORCE_FIELD, :1821-1827
+	fields_of_cell<Q, VF>(f, fxn, fyn, fzn, rhon, uxn, uyn, uzn);
 	if(L.eb!=0u && fb==TYPE_E) return;
 	L.rho[n] = rhon; L.u[n] = uxn; L.u[N+n] = uyn; L.u[2ull*N+n] = uzn;
 }
@@ -1342,6 +1376,135 @@ __global__ void __launch_bounds__(128) k_unvoxelize_mesh(const Lattice L, const 
 	if(p.x>=x0-1.0f&&p.y>=y0-1.0f&&p.z>=z0-1.0f&&p.x<=x1+1.0f&&p.y<=y1+1.0f&&p.z<=z1+1.0f) L.flags[n] &= (uint8_t)~flag;
 }
 #endif
+
+FX3D_HD uint32_t face_area_of(const Lattice& L, uint32_t axis) { return axis==0u ? L.Ny*L.Nz : axis==1u ? L.Nz*L.Nx : L.Nx*L.Ny; } // get_area, src/kernel.cpp:2049-2052
+FX3D_HD void face_cell_of(const Lattice& L, uint32_t axis, uint32_t a, uint32_t layer, uint32_t& x, uint32_t& y, uint32_t& z) { // :2053-2068
+	if(axis==0u) { x = layer; y = a%L.Ny; z = a/L.Ny; } else if(axis==1u) { x = a/L.Nz; y = layer; z = a%L.Nz; } else { x = a%L.Nx; y = a/L.Nx; z = layer; }
+}
+// ================================================================================================================
+// FORCE_FIELD, src/kernel.cpp:1873-1959; host side src/lbm.cpp:206-239,986-1016
+// ================================================================================================================
+// update_force_field, :1873-1884: the force of the fluid on a solid cell is twice the momentum of the populations streaming into it
+// (they bounce back): calculate_rho_u on them, F = 2*Fb*(fx,fy,fz)
+template<int Q, int ST>
+__global__ void __launch_bounds__(128) k_update_force_field(const Lattice L, const Region R) {
+	uint32_t x, y, z;
+	if(!region_cell(R, x, y, z)) return;
+	const uint64_t n = lin(L, x, y, z), N = cells(L);
+	if((L.flags[n]&TYPE_BO)!=TYPE_S) return;
+	CellIO<Q, ST> io; io.locate(L, x, y, z);
+	float f[Q];
+	io.pull(L, L.odd, f);
+	float Fb, fx, fy, fz;
+	moments<Q, float>(f, 1.0f, 1.0f, Fb, fx, fy, fz);
+	const float s = 2.0f*Fb;
+	L.F[n] = s*fx; L.F[N+n] = s*fy; L.F[2ull*N+n] = s*fz;
+}
+// object_center_of_mass (KIND 0) / object_force (1) / object_torque (2), :1901-1959. The reference adds one partial sum per work-group into
+// object_sum with floating-point atomics, i.e. in no defined order; here the order is fixed so that results are reproducible (and equal the
+// oracle's bit for bit): pass 1 reduces every group of 64 consecutive cells with the reference's stride-doubling tree into partial[group],
+// pass 2 (one warp) adds the non-zero partial sums in ascending group order -- one of the orders the reference's atomics can produce.
+constexpr uint32_t OBJECT_GROUP = 64u; // the reference's work-group size (src/opencl.hpp WORKGROUP_SIZE)
+struct alignas(16) ObjectPartial { float x, y, z; uint32_t cells; };
+template<int KIND>
+__global__ void __launch_bounds__(OBJECT_GROUP) k_object_partial(const Lattice L, const uint8_t flag_marker, const float cx, const float cy, const float cz, ObjectPartial* partial) {
+	float (*cache)[OBJECT_GROUP] = reinterpret_cast<float (*)[OBJECT_GROUP]>(dynamic_smem()); // [3][OBJECT_GROUP] floats, then the cell counts
+	uint32_t* count = reinterpret_cast<uint32_t*>(dynamic_smem())+3u*OBJECT_GROUP;
+	const uint32_t lid = threadIdx.x;
+	const uint64_t n = (uint64_t)blockIdx.x*OBJECT_GROUP+lid, N = cells(L);
+	float vx = 0.0f, vy = 0.0f, vz = 0.0f; uint32_t c = 0u;
+	if(n<N && L.flags[n]==flag_marker) {
+		const uint64_t plane = (uint64_t)L.Nx*L.Ny, r = n%plane;
+		const Float3 p = cell_position(L, (uint32_t)(r%L.Nx), (uint32_t)(r/L.Nx), (uint32_t)(n/plane));
+		if constexpr(KIND==0) { vx = p.x; vy = p.y; vz = p.z; c = 1u; }
+		else if constexpr(KIND==1) { vx = L.F[n]; vy = L.F[N+n]; vz = L.F[2ull*N+n]; }
+		else { const Float3 t = cross3(p-f3(cx, cy, cz), f3(L.F[n], L.F[N+n], L.F[2ull*N+n])); vx = t.x; vy = t.y; vz = t.z; }
+	}
+	cache[0][lid] = vx; cache[1][lid] = vy; cache[2][lid] = vz; count[lid] = c;
+	__syncthreads();
+	for(uint32_t s=1u; s<OBJECT_GROUP; s*=2u) {
+		if(lid%(2u*s)==0u) { cache[0][lid] += cache[0][lid+s]; cache[1][lid] += cache[1][lid+s]; cache[2][lid] += cache[2][lid+s]; count[lid] += count[lid+s]; }
+		__syncthreads();
+	}
+	if(lid==0u) partial[blockIdx.x] = ObjectPartial{ cache[0][0], cache[1][0], cache[2][0], count[0] };
+}
+#if defined(FX3D_TU_LBM)
+__global__ void __launch_bounds__(32) k_object_total(const ObjectPartial* partial, const uint32_t groups, const uint32_t kind, float* object_sum) {
+	const uint32_t lane = threadIdx.x;
+	float sx = 0.0f, sy = 0.0f, sz = 0.0f; uint32_t cells_total = 0u;
+	for(uint32_t base=0u; base<groups; base+=32u) {
+		ObjectPartial p = ObjectPartial{ 0.0f, 0.0f, 0.0f, 0u };
+		if(base+lane<groups) p = partial[base+lane];
+		const bool any = kind==0u ? p.cells>0u : (p.x!=0.0f || p.y!=0.0f || p.z!=0.0f);
+		uint32_t todo = __ballot_sync(0xFFFFFFFFu, any);
+		while(todo) { // ascending group order; adding a zero component changes nothing, so components need no separate test
+#if defined(FX3D_HOST_EMULATION)
+			const int k = __builtin_ctz(todo);
+#else
+			const int k = __ffs((int)todo)-1;
+#endif
+			todo &= todo-1u;
+			sx += __uint_as_float(__shfl_sync(0xFFFFFFFFu, __float_as_uint(p.x), k)); sy += __uint_as_float(__shfl_sync(0xFFFFFFFFu, __float_as_uint(p.y), k));
+			sz += __uint_as_float(__shfl_sync(0xFFFFFFFFu, __float_as_uint(p.z), k)); cells_total += __shfl_sync(0xFFFFFFFFu, p.cells, k);
+		}
+	}
+	if(lane==0u) { object_sum[0] = sx; object_sum[1] = sy; object_sum[2] = sz; object_sum[3] = __uint_as_float(cells_total); }
+}
+// transfer_extract_F / transfer__insert_F, :2173-2196: three float planes per side
+template<bool EXTRACT>
+__global__ void __launch_bounds__(128) k_transfer_F(const Lattice L, const uint32_t axis, float* buf_p, float* buf_m) {
+	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x, A = face_area_of(L, axis), len = axis==0u ? L.Nx : axis==1u ? L.Ny : L.Nz;
+	if(a>=A) return;
+	const uint64_t N = cells(L);
+	uint32_t x, y, z;
+	for(int side=0; side<2; side++) {
+		face_cell_of(L, axis, a, side==0 ? (EXTRACT ? len-2u : len-1u) : (EXTRACT ? 1u : 0u), x, y, z);
+		const uint64_t n = lin(L, x, y, z);
+		float* fb = side==0 ? buf_p : buf_m;
+		for(uint32_t k=0u; k<3u; k++) { if(EXTRACT) fb[(uint64_t)k*A+a] = L.F[k*N+n]; else L.F[k*N+n] = fb[(uint64_t)k*A+a]; }
+	}
+}
+// direct peer pull of the F halo (communicate_F, src/lbm.cpp:1395-1397) and of the flags halo alone (communicate_flags, :1391-1393;
+// transfer_extract/insert_flags, src/kernel.cpp:2160-2171: one byte per face cell)
+__global__ void __launch_bounds__(128) k_exchange_F(const Lattice L, const uint32_t axis, const float* F_plus, const float* F_minus) {
+	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x, A = face_area_of(L, axis), len = axis==0u ? L.Nx : axis==1u ? L.Ny : L.Nz;
+	if(a>=A) return;
+	const uint64_t N = cells(L);
+	uint32_t x, y, z;
+	for(int side=0; side<2; side++) {
+		const float* src = side==0 ? F_plus : F_minus;
+		face_cell_of(L, axis, a, side==0 ? 1u : len-2u, x, y, z);
+		const uint64_t ns = lin(L, x, y, z);
+		face_cell_of(L, axis, a, side==0 ? len-1u : 0u, x, y, z);
+		const uint64_t nd = lin(L, x, y, z);
+		for(uint32_t k=0u; k<3u; k++) L.F[k*N+nd] = src[k*N+ns];
+	}
+}
+__global__ void __launch_bounds__(128) k_exchange_flags(const Lattice L, const uint32_t axis, const uint8_t* flags_plus, const uint8_t* flags_minus) {
+	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x, A = face_area_of(L, axis), len = axis==0u ? L.Nx : axis==1u ? L.Ny : L.Nz;
+	if(a>=A) return;
+	uint32_t x, y, z;
+	for(int side=0; side<2; side++) {
+		const uint8_t* src = side==0 ? flags_plus : flags_minus;
+		face_cell_of(L, axis, a, side==0 ? 1u : len-2u, x, y, z);
+		const uint64_t ns = lin(L, x, y, z);
+		face_cell_of(L, axis, a, side==0 ? len-1u : 0u, x, y, z);
+		L.flags[lin(L, x, y, z)] = src[ns];
+	}
+}
+template<bool EXTRACT>
+__global__ void __launch_bounds__(128) k_transfer_flags(const Lattice L, const uint32_t axis, uint8_t* buf_p, uint8_t* buf_m) {
+	const uint32_t a = blockIdx.x*blockDim.x+threadIdx.x, A = face_area_of(L, axis), len = axis==0u ? L.Nx : axis==1u ? L.Ny : L.Nz;
+	if(a>=A) return;
+	uint32_t x, y, z;
+	for(int side=0; side<2; side++) {
+		face_cell_of(L, axis, a, side==0 ? (EXTRACT ? len-2u : len-1u) : (EXTRACT ? 1u : 0u), x, y, z);
+		const uint64_t n = lin(L, x, y, z);
+		uint8_t* b = side==0 ? buf_p : buf_m;
+		if(EXTRACT) b[a] = L.flags[n]; else L.flags[n] = b[a];
+	}
+}
+#endif // FX3D_TU_LBM
 
 // ================================================================================================================
 // halo transfer. Direction lists per face side (position b pairs opposite directions on the two sides),

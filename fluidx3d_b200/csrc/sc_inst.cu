@@ -42,11 +42,12 @@ template<int Q, int COLL, int ST, bool VF> static int launch_pipe(const Lattice&
 	return L.odd ? launch_pipe_parity<Q, COLL, ST, VF, 1>(L, R, block, stream, reserve) : launch_pipe_parity<Q, COLL, ST, VF, 0>(L, R, block, stream, reserve);
 }
 
-// bulk-copy (TMA) kernel: the tile must span whole rows -- see the kernel's header comment. Block = (bx, 128/bx, G); the ring depth
-// S is whatever fits the shared memory of one SM (one block per SM), at least G+1.
+// bulk-copy (TMA) kernel: the tile must span whole rows -- see the kernel's header comment. Block = (bx, 128/bx, G), B blocks per SM; the ring
+// depth S is whatever fits this block's share of the SM's shared memory (228 KB, 1 KB of it reserved per resident block), at least G+1.
 template<int Q, int ST> static uint32_t row_stages(const dim3& block) {
-	const uint32_t stage = row_stage_bytes((uint32_t)Q, ST==ST_FP32 ? 4u : 2u, block.x, block.y);
-	return std::min<uint32_t>(ROW_MAX_STAGES, (227u*1024u-1024u-128u)/stage);
+	const uint32_t stage = row_stage_bytes((uint32_t)Q, ST==ST_FP32 ? 4u : 2u, block.x, block.y), B = (uint32_t)row_blocks<Q, ST>();
+	const uint32_t share = std::min<uint32_t>(227u*1024u, (228u*1024u)/B-1024u);
+	return std::min<uint32_t>(ROW_MAX_STAGES, (share-ROW_HEADER)/stage);
 }
 template<int Q, int ST> static bool tma_eligible(const Lattice& L, const Region& R, const dim3& block) {
 	const uint32_t esz = ST==ST_FP32 ? 4u : 2u, inner = L.Nx-2u*L.Hx;
@@ -60,21 +61,21 @@ template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = f
 	const uint32_t tiles_y = (R.y1-R.y0)/block.y, nz = R.z1-R.z0;
 	constexpr uint32_t G = (uint32_t)row_groups<Q, ST>();
 	const uint32_t S = row_stages<Q, ST>(block);
-	const uint32_t smem = 128u+S*row_stage_bytes((uint32_t)Q, ST==ST_FP32 ? 4u : 2u, block.x, block.y);
+	const uint32_t smem = ROW_HEADER+S*row_stage_bytes((uint32_t)Q, ST==ST_FP32 ? 4u : 2u, block.x, block.y);
 	int sms = 148;
 #if !defined(FX3D_HOST_EMULATION)
-	static std::atomic<uint64_t> configured{0ull};
+	static std::atomic<uint32_t> configured[64]; // per instantiation and device: the opt-in shared memory size that is set (the ring depth depends on the tile shape)
 	int dev = 0; cudaGetDevice(&dev);
-	if(dev>=64 || !((configured.load()>>dev)&1ull)) {
-		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227*1024-1024);
+	if(dev>=64 || configured[dev].load()!=smem) {
+		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if(e!=cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stream_collide_tma)");
-		if(dev<64) configured.fetch_or(1ull<<dev);
+		if(dev<64) configured[dev].store(smem);
 	}
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 #else
 	sms = 2;
 #endif
-	const uint64_t all_blocks = (uint64_t)sms, take = (uint64_t)std::max(reserve, 0)/4ull, blocks = all_blocks>2ull*take ? all_blocks-take : all_blocks, ntiles = (uint64_t)tiles_y*nz;
+	const uint64_t all_blocks = (uint64_t)sms*(uint64_t)row_blocks<Q, ST>(), take = (uint64_t)std::max(reserve, 0)*(uint64_t)row_blocks<Q, ST>()/4ull, blocks = all_blocks>2ull*take ? all_blocks-take : all_blocks, ntiles = (uint64_t)tiles_y*nz;
 	if(ntiles==0ull) return FX3D_OK;
 	const dim3 grid((uint32_t)std::min<uint64_t>((ntiles+G-1u)/G, blocks), 1u, 1u);
 	g_kind_launches[3]++;

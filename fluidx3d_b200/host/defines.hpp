@@ -24,10 +24,10 @@
 //#define EQUILIBRIUM_BOUNDARIES
 //#define UPDATE_FIELDS
 //#define SUBGRID // Smagorinsky-Lilly subgrid turbulence model (runs the whole-row bulk-copy kernel or the general kernel)
-//#define MOVING_BOUNDARIES // moving solid boundaries (TYPE_S cells with non-zero velocity); runs the general kernel
+//#define MOVING_BOUNDARIES // moving solid boundaries (TYPE_S cells with non-zero velocity)
+//#define FORCE_FIELD // boundary forces on solid cells (lbm.object_force() etc.); with VOLUME_FORCE also a per-cell force lbm.F
 
 // extensions of the reference that this build does not provide
-//#define FORCE_FIELD
 //#define SURFACE
 //#define TEMPERATURE
 //#define PARTICLES
@@ -69,8 +69,8 @@
 #undef GRAPHICS
 #endif
 
-#if defined(FORCE_FIELD) || defined(SURFACE) || defined(TEMPERATURE) || defined(PARTICLES)
-#error "FORCE_FIELD / SURFACE / TEMPERATURE / PARTICLES are not part of the B200 hot-path build (see DESIGN.md, out of scope)"
+#if defined(SURFACE) || defined(TEMPERATURE) || defined(PARTICLES)
+#error "SURFACE / TEMPERATURE / PARTICLES are not part of the B200 hot-path build (see DESIGN.md, out of scope)"
 #endif
 #if defined(INTERACTIVE_GRAPHICS) || defined(INTERACTIVE_GRAPHICS_ASCII) || defined(GRAPHICS)
 #error "graphics are not part of the B200 hot-path build (see DESIGN.md, out of scope)"

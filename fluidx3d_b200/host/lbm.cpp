@@ -40,15 +40,26 @@ static uint extension_mask() {
 #ifdef MOVING_BOUNDARIES
 	m |= FX3D_MOVING_BOUNDARIES;
 #endif
+#ifdef FORCE_FIELD
+	m |= FX3D_FORCE_FIELD;
+#endif
 	return m;
 }
 
-uint bytes_per_cell_host() { return 17u; } // rho 4 + u 12 + flags 1
-uint bytes_per_cell_device() { return velocity_set*(uint)sizeof(fpxx)+17u; }
+#ifdef FORCE_FIELD
+static const uint force_field_bytes = 12u; // F
+#else
+static const uint force_field_bytes = 0u;
+#endif
+uint bytes_per_cell_host() { return 17u+force_field_bytes; } // rho 4 + u 12 + flags 1 (+ F 12)
+uint bytes_per_cell_device() { return velocity_set*(uint)sizeof(fpxx)+17u+force_field_bytes; }
 uint bandwidth_bytes_per_cell_device() {
-	uint b = velocity_set*2u*(uint)sizeof(fpxx)+1u; // every DDF read once and written once, plus the flag byte
+	uint b = velocity_set*2u*(uint)sizeof(fpxx)+1u+force_field_bytes; // every DDF read once and written once, plus the flag byte
 #ifdef UPDATE_FIELDS
 	b += 16u;
+#endif
+#ifdef MOVING_BOUNDARIES
+	b += velocity_set-1u; // the reference counts the neighbour flags
 #endif
 	return b;
 }
@@ -71,7 +82,7 @@ LBM_Domain::LBM_Domain(const Device_Info& device_info, fx3d_stream shared_stream
 	lattice.Nx = Nx; lattice.Ny = Ny; lattice.Nz = Nz; lattice.Dx = Dx; lattice.Dy = Dy; lattice.Dz = Dz;
 	lattice.velocity_set = velocity_set; lattice.collision = collision_operator; lattice.storage = storage_format; lattice.features = extension_mask();
 	lattice.w = fx3d_relaxation_rate(nu); // 1/tau with the decimal round trip the reference's JIT constant goes through
-	lattice.fi = nullptr; lattice.rho = nullptr; lattice.u = nullptr; lattice.flags = nullptr;
+	lattice.fi = nullptr; lattice.rho = nullptr; lattice.u = nullptr; lattice.flags = nullptr; lattice.F = nullptr;
 	const size_t fi_bytes = fx3d_fi_bytes(&lattice);
 	if(fi_bytes==0u) print_error(string("lattice rejected: ")+fx3d_last_error());
 	print_info("Allocating memory. This may take a few seconds.");
@@ -86,6 +97,12 @@ LBM_Domain::LBM_Domain(const Device_Info& device_info, fx3d_stream shared_stream
 		staging_bytes = ((ulong)fx3d_transfer_bytes(&lattice)+255ull)/256ull*256ull;
 		staging = Memory<char>(device, 2ull*staging_bytes, 1u, false);
 	}
+#ifdef FORCE_FIELD
+	F = Memory<float>(device, N, 3u);
+	object_sum = Memory<float>(device, 1ull, 4u);
+	object_scratch = Memory<char>(device, (ulong)fx3d_object_scratch_bytes(&lattice), 1u, false);
+	lattice.F = F.device_data();
+#endif
 }
 uint LBM_Domain::get_velocity_set() const { return velocity_set; }
 
@@ -96,6 +113,60 @@ void LBM_Domain::enqueue_run_steps(const ulong steps) { fx3d_check(fx3d_run_step
 #ifdef MOVING_BOUNDARIES
 void LBM_Domain::enqueue_update_moving_boundaries() { fx3d_check(fx3d_update_moving_boundaries(&lattice, device.get_stream()), "update_moving_boundaries"); }
 #endif
+#ifdef FORCE_FIELD
+void LBM_Domain::enqueue_update_force_field() {
+	if(t!=t_last_force_field) { // F is stale only if time has advanced since the last update
+		fx3d_check(fx3d_update_force_field(&lattice, t, device.get_stream()), "update_force_field");
+		t_last_force_field = t;
+	}
+}
+void LBM_Domain::enqueue_object_center_of_mass(const uchar flag_marker) {
+	fx3d_check(fx3d_object_center_of_mass(&lattice, flag_marker, object_sum.device_data(), object_scratch.device_data(), device.get_stream()), "object_center_of_mass");
+	object_sum.enqueue_read_from_device();
+}
+void LBM_Domain::enqueue_object_force(const uchar flag_marker) {
+	enqueue_update_force_field();
+	fx3d_check(fx3d_object_force(&lattice, flag_marker, object_sum.device_data(), object_scratch.device_data(), device.get_stream()), "object_force");
+	object_sum.enqueue_read_from_device();
+}
+void LBM_Domain::enqueue_object_torque(const float3& rotation_center, const uchar flag_marker) {
+	enqueue_update_force_field();
+	fx3d_check(fx3d_object_torque(&lattice, flag_marker, rotation_center.x, rotation_center.y, rotation_center.z, object_sum.device_data(), object_scratch.device_data(), device.get_stream()), "object_torque");
+	object_sum.enqueue_read_from_device();
+}
+void LBM_Domain::enqueue_exchange_F(const uint axis, const LBM_Domain& plus, const LBM_Domain& minus) {
+	fx3d_check(fx3d_exchange_F(&lattice, axis, plus.lattice.F, minus.lattice.F, device.get_stream()), "halo exchange (F)");
+}
+#endif
+void LBM_Domain::voxelize_mesh_on_device(const Mesh* mesh, const uchar flag, const float3& rotation_center, const float3& linear_velocity, const float3& rotational_velocity) {
+	Memory<float> p0(device, (ulong)mesh->triangle_number, 3u), p1(device, (ulong)mesh->triangle_number, 3u), p2(device, (ulong)mesh->triangle_number, 3u); // xyz interleaved per triangle
+	for(uint k=0u; k<mesh->triangle_number; k++) {
+		p0[3ull*k] = mesh->p0[k].x; p0[3ull*k+1ull] = mesh->p0[k].y; p0[3ull*k+2ull] = mesh->p0[k].z;
+		p1[3ull*k] = mesh->p1[k].x; p1[3ull*k+1ull] = mesh->p1[k].y; p1[3ull*k+2ull] = mesh->p1[k].z;
+		p2[3ull*k] = mesh->p2[k].x; p2[3ull*k+1ull] = mesh->p2[k].y; p2[3ull*k+2ull] = mesh->p2[k].z;
+	}
+	// bounding box with 2 cells of tolerance (re-voxelisation of moving objects), rotation centre, velocities: the kernel's parameter block
+	const float x0 = mesh->pmin.x-2.0f, y0 = mesh->pmin.y-2.0f, z0 = mesh->pmin.z-2.0f, x1 = mesh->pmax.x+2.0f, y1 = mesh->pmax.y+2.0f, z1 = mesh->pmax.z+2.0f;
+	const float block[16] = { as_float(mesh->triangle_number), x0, y0, z0, x1, y1, z1, rotation_center.x, rotation_center.y, rotation_center.z,
+		linear_velocity.x, linear_velocity.y, linear_velocity.z, rotational_velocity.x, rotational_velocity.y, rotational_velocity.z };
+	uint direction = 0u; // rays along the rotation axis, or -- for a body that does not rotate -- through the smallest face of the bounding box
+	if(length(rotational_velocity)==0.0f) {
+		const float area[3] = { (y1-y0)*(z1-z0), (z1-z0)*(x1-x0), (x1-x0)*(y1-y0) };
+		for(uint i=1u; i<3u; i++) if(area[i]<area[direction]) direction = i;
+	} else {
+		const float along[3] = { fabsf(rotational_velocity.x), fabsf(rotational_velocity.y), fabsf(rotational_velocity.z) };
+		for(uint i=1u; i<3u; i++) if(along[i]>along[direction]) direction = i;
+	}
+	p0.write_to_device(); p1.write_to_device(); p2.write_to_device();
+	fx3d_check(fx3d_voxelize_mesh(&lattice, Ox, Oy, Oz, direction, t+1ull, flag, p0.device_data(), p1.device_data(), p2.device_data(), block, device.get_stream()), "voxelize_mesh");
+	finish_queue();
+}
+void LBM_Domain::enqueue_unvoxelize_mesh_on_device(const Mesh* mesh, const uchar flag) {
+	fx3d_check(fx3d_unvoxelize_mesh(&lattice, Ox, Oy, Oz, flag, mesh->pmin.x, mesh->pmin.y, mesh->pmin.z, mesh->pmax.x, mesh->pmax.y, mesh->pmax.z, device.get_stream()), "unvoxelize_mesh");
+}
+void LBM_Domain::enqueue_exchange_flags(const uint axis, const LBM_Domain& plus, const LBM_Domain& minus) {
+	fx3d_check(fx3d_exchange_flags(&lattice, axis, plus.lattice.flags, minus.lattice.flags, device.get_stream()), "halo exchange (flags)");
+}
 void LBM_Domain::enqueue_update_fields() {
 #ifndef UPDATE_FIELDS
 	if(t!=t_last_update_fields) { // rho/u on the device are stale only if time has advanced since the last update
@@ -188,6 +259,11 @@ void LBM::construct(const uint Nx_, const uint Ny_, const uint Nz_, const uint D
 	rho = Memory_Container<float>(this, b_rho, "rho");
 	u = Memory_Container<float>(this, b_u, "u");
 	flags = Memory_Container<uchar>(this, b_flags, "flags");
+#ifdef FORCE_FIELD
+	vector<Memory<float>*> b_F;
+	for(uint d=0u; d<D; d++) b_F.push_back(&lbm_domain[d]->F);
+	F = Memory_Container<float>(this, b_F, "F");
+#endif
 	fused_halo = Dy*Dz>1u;
 	for(uint d=0u; d<D && fused_halo; d++) fused_halo = fx3d_fused_halo_supported(&lbm_domain[d]->get_lattice())==1;
 }
@@ -293,14 +369,19 @@ void LBM::rendezvous() { // every domain tells its face neighbours "I am here" a
 	}
 	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_rendezvous_wait(nb[d], rendezvous_count);
 }
-void LBM::communicate_field(const bool ddfs, const uint axes) { // x, then y, then z, so that edges and corners travel with later faces
+void LBM::communicate_field(const Field field, const uint axes) { // x, then y, then z, so that edges and corners travel with later faces
 	const uint Dn[3] = { Dx, Dy, Dz };
 	for(uint axis=0u; axis<3u; axis++) if(Dn[axis]>1u && ((axes>>axis)&1u)) {
-		if(ddfs && axis==0u) for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_pack_x_faces();
+		if(field==FIELD_FI && axis==0u) for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_pack_x_faces();
 		rendezvous(); // what this phase reads (stream_collide output, or the previous axis' halos) is complete everywhere
 		for(uint d=0u; d<get_D(); d++) {
 			LBM_Domain& plus = *lbm_domain[neighbour(d, axis, +1)]; LBM_Domain& minus = *lbm_domain[neighbour(d, axis, -1)];
-			if(ddfs) lbm_domain[d]->enqueue_exchange_fi(axis, plus, minus); else lbm_domain[d]->enqueue_exchange_rho_u_flags(axis, plus, minus);
+			if(field==FIELD_FI) lbm_domain[d]->enqueue_exchange_fi(axis, plus, minus);
+			else if(field==FIELD_FLAGS) lbm_domain[d]->enqueue_exchange_flags(axis, plus, minus);
+#ifdef FORCE_FIELD
+			else if(field==FIELD_F) lbm_domain[d]->enqueue_exchange_F(axis, plus, minus);
+#endif
+			else lbm_domain[d]->enqueue_exchange_rho_u_flags(axis, plus, minus);
 		}
 	}
 	rendezvous(); // nobody overwrites what a neighbour is still reading
@@ -308,12 +389,59 @@ void LBM::communicate_field(const bool ddfs, const uint axes) { // x, then y, th
 #ifdef MOVING_BOUNDARIES
 void LBM::update_moving_boundaries() { // src/lbm.cpp:1018-1027
 	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_update_moving_boundaries();
-	if(get_D()>1u) communicate_rho_u_flags(); // the reference exchanges the flags alone; rho and u halos are unchanged copies
+	if(get_D()>1u) communicate_flags();
 	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue();
 }
 #endif
-void LBM::communicate_fi() { communicate_field(true); }
-void LBM::communicate_rho_u_flags() { communicate_field(false); }
+void LBM::communicate_fi() { communicate_field(FIELD_FI); }
+void LBM::communicate_rho_u_flags() { communicate_field(FIELD_RHO_U_FLAGS); }
+void LBM::communicate_flags() { communicate_field(FIELD_FLAGS); }
+#ifdef FORCE_FIELD
+void LBM::communicate_F() { communicate_field(FIELD_F); }
+void LBM::update_force_field() {
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_update_force_field();
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue();
+}
+float3 LBM::object_center_of_mass(const uchar flag_marker) { // per-domain sums, added in domain order
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_object_center_of_mass(flag_marker);
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue();
+	float3 sum(0.0f); ulong cells = 0ull;
+	for(uint d=0u; d<get_D(); d++) { sum += float3(lbm_domain[d]->object_sum.x[0], lbm_domain[d]->object_sum.y[0], lbm_domain[d]->object_sum.z[0]); cells += (ulong)as_uint(lbm_domain[d]->object_sum.w[0]); }
+	return sum/(float)cells;
+}
+float3 LBM::object_force(const uchar flag_marker) {
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_object_force(flag_marker);
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue();
+	float3 sum(0.0f);
+	for(uint d=0u; d<get_D(); d++) sum += float3(lbm_domain[d]->object_sum.x[0], lbm_domain[d]->object_sum.y[0], lbm_domain[d]->object_sum.z[0]);
+	return sum;
+}
+float3 LBM::object_torque(const float3& rotation_center, const uchar flag_marker) {
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_object_torque(rotation_center, flag_marker);
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue();
+	float3 sum(0.0f);
+	for(uint d=0u; d<get_D(); d++) sum += float3(lbm_domain[d]->object_sum.x[0], lbm_domain[d]->object_sum.y[0], lbm_domain[d]->object_sum.z[0]);
+	return sum;
+}
+#endif
+void LBM::voxelize_mesh_on_device(const Mesh* mesh, const uchar flag, const float3& rotation_center, const float3& linear_velocity, const float3& rotational_velocity) {
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->voxelize_mesh_on_device(mesh, flag, rotation_center, linear_velocity, rotational_velocity);
+#ifdef MOVING_BOUNDARIES
+	if((flag&(TYPE_S|TYPE_E))==TYPE_S&&(length(linear_velocity)>0.0f||length(rotational_velocity)>0.0f)) update_moving_boundaries();
+#endif
+	if(!initialized) { flags.read_from_device(); u.read_from_device(); } // so that initialize() does not overwrite the result with the host copies
+}
+void LBM::unvoxelize_mesh_on_device(const Mesh* mesh, const uchar flag) {
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_unvoxelize_mesh_on_device(mesh, flag);
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->finish_queue();
+}
+void LBM::voxelize_stl(const string& path, const float3& center, const float3x3& rotation, const float size, const uchar flag) {
+	const Mesh* mesh = read_stl(path, this->size(), center, rotation, size);
+	flags.write_to_device();
+	voxelize_mesh_on_device(mesh, flag);
+	delete mesh;
+	flags.read_from_device();
+}
 
 void LBM::initialize() {
 #ifndef BENCHMARK
@@ -322,6 +450,10 @@ void LBM::initialize() {
 	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->rho.enqueue_write_to_device();
 	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->u.enqueue_write_to_device();
 	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->flags.enqueue_write_to_device();
+#ifdef FORCE_FIELD
+	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->F.enqueue_write_to_device();
+	if(get_D()>1u) communicate_F();
+#endif
 	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->increment_time_step(); // halo exchange during initialisation runs at an odd step
 	if(get_D()>1u) communicate_rho_u_flags();
 	for(uint d=0u; d<get_D(); d++) lbm_domain[d]->enqueue_initialize();
@@ -338,7 +470,7 @@ void LBM::do_time_step() {
 			lbm_domain[d]->enqueue_stream_collide_fused(table);
 		}
 		rendezvous();
-		if(Dx>1u) communicate_field(true, 1u);
+		if(Dx>1u) communicate_field(FIELD_FI, 1u);
 		for(uint d=0u; d<get_D(); d++) lbm_domain[d]->increment_time_step();
 		return;
 	}

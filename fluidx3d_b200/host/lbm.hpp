@@ -10,6 +10,7 @@
 #include "cuda.hpp"
 #include "units.hpp"
 #include "info.hpp"
+#include "mesh.hpp"
 
 uint bytes_per_cell_host();              // host memory per cell: rho, u, flags
 uint bytes_per_cell_device();            // device memory per cell: fi, rho, u, flags
@@ -24,6 +25,10 @@ class LBM_Domain {
 	ulong t = 0ull;
 	float nu = 1.0f/6.0f, fx = 0.0f, fy = 0.0f, fz = 0.0f;
 	ulong t_last_update_fields = max_ulong;
+#ifdef FORCE_FIELD
+	ulong t_last_force_field = max_ulong;
+	Memory<char> object_scratch; // per-work-group partial sums of the object_* reductions (device only)
+#endif
 	Device device;
 	Memory<char> fi;          // DDFs exist on the device only, in the library's private layout
 	fx3d_lattice lattice;
@@ -31,6 +36,10 @@ public:
 	Memory<float> rho;        // density of every cell
 	Memory<float> u;          // velocity of every cell (x, y, z planes)
 	Memory<uchar> flags;      // flags of every cell
+#ifdef FORCE_FIELD
+	Memory<float> F;          // force on every cell (x, y, z planes)
+	Memory<float> object_sum; // x, y, z, cell count (raw bits) of the last object_* reduction
+#endif
 	Memory<ulong> rendezvous; // 64 counters, written by the neighbouring domains (device side only)
 	Memory<char> staging;     // x faces only: linear buffers [+x | -x] the neighbours pull from (x faces are strided in memory)
 	ulong staging_bytes = 0ull;
@@ -45,6 +54,16 @@ public:
 #ifdef MOVING_BOUNDARIES
 	void enqueue_update_moving_boundaries(); // mark/unmark cells next to TYPE_S cells with velocity!=0 with TYPE_MS
 #endif
+#ifdef FORCE_FIELD
+	void enqueue_update_force_field(); // forces of the fluid on the TYPE_S cells -> F
+	void enqueue_object_center_of_mass(const uchar flag_marker=TYPE_S); // sums over all cells whose flag byte equals flag_marker -> object_sum
+	void enqueue_object_force(const uchar flag_marker=TYPE_S);
+	void enqueue_object_torque(const float3& rotation_center, const uchar flag_marker=TYPE_S);
+	void enqueue_exchange_F(const uint axis, const LBM_Domain& plus, const LBM_Domain& minus);
+#endif
+	void voxelize_mesh_on_device(const Mesh* mesh, const uchar flag=TYPE_S, const float3& rotation_center=float3(0.0f), const float3& linear_velocity=float3(0.0f), const float3& rotational_velocity=float3(0.0f)); // marks the cells inside the mesh
+	void enqueue_unvoxelize_mesh_on_device(const Mesh* mesh, const uchar flag=TYPE_S); // clears `flag` in the bounding box of the mesh
+	void enqueue_exchange_flags(const uint axis, const LBM_Domain& plus, const LBM_Domain& minus);
 	void enqueue_exchange_fi(const uint axis, const LBM_Domain& plus, const LBM_Domain& minus);
 	void enqueue_pack_x_faces(); // stage my outgoing x layers (transfer_extract_fi) before the rendezvous
 	void enqueue_exchange_rho_u_flags(const uint axis, const LBM_Domain& plus, const LBM_Domain& minus);
@@ -92,9 +111,14 @@ class LBM {
 	uint neighbour_yz(const uint d, const int dy, const int dz) const;
 	bool fused_halo = false;           // every domain's shape qualifies for fx3d_stream_collide_fused
 	void rendezvous();                 // all domains meet their face neighbours on the device
-	void communicate_field(const bool ddfs, const uint axes=7u); // axes: bit per axis
+	enum Field { FIELD_FI, FIELD_RHO_U_FLAGS, FIELD_FLAGS, FIELD_F };
+	void communicate_field(const Field field, const uint axes=7u); // axes: bit per axis
 	void communicate_fi();
 	void communicate_rho_u_flags();
+	void communicate_flags(); // one byte per face cell
+#ifdef FORCE_FIELD
+	void communicate_F();
+#endif
 	void construct(const uint Nx, const uint Ny, const uint Nz, const uint Dx, const uint Dy, const uint Dz, const float nu, const float fx, const float fy, const float fz, const float sigma, const float alpha, const float beta, const uint particles_N, const float particles_rho);
 
 public:
@@ -171,6 +195,9 @@ public:
 	Memory_Container<float> rho;
 	Memory_Container<float> u;
 	Memory_Container<uchar> flags;
+#ifdef FORCE_FIELD
+	Memory_Container<float> F;
+#endif
 
 	// same constructor forms as the reference; sigma/alpha/beta/particles exist so that existing calls compile and are
 	// rejected at run time when non-zero (their extensions are not part of this build)
@@ -188,6 +215,19 @@ public:
 	void update_moving_boundaries(); // mark/unmark cells next to TYPE_S cells with velocity!=0 with TYPE_MS (call after changing boundary velocities)
 #endif
 	void reset();
+#ifdef FORCE_FIELD
+	void update_force_field(); // forces of the fluid on the TYPE_S cells -> lbm.F on the device (lbm.F.read_from_device() to look at them)
+	float3 object_center_of_mass(const uchar flag_marker=TYPE_S); // of all cells whose flag byte equals flag_marker
+	float3 object_force(const uchar flag_marker=TYPE_S); // total force of the fluid on those cells
+	float3 object_torque(const float3& rotation_center, const uchar flag_marker=TYPE_S);
+#endif
+	// triangle meshes: GPU voxeliser (the cells inside the closed surface receive `flag`)
+	void voxelize_mesh_on_device(const Mesh* mesh, const uchar flag=TYPE_S, const float3& rotation_center=float3(0.0f), const float3& linear_velocity=float3(0.0f), const float3& rotational_velocity=float3(0.0f));
+	void unvoxelize_mesh_on_device(const Mesh* mesh, const uchar flag=TYPE_S); // only needed when the bounding box changes between re-voxelisations
+	void voxelize_stl(const string& path, const float3& center, const float3x3& rotation, const float size=0.0f, const uchar flag=TYPE_S); // size 0: fit into the box; >0: longest side in cells; <0: scale factor
+	void voxelize_stl(const string& path, const float3x3& rotation, const float size=0.0f, const uchar flag=TYPE_S) { voxelize_stl(path, center(), rotation, size, flag); }
+	void voxelize_stl(const string& path, const float3& center, const float size=0.0f, const uchar flag=TYPE_S) { voxelize_stl(path, center, float3x3(1.0f), size, flag); }
+	void voxelize_stl(const string& path, const float size=0.0f, const uchar flag=TYPE_S) { voxelize_stl(path, center(), float3x3(1.0f), size, flag); }
 
 	uint get_Nx() const { return Nx; }
 	uint get_Ny() const { return Ny; }

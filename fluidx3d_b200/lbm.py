@@ -17,7 +17,7 @@ The C++ twin of this file (what setup.cpp scenes compile against) is fluidx3d_b2
 import ctypes as C
 import numpy as np
 from . import capi
-from .capi import (FP32, FP16S, FP16C, SRT, TRT, VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID, MOVING_BOUNDARIES, TYPE_S, TYPE_E,
+from .capi import (FP32, FP16S, FP16C, SRT, TRT, VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID, MOVING_BOUNDARIES, FORCE_FIELD, TYPE_S, TYPE_E,
                    REGION_ALL, REGION_SHELL, REGION_INTERIOR, Fx3dError)
 
 max_ulong = 2 ** 64 - 1
@@ -82,9 +82,10 @@ class LBM_Domain:
         self.nu, self.fx, self.fy, self.fz = nu, fx, fy, fz
         self.t = 0
         self.t_last_update_fields = max_ulong
+        self.t_last_force_field = max_ulong
         self.velocity_set, self.features = velocity_set, features
         N = self.get_N()
-        self.lat = capi.Lattice(device, Nx, Ny, Nz, Dx, Dy, Dz, velocity_set, collision, storage, features, lib.relaxation_rate(C.c_float(nu)), None, None, None, None)
+        self.lat = capi.Lattice(device, Nx, Ny, Nz, Dx, Dy, Dz, velocity_set, collision, storage, features, lib.relaxation_rate(C.c_float(nu)), None, None, None, None, None)
         # allocate(), src/lbm.cpp:121-129: fi device only; rho (=1), u, flags host+device
         fi_bytes = lib.fi_bytes(C.byref(self.lat))
         self.fi = Memory(lib, device, fi_bytes, 1, np.uint8, alloc_host=False)
@@ -94,6 +95,12 @@ class LBM_Domain:
         if not host_fields:  # benchmark path: default fields (rho=1, u=0, flags=0) are produced on the device
             lib.fill_f32(device, self.rho.device_ptr, C.c_float(1.0), N, stream)
         self.lat.fi, self.lat.rho, self.lat.u, self.lat.flags = self.fi.device_ptr, self.rho.device_ptr, self.u.device_ptr, self.flags.device_ptr
+        self.F, self.object_sum, self.object_scratch = None, None, None
+        if features & FORCE_FIELD:  # src/lbm.cpp:131-141: F (host+device) and object_sum (x, y, z, cell count)
+            self.F = Memory(lib, device, N, 3, np.float32, alloc_host=True)
+            self.object_sum = Memory(lib, device, 1, 4, np.float32, alloc_host=True)
+            self.object_scratch = Memory(lib, device, lib.object_scratch_bytes(C.byref(self.lat)), 1, np.uint8, alloc_host=False)
+            self.lat.F = self.F.device_ptr
         self.sync_array, self.xfer, self.xfer_bytes = None, None, 0
         if Dx * Dy * Dz > 1:  # allocate_transfer(), src/lbm.cpp:1308-1337: the rendezvous counters ...
             p = C.c_void_p()
@@ -120,6 +127,27 @@ class LBM_Domain:
     def enqueue_update_moving_boundaries(self):  # src/lbm.cpp:241-243
         self.lib.update_moving_boundaries(C.byref(self.lat), self.stream)
 
+    # ---- FORCE_FIELD, src/lbm.cpp:206-239 ----
+    def enqueue_update_force_field(self):
+        if self.t != self.t_last_force_field:  # only if the time step has changed since the last update
+            self.lib.update_force_field(C.byref(self.lat), self.t, self.stream)
+            self.t_last_force_field = self.t
+
+    def enqueue_object_center_of_mass(self, flag_marker):
+        self.lib.object_center_of_mass(C.byref(self.lat), flag_marker, self.object_sum.device_ptr, self.object_scratch.device_ptr, self.stream)
+        self.object_sum.enqueue_read_from_device(self.stream)
+
+    def enqueue_object_force(self, flag_marker):
+        self.enqueue_update_force_field()
+        self.lib.object_force(C.byref(self.lat), flag_marker, self.object_sum.device_ptr, self.object_scratch.device_ptr, self.stream)
+        self.object_sum.enqueue_read_from_device(self.stream)
+
+    def enqueue_object_torque(self, rotation_center, flag_marker):
+        self.enqueue_update_force_field()
+        self.lib.object_torque(C.byref(self.lat), flag_marker, C.c_float(rotation_center[0]), C.c_float(rotation_center[1]), C.c_float(rotation_center[2]),
+                               self.object_sum.device_ptr, self.object_scratch.device_ptr, self.stream)
+        self.object_sum.enqueue_read_from_device(self.stream)
+
     def enqueue_update_fields(self):  # src/lbm.cpp:184-191
         if not (self.features & UPDATE_FIELDS) and self.t != self.t_last_update_fields:
             self.lib.update_fields(C.byref(self.lat), self.t, self.fx, self.fy, self.fz, self.stream)
@@ -139,8 +167,8 @@ class LBM_Domain:
         self.lib.stream_sync(self.device, self.stream)
 
     def free(self):
-        for m in (self.fi, self.rho, self.u, self.flags):
-            m.free()
+        for m in (self.fi, self.rho, self.u, self.flags, self.F, self.object_sum, self.object_scratch):
+            if m is not None: m.free()
         if self.sync_array:
             self.lib.free(self.device, self.sync_array); self.sync_array = None
         if self.xfer:
@@ -280,6 +308,7 @@ class LBM:
         self.rho = Memory_Container(self, "rho", 1)
         self.u = Memory_Container(self, "u", 3)
         self.flags = Memory_Container(self, "flags", 1)
+        if features & FORCE_FIELD: self.F = Memory_Container(self, "F", 3)  # src/lbm.hpp:412-414
         self._seq = 0
         self._peers = None
         if D > 1:
@@ -338,9 +367,10 @@ class LBM:
 
     def _connect_peers(self):
         """table d -> {fi, rho, u, flags, sync} device pointers for every domain this process needs to read or signal"""
-        peers = {d: dict(fi=dom.fi.device_ptr, rho=dom.rho.device_ptr, u=dom.u.device_ptr, flags=dom.flags.device_ptr, sync=dom.sync_array, xfer=dom.xfer, device=dom.device)
+        peers = {d: dict(fi=dom.fi.device_ptr, rho=dom.rho.device_ptr, u=dom.u.device_ptr, flags=dom.flags.device_ptr, sync=dom.sync_array, xfer=dom.xfer, device=dom.device,
+                         F=dom.F.device_ptr if dom.F is not None else None)
                  for d, dom in self.lbm_domain.items()}
-        shared = ("fi", "rho", "u", "flags", "sync") + (("xfer",) if self.Dx > 1 else ())
+        shared = ("fi", "rho", "u", "flags", "sync") + (("xfer",) if self.Dx > 1 else ()) + (("F",) if self.features & FORCE_FIELD else ())
         if self.comm is None:
             devs = sorted({dom.device for dom in self.lbm_domain.values()})
             for a in devs:
@@ -403,12 +433,18 @@ class LBM:
                     self.lib.transfer_insert_fi(C.byref(dom.lat), 0, dom.t, p["xfer"] + dom.xfer_bytes, m["xfer"], dom.stream)
                 elif field == "fi":
                     self.lib.exchange_fi(C.byref(dom.lat), axis, dom.t, p["fi"], m["fi"], dom.stream)
+                elif field == "flags":
+                    self.lib.exchange_flags(C.byref(dom.lat), axis, p["flags"], m["flags"], dom.stream)
+                elif field == "F":
+                    self.lib.exchange_F(C.byref(dom.lat), axis, p["F"], m["F"], dom.stream)
                 else:
                     self.lib.exchange_rho_u_flags(C.byref(dom.lat), axis, p["rho"], p["u"], p["flags"], m["rho"], m["u"], m["flags"], dom.stream)
         self._barrier(None)  # every neighbour has finished pulling from me before I overwrite what it read
 
     def communicate_fi(self): self._communicate("fi")  # src/lbm.cpp:1385-1387
     def communicate_rho_u_flags(self): self._communicate("rho_u_flags")  # src/lbm.cpp:1388-1390
+    def communicate_flags(self): self._communicate("flags")  # src/lbm.cpp:1391-1393: one byte per face cell
+    def communicate_F(self): self._communicate("F")  # src/lbm.cpp:1395-1397
 
     # ---- src/lbm.cpp:881-980 ----
     def initialize(self):
@@ -417,6 +453,9 @@ class LBM:
             for _, dom in self.local_domains(): dom.rho.enqueue_write_to_device(dom.stream)
             for _, dom in self.local_domains(): dom.u.enqueue_write_to_device(dom.stream)
             for _, dom in self.local_domains(): dom.flags.enqueue_write_to_device(dom.stream)
+        if self.features & FORCE_FIELD:  # src/lbm.cpp:889-892
+            for _, dom in self.local_domains(): dom.F.enqueue_write_to_device(dom.stream)
+            if self.get_D() > 1: self.communicate_F()
         for _, dom in self.local_domains(): dom.increment_time_step()  # the communicate calls at initialization need an odd time step
         if self.get_D() > 1: self.communicate_rho_u_flags()
         for _, dom in self.local_domains(): dom.enqueue_initialize()
@@ -491,8 +530,47 @@ class LBM:
         if not (self.features & MOVING_BOUNDARIES): raise ValueError("update_moving_boundaries() needs the MOVING_BOUNDARIES extension")
         if self._streams2: self._join_streams()
         for _, dom in self.local_domains(): dom.enqueue_update_moving_boundaries()
-        if self.get_D() > 1: self.communicate_rho_u_flags()  # the reference exchanges the flags alone; rho and u halos are unchanged copies
+        if self.get_D() > 1: self.communicate_flags()
         for _, dom in self.local_domains(): dom.finish_queue()
+
+    # ---- FORCE_FIELD, src/lbm.cpp:986-1016 ----
+    def _need_force_field(self):
+        if not (self.features & FORCE_FIELD): raise ValueError("this call needs the FORCE_FIELD extension")
+        if self._streams2: self._join_streams()
+
+    def update_force_field(self):
+        """forces of the fluid on the TYPE_S cells -> lbm.F on the device (read with lbm.F.read_from_device())"""
+        self._need_force_field()
+        for _, dom in self.local_domains(): dom.enqueue_update_force_field()
+        for _, dom in self.local_domains(): dom.finish_queue()
+
+    def _object_sums(self):
+        for _, dom in self.local_domains(): dom.finish_queue()
+        parts = [(np.array(dom.object_sum.host[:3], np.float32), int(dom.object_sum.host[3:4].view(np.uint32)[0])) for _, dom in self.local_domains()]
+        if self.comm is not None:  # one process per GPU: the per-domain sums are added in domain order, as the reference does
+            parts = [p for rank_parts in self.comm.allgather(parts) for p in rank_parts]
+        total, cells = np.zeros(3, np.float32), 0
+        for v, c in parts:
+            total = (total + v).astype(np.float32); cells += c
+        return total, cells
+
+    def object_center_of_mass(self, flag_marker=TYPE_S):
+        """centre of mass of all cells whose flag byte equals flag_marker (positions local to each domain, as in the reference)"""
+        self._need_force_field()
+        for _, dom in self.local_domains(): dom.enqueue_object_center_of_mass(flag_marker)
+        total, cells = self._object_sums()
+        return total / np.float32(cells)
+
+    def object_force(self, flag_marker=TYPE_S):
+        """total force of the fluid on all cells whose flag byte equals flag_marker"""
+        self._need_force_field()
+        for _, dom in self.local_domains(): dom.enqueue_object_force(flag_marker)
+        return self._object_sums()[0]
+
+    def object_torque(self, rotation_center, flag_marker=TYPE_S):
+        self._need_force_field()
+        for _, dom in self.local_domains(): dom.enqueue_object_torque(rotation_center, flag_marker)
+        return self._object_sums()[0]
 
     # ---- GPU voxeliser, src/lbm.cpp:1074-1145 ----
     def voxelize_mesh_on_device(self, mesh, flag=TYPE_S, rotation_center=None, linear_velocity=(0.0, 0.0, 0.0), rotational_velocity=(0.0, 0.0, 0.0)):
@@ -571,7 +649,7 @@ class LBM:
         if self.comm is not None and getattr(self, "_ipc_opened", None):
             (_, dom), = self.lbm_domain.items()
             for entry in self._ipc_opened.values():
-                for k in ("fi", "rho", "u", "flags", "sync", "xfer"):
+                for k in ("fi", "rho", "u", "flags", "sync", "xfer", "F"):
                     if entry.get(k): self.lib.ipc_close_handle(dom.device, entry[k])
             self._ipc_opened = None
             self.comm.barrier()

@@ -29,9 +29,9 @@ typedef enum fx3d_status {
 
 enum { FX3D_FP32 = 0, FX3D_FP16S = 1, FX3D_FP16C = 2 };                 /* defines.hpp: (none) | FP16S | FP16C */
 enum { FX3D_SRT = 0, FX3D_TRT = 1 };                                    /* defines.hpp: SRT | TRT */
-enum { FX3D_VOLUME_FORCE = 1, FX3D_EQUILIBRIUM_BOUNDARIES = 2, FX3D_UPDATE_FIELDS = 4, FX3D_SUBGRID = 8, FX3D_MOVING_BOUNDARIES = 16 }; /* defines.hpp extension flags on the path;
- * SUBGRID (Smagorinsky-Lilly, kernel.cpp:1579-1593) and MOVING_BOUNDARIES (kernel.cpp:1104-1113,1378-1387,1432-1450) are the first
- * widenings beyond the north_star feature set */
+enum { FX3D_VOLUME_FORCE = 1, FX3D_EQUILIBRIUM_BOUNDARIES = 2, FX3D_UPDATE_FIELDS = 4, FX3D_SUBGRID = 8, FX3D_MOVING_BOUNDARIES = 16, FX3D_FORCE_FIELD = 32 }; /* defines.hpp extension flags on the path;
+ * SUBGRID (Smagorinsky-Lilly, kernel.cpp:1579-1593), MOVING_BOUNDARIES (kernel.cpp:1104-1113,1378-1387,1432-1450) and FORCE_FIELD (kernel.cpp:1497-1503,
+ * 1873-1959) are the widenings beyond the north_star feature set */
 enum { FX3D_REGION_ALL = 0, FX3D_REGION_SHELL = 1, FX3D_REGION_INTERIOR = 2 };
 
 const char* fx3d_last_error(void); /* thread-local, valid until the next failing call on this thread */
@@ -95,6 +95,7 @@ typedef struct fx3d_lattice {
 	float* rho;                /* [N] */
 	float* u;                  /* [3N] SoA */
 	uint8_t* flags;            /* [N] */
+	float* F;                  /* [3N] SoA, FORCE_FIELD lattices only (LBM_Domain::F, lbm.cpp:132); else NULL */
 } fx3d_lattice;
 
 size_t fx3d_fi_bytes(const fx3d_lattice* lattice);                    /* size of the DDF buffer to allocate */
@@ -108,6 +109,18 @@ int fx3d_update_fields(const fx3d_lattice* lattice, uint64_t t, float fx, float 
 /* MOVING_BOUNDARIES: re-mark the cells next to TYPE_S cells with non-zero velocity as TYPE_MS after the boundary velocities
  * changed (kernel update_moving_boundaries, kernel.cpp:1432-1450; LBM::update_moving_boundaries, lbm.cpp:1018-1027) */
 int fx3d_update_moving_boundaries(const fx3d_lattice* lattice, fx3d_stream stream);
+/* FORCE_FIELD (kernels update_force_field / reset_force_field / object_center_of_mass / object_force / object_torque, kernel.cpp:1873-1959;
+ * LBM_Domain::enqueue_update_force_field.. lbm.cpp:206-239): update_force_field writes the force of the fluid on every TYPE_S cell into lattice->F
+ * (boundary forces for lift/drag); with VOLUME_FORCE, stream_collide and update_fields add lattice->F to (fx,fy,fz) cell by cell. The object sums add
+ * position, force or torque about (cx,cy,cz) over the cells whose flag byte EQUALS flag_marker into object_sum (DEVICE, 4 floats: x, y, z, cell count
+ * as raw bits). Where the reference adds its work-group partial sums with floating-point atomics in arbitrary order, the order here is fixed
+ * (ascending), so results are reproducible. scratch: device buffer of fx3d_object_scratch_bytes(). */
+int fx3d_update_force_field(const fx3d_lattice* lattice, uint64_t t, fx3d_stream stream);
+int fx3d_reset_force_field(const fx3d_lattice* lattice, fx3d_stream stream);
+size_t fx3d_object_scratch_bytes(const fx3d_lattice* lattice);
+int fx3d_object_center_of_mass(const fx3d_lattice* lattice, uint8_t flag_marker, float* object_sum, void* scratch, fx3d_stream stream);
+int fx3d_object_force(const fx3d_lattice* lattice, uint8_t flag_marker, float* object_sum, void* scratch, fx3d_stream stream);
+int fx3d_object_torque(const fx3d_lattice* lattice, uint8_t flag_marker, float cx, float cy, float cz, float* object_sum, void* scratch, fx3d_stream stream);
 /* stream_collide over every non-halo cell WITH the y/z part of the halo exchange fused into it (replaces communicate_fi for those axes,
  * lbm.cpp:1355-1387): each DDF row a step writes goes straight to the memory of the domain that reads it in the next step -- this domain's,
  * or a y/z/diagonal neighbour's over NVLink. fi_neighbours[(dy+1)+3*(dz+1)] = DDF buffer of the domain at offset (dy,dz) in the domain grid
@@ -153,6 +166,12 @@ int fx3d_transfer_extract_fi(const fx3d_lattice* lattice, uint32_t axis, uint64_
 int fx3d_transfer_insert_fi(const fx3d_lattice* lattice, uint32_t axis, uint64_t t, const void* buf_p, const void* buf_m, fx3d_stream stream);
 int fx3d_transfer_extract_rho_u_flags(const fx3d_lattice* lattice, uint32_t axis, uint64_t t, void* buf_p, void* buf_m, fx3d_stream stream);
 int fx3d_transfer_insert_rho_u_flags(const fx3d_lattice* lattice, uint32_t axis, uint64_t t, const void* buf_p, const void* buf_m, fx3d_stream stream);
+/* the flags alone, one byte per face cell (transfer_extract_flags / transfer__insert_flags, kernel.cpp:2160-2171), and the force field, three float
+ * planes per side (transfer_extract_F / transfer__insert_F, kernel.cpp:2173-2196) */
+int fx3d_transfer_extract_flags(const fx3d_lattice* lattice, uint32_t axis, uint64_t t, void* buf_p, void* buf_m, fx3d_stream stream);
+int fx3d_transfer_insert_flags(const fx3d_lattice* lattice, uint32_t axis, uint64_t t, const void* buf_p, const void* buf_m, fx3d_stream stream);
+int fx3d_transfer_extract_F(const fx3d_lattice* lattice, uint32_t axis, uint64_t t, void* buf_p, void* buf_m, fx3d_stream stream);
+int fx3d_transfer_insert_F(const fx3d_lattice* lattice, uint32_t axis, uint64_t t, const void* buf_p, const void* buf_m, fx3d_stream stream);
 
 /* direct peer halo exchange of one axis, replacing LBM::communicate_field (lbm.cpp:1355-1383): this domain pulls what
  * the extract/swap/insert sequence would have delivered straight out of its +axis / -axis neighbours' buffers
@@ -162,6 +181,8 @@ int fx3d_exchange_fi(const fx3d_lattice* lattice, uint32_t axis, uint64_t t, con
 int fx3d_exchange_rho_u_flags(const fx3d_lattice* lattice, uint32_t axis,
 	const float* rho_plus, const float* u_plus, const uint8_t* flags_plus,
 	const float* rho_minus, const float* u_minus, const uint8_t* flags_minus, fx3d_stream stream);
+int fx3d_exchange_flags(const fx3d_lattice* lattice, uint32_t axis, const uint8_t* flags_plus, const uint8_t* flags_minus, fx3d_stream stream); /* communicate_flags, lbm.cpp:1391-1393 */
+int fx3d_exchange_F(const fx3d_lattice* lattice, uint32_t axis, const float* F_plus, const float* F_minus, fx3d_stream stream);                /* communicate_F, lbm.cpp:1395-1397 */
 
 /* device-side rendezvous between domains (replaces the finish_queue barriers of lbm.cpp:1357,1366,1375): each domain
  * owns an array of 64-bit counters in device memory, one per peer. signal stores `value` into slot `my_index` of every

@@ -307,7 +307,7 @@ void orc_initialize(const orc_grid* g, void* fi, const float* rho, float* u, uin
 
 /* shared front half of stream_collide / update_fields: load, moments (or preset), force shift, clamp */
 static int cell_front(const orc_grid* g, const void* fi, const float* rho, const float* u, const uint8_t* flags, uint64_t n, uint64_t t,
-	float fx, float fy, float fz, int allow_preset, uint64_t* j, float* fhn, float* rhon, float* uxn, float* uyn, float* uzn, uint8_t* flag_bo) {
+	float* fxp, float* fyp, float* fzp, const float* F, int allow_preset, uint64_t* j, float* fhn, float* rhon, float* uxn, float* uyn, float* uzn, uint8_t* flag_bo) {
 	const uint64_t N = cells_of(g);
 	const xyz_t c = coords_of(g, n);
 	if(halo_cell(g, c)) return 0;
@@ -320,6 +320,9 @@ static int cell_front(const orc_grid* g, const void* fi, const float* rho, const
 	if(allow_preset && (g->features&ORC_EQUILIBRIUM_BOUNDARIES) && fb==TYPE_E) { /* :1482-1493 */
 		*rhon = rho[n]; *uxn = u[n]; *uyn = u[N+n]; *uzn = u[2ull*N+n];
 	} else moments(g, fhn, rhon, uxn, uyn, uzn);
+	float fx = *fxp, fy = *fyp, fz = *fzp; /* :1494 / :1819: the force starts as the constant volume force */
+	if((g->features&ORC_FORCE_FIELD) && F) { fx += F[n]; fy += F[N+n]; fz += F[2ull*N+n]; } /* FORCE_FIELD, :1497-1503 / :1821-1827 */
+	*fxp = fx; *fyp = fy; *fzp = fz;
 	if(g->features&ORC_VOLUME_FORCE) { /* :1552-1555 / :1851-1854 */
 		const float rho2 = 0.5f/(*rhon);
 		*uxn = clamp_c(fmaf(fx, rho2, *uxn)); *uyn = clamp_c(fmaf(fy, rho2, *uyn)); *uzn = clamp_c(fmaf(fz, rho2, *uzn));
@@ -328,7 +331,7 @@ static int cell_front(const orc_grid* g, const void* fi, const float* rho, const
 }
 
 /* ---- stream_collide: src/kernel.cpp:1454-1636 (north_star subset) ---- */
-void orc_stream_collide(const orc_grid* g, void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t, float fx, float fy, float fz) {
+void orc_stream_collide_F(const orc_grid* g, void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t, float fx0, float fy0, float fz0, const float* F) {
 	const uint64_t N = cells_of(g);
 	const uint32_t Q = g->Q;
 	const int eb = (g->features&ORC_EQUILIBRIUM_BOUNDARIES)!=0u, vf = (g->features&ORC_VOLUME_FORCE)!=0u;
@@ -336,7 +339,8 @@ void orc_stream_collide(const orc_grid* g, void* fi, float* rho, float* u, const
 	for(uint64_t n=0ull; n<N; n++) {
 		uint64_t j[QMAX]; float fhn[QMAX], feq[QMAX], Fin[QMAX];
 		float rhon, uxn, uyn, uzn; uint8_t fb;
-		if(!cell_front(g, fi, rho, u, flags, n, t, fx, fy, fz, 1, j, fhn, &rhon, &uxn, &uyn, &uzn, &fb)) continue;
+		float fx = fx0, fy = fy0, fz = fz0;
+		if(!cell_front(g, fi, rho, u, flags, n, t, &fx, &fy, &fz, F, 1, j, fhn, &rhon, &uxn, &uyn, &uzn, &fb)) continue;
 		if(vf) forcing_terms(g, uxn, uyn, uzn, fx, fy, fz, Fin); else for(uint32_t i=0u; i<Q; i++) Fin[i] = 0.0f;
 		const int is_e = eb && fb==TYPE_E;
 		if((g->features&ORC_UPDATE_FIELDS) && !is_e) { rho[n] = rhon; u[n] = uxn; u[N+n] = uyn; u[2ull*N+n] = uzn; } /* :1565-1573 */
@@ -378,20 +382,90 @@ void orc_stream_collide(const orc_grid* g, void* fi, float* rho, float* u, const
 	}
 }
 
+void orc_stream_collide(const orc_grid* g, void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t, float fx, float fy, float fz) {
+	orc_stream_collide_F(g, fi, rho, u, flags, t, fx, fy, fz, NULL);
+}
+
 /* ---- update_fields: src/kernel.cpp:1794-1870 ---- */
-void orc_update_fields(const orc_grid* g, const void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t, float fx, float fy, float fz) {
+void orc_update_fields_F(const orc_grid* g, const void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t, float fx0, float fy0, float fz0, const float* F) {
 	const uint64_t N = cells_of(g);
 	const int eb = (g->features&ORC_EQUILIBRIUM_BOUNDARIES)!=0u;
 	ORC_PARALLEL_FOR
 	for(uint64_t n=0ull; n<N; n++) {
 		uint64_t j[QMAX]; float fhn[QMAX];
 		float rhon, uxn, uyn, uzn; uint8_t fb;
-		if(!cell_front(g, fi, rho, u, flags, n, t, fx, fy, fz, 0, j, fhn, &rhon, &uxn, &uyn, &uzn, &fb)) continue;
+		float fx = fx0, fy = fy0, fz = fz0;
+		if(!cell_front(g, fi, rho, u, flags, n, t, &fx, &fy, &fz, F, 0, j, fhn, &rhon, &uxn, &uyn, &uzn, &fb)) continue;
 		if(eb && fb==TYPE_E) continue; /* :1862-1864 */
 		rho[n] = rhon; u[n] = uxn; u[N+n] = uyn; u[2ull*N+n] = uzn;
 	}
 }
+void orc_update_fields(const orc_grid* g, const void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t, float fx, float fy, float fz) {
+	orc_update_fields_F(g, fi, rho, u, flags, t, fx, fy, fz, NULL);
+}
 
+/* ================================================================================================================
+ * FORCE_FIELD: src/kernel.cpp:1873-1959, host side src/lbm.cpp:206-239,986-1016
+ * ================================================================================================================ */
+/* update_force_field, :1873-1884: force of the fluid on every solid cell = twice the momentum of the populations that stream into it
+   (they are bounced back), via calculate_rho_u -> F = 2*Fb*(fx,fy,fz) with Fb the "density" and f the "velocity" */
+void orc_update_force_field(const orc_grid* g, const void* fi, const uint8_t* flags, uint64_t t, float* F) {
+	const uint64_t N = cells_of(g);
+	ORC_PARALLEL_FOR
+	for(uint64_t n=0ull; n<N; n++) {
+		const xyz_t c = coords_of(g, n);
+		if(halo_cell(g, c)) continue;
+		if((flags[n]&TYPE_BO)!=TYPE_S) continue;
+		uint64_t j[QMAX]; float fhn[QMAX];
+		neighbours_of(g, n, j);
+		pull_ddfs(g, n, fhn, fi, j, t);
+		float Fb, fx, fy, fz;
+		moments(g, fhn, &Fb, &fx, &fy, &fz);
+		const float s = 2.0f*Fb; /* 2.0f*Fb*(float3)(fx,fy,fz): scalar product first, then scalar times vector */
+		F[n] = s*fx; F[N+n] = s*fy; F[2ull*N+n] = s*fz;
+	}
+}
+void orc_reset_force_field(const orc_grid* g, float* F) { /* :1885-1889, halo included */
+	const uint64_t N = cells_of(g);
+	for(uint64_t n=0ull; n<3ull*N; n++) F[n] = 0.0f;
+}
+/* object_center_of_mass / object_force / object_torque, :1901-1959. The reference reduces 3 floats per work-group in local memory with a
+   stride-doubling tree (cache[lid] += cache[lid+s] for lid%(2s)==0, s = 1,2,4,..) and then adds the group results into object_sum with
+   floating-point ATOMICS, i.e. in no defined order. The oracle fixes that order: the same tree per group of `group` consecutive cells
+   (cl_workgroup_size), then the non-zero group sums added in ascending group order. The reference's result is one of the orderings of the
+   same group sums; tests compare against it with a tolerance and against this function bit for bit. kind: 0 centre of mass (out[3] = cell
+   count as raw bits), 1 force, 2 torque about (cx,cy,cz). position() = coordinates + 0.5 - 0.5*N (:827-829), local to the domain. */
+static void tree_reduce3(float* cache, uint32_t group) {
+	for(uint32_t s=1u; s<group; s*=2u) for(uint32_t lid=0u; lid+s<group; lid+=2u*s) { cache[3u*lid] += cache[3u*(lid+s)]; cache[3u*lid+1u] += cache[3u*(lid+s)+1u]; cache[3u*lid+2u] += cache[3u*(lid+s)+2u]; }
+}
+void orc_object_sum(const orc_grid* g, uint32_t kind, const float* F, const uint8_t* flags, uint8_t flag_marker, float cx, float cy, float cz, uint32_t group, float* out4) {
+	const uint64_t N = cells_of(g);
+	float sum[3] = { 0.0f, 0.0f, 0.0f }; uint32_t count = 0u;
+	float* cache = (float*)malloc(sizeof(float)*3u*group);
+	for(uint64_t base=0ull; base<N; base+=group) { /* one work-group; the NDRange is padded to a multiple of the group size with idle items */
+		uint32_t cells = 0u;
+		for(uint32_t lid=0u; lid<group; lid++) {
+			const uint64_t n = base+lid;
+			float v[3] = { 0.0f, 0.0f, 0.0f };
+			if(n<N && flags[n]==flag_marker) {
+				const xyz_t c = coords_of(g, n);
+				const float px = (float)c.x+0.5f-0.5f*(float)g->Nx, py = (float)c.y+0.5f-0.5f*(float)g->Ny, pz = (float)c.z+0.5f-0.5f*(float)g->Nz;
+				if(kind==0u) { v[0] = px; v[1] = py; v[2] = pz; cells++; }
+				else if(kind==1u) { v[0] = F[n]; v[1] = F[N+n]; v[2] = F[2ull*N+n]; }
+				else { /* cross(position-centre, F), src/kernel.cpp:1947 */
+					const float rx = px-cx, ry = py-cy, rz = pz-cz, Fx = F[n], Fy = F[N+n], Fz = F[2ull*N+n];
+					v[0] = ry*Fz-rz*Fy; v[1] = rz*Fx-rx*Fz; v[2] = rx*Fy-ry*Fx;
+				}
+			}
+			cache[3u*lid] = v[0]; cache[3u*lid+1u] = v[1]; cache[3u*lid+2u] = v[2];
+		}
+		tree_reduce3(cache, group);
+		if(kind==0u) { if(cells>0u) { sum[0] += cache[0]; sum[1] += cache[1]; sum[2] += cache[2]; count += cells; } }
+		else { if(cache[0]!=0.0f) sum[0] += cache[0]; if(cache[1]!=0.0f) sum[1] += cache[1]; if(cache[2]!=0.0f) sum[2] += cache[2]; }
+	}
+	free(cache);
+	out4[0] = sum[0]; out4[1] = sum[1]; out4[2] = sum[2]; out4[3] = float_of(count);
+}
 /* ---- halo transfer: src/kernel.cpp:2049-2158, host side src/lbm.cpp:1308-1354 ---- */
 uint32_t orc_transfers(const orc_grid* g) { return g->Q==19u ? 5u : 9u; } /* src/lbm.cpp:7-23 */
 uint64_t orc_area(const orc_grid* g, uint32_t axis) {
@@ -483,6 +557,24 @@ void orc_transfer_insert_rho_u_flags(const orc_grid* g, uint32_t axis, uint64_t 
 	for(uint64_t a=0ull; a<A; a++) {
 		insert_ruf(a, A, face_cell(g, axis, a, L-1u), N, buf_p, rho, u, flags);
 		insert_ruf(a, A, face_cell(g, axis, a, 0u   ), N, buf_m, rho, u, flags);
+	}
+}
+
+/* transfer_extract_F / transfer__insert_F, :2173-2196: three float planes per side */
+void orc_transfer_extract_F(const orc_grid* g, uint32_t axis, uint64_t t, void* buf_p, void* buf_m, const float* F) {
+	const uint64_t A = orc_area(g, axis), N = cells_of(g); const uint32_t L = axis_len(g, axis);
+	(void)t;
+	for(uint64_t a=0ull; a<A; a++) {
+		const uint64_t np = face_cell(g, axis, a, L-2u), nm = face_cell(g, axis, a, 1u);
+		for(uint64_t k=0ull; k<3ull; k++) { ((float*)buf_p)[k*A+a] = F[k*N+np]; ((float*)buf_m)[k*A+a] = F[k*N+nm]; }
+	}
+}
+void orc_transfer_insert_F(const orc_grid* g, uint32_t axis, uint64_t t, const void* buf_p, const void* buf_m, float* F) {
+	const uint64_t A = orc_area(g, axis), N = cells_of(g); const uint32_t L = axis_len(g, axis);
+	(void)t;
+	for(uint64_t a=0ull; a<A; a++) {
+		const uint64_t np = face_cell(g, axis, a, L-1u), nm = face_cell(g, axis, a, 0u);
+		for(uint64_t k=0ull; k<3ull; k++) { F[k*N+np] = ((const float*)buf_p)[k*A+a]; F[k*N+nm] = ((const float*)buf_m)[k*A+a]; }
 	}
 }
 

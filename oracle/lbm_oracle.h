@@ -24,7 +24,7 @@ extern "C" {
 
 enum { ORC_FP32 = 0, ORC_FP16S = 1, ORC_FP16C = 2 };
 enum { ORC_SRT = 0, ORC_TRT = 1 };
-enum { ORC_VOLUME_FORCE = 1u, ORC_EQUILIBRIUM_BOUNDARIES = 2u, ORC_UPDATE_FIELDS = 4u, ORC_SUBGRID = 8u, ORC_MOVING_BOUNDARIES = 16u };
+enum { ORC_VOLUME_FORCE = 1u, ORC_EQUILIBRIUM_BOUNDARIES = 2u, ORC_UPDATE_FIELDS = 4u, ORC_SUBGRID = 8u, ORC_MOVING_BOUNDARIES = 16u, ORC_FORCE_FIELD = 32u };
 
 /* One LBM_Domain worth of compile-time constants of the reference (src/lbm.cpp:334-425), made run-time. */
 typedef struct orc_grid {
@@ -51,6 +51,15 @@ int   orc_float_to_string(float x, char* out, int cap);
 void orc_initialize(const orc_grid* g, void* fi, const float* rho, float* u, uint8_t* flags);
 void orc_stream_collide(const orc_grid* g, void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t, float fx, float fy, float fz);
 void orc_update_fields(const orc_grid* g, const void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t, float fx, float fy, float fz);
+/* FORCE_FIELD: the same two kernels with the per-cell force F (float[3N] SoA) added to (fx,fy,fz), src/kernel.cpp:1497-1503,1821-1827 */
+void orc_stream_collide_F(const orc_grid* g, void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t, float fx, float fy, float fz, const float* F);
+void orc_update_fields_F(const orc_grid* g, const void* fi, float* rho, float* u, const uint8_t* flags, uint64_t t, float fx, float fy, float fz, const float* F);
+void orc_update_force_field(const orc_grid* g, const void* fi, const uint8_t* flags, uint64_t t, float* F); /* src/kernel.cpp:1873-1884 */
+void orc_reset_force_field(const orc_grid* g, float* F);                                                     /* :1885-1889 */
+/* object_center_of_mass (kind 0) / object_force (1) / object_torque (2), :1901-1959, with the reduction order fixed (see lbm_oracle.c); out4 = x,y,z,count bits */
+void orc_object_sum(const orc_grid* g, uint32_t kind, const float* F, const uint8_t* flags, uint8_t flag_marker, float cx, float cy, float cz, uint32_t group, float* out4);
+void orc_transfer_extract_F(const orc_grid* g, uint32_t axis, uint64_t t, void* buf_p, void* buf_m, const float* F); /* :2173-2196 */
+void orc_transfer_insert_F(const orc_grid* g, uint32_t axis, uint64_t t, const void* buf_p, const void* buf_m, float* F);
 /* MOVING_BOUNDARIES: mark / unmark the cells next to TYPE_S cells with non-zero velocity as TYPE_MS (src/kernel.cpp:1432-1450) */
 void orc_update_moving_boundaries(const orc_grid* g, const float* u, uint8_t* flags);
 

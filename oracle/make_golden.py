@@ -53,6 +53,14 @@ def main():
                             out_rho=o_rho, out_u=np.stack([o_ux, o_uy, o_uz]), out_flags=o_flags,
                             out_fi=np.stack([d.fi for d in sim.dom]))
         print("wrote", case_name(Q, coll, st, feat, dims, D, steps))
+    # FORCE_FIELD: the scenario, the sequence and the outputs of tests/test_force_field.run_host, from the reference's device code
+    import test_force_field as T
+    for v, dims, D, steps, seed in [((19, SRT, FP32, 33), (12, 10, 8), (1, 1, 1), 5, 21), ((19, TRT, FP16S, 35), (12, 10, 8), (2, 1, 2), 4, 22),
+                                    ((27, SRT, FP16C, 33), (12, 10, 8), (1, 2, 1), 4, 23), ((19, SRT, FP32, 34), (12, 10, 8), (1, 1, 1), 5, 24)]:
+        _, out = T.run_host(RefBackend, v, dims, D, steps, seed)
+        name = f"ff_{ref_variant_name(*v)}_{dims[0]}x{dims[1]}x{dims[2]}_d{D[0]}{D[1]}{D[2]}_t{steps}"
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=np.array([*v, *dims, *D, steps, seed], dtype=np.int64), **{f"out{k}": np.asarray(x) for k, x in enumerate(out)})
+        print("wrote", name)
     # storage codec known-answer vectors from the reference's device converters (src/kernel.cpp:848-859)
     b = RefBackend(19, SRT, FP16C, 0)
     codes = np.arange(65536, dtype=np.uint32)

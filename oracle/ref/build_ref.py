@@ -11,7 +11,7 @@ plus a tiny NDRange driver.
 
 usage: build_ref.py [--reference /root/reference] [--variants q19_srt_fp32_f0,...]
 Variant name: q<19|27>_<srt|trt>_<fp32|fp16s|fp16c>_f<mask>  (mask bit0 VOLUME_FORCE, bit1 EQUILIBRIUM_BOUNDARIES,
-bit2 UPDATE_FIELDS, bit3 SUBGRID, bit4 MOVING_BOUNDARIES)
+bit2 UPDATE_FIELDS, bit3 SUBGRID, bit4 MOVING_BOUNDARIES, bit5 FORCE_FIELD)
 """
 import argparse, os, re, subprocess, sys
 from concurrent.futures import ThreadPoolExecutor
@@ -26,6 +26,7 @@ DEFAULT_VARIANTS = [
     "q27_srt_fp32_f0", "q27_trt_fp32_f3", "q27_srt_fp16s_f0", "q27_trt_fp16c_f3",
     "q19_srt_fp32_f8", "q19_trt_fp16s_f11", "q27_srt_fp16c_f8", "q19_srt_fp16s_f8",  # bit3: SUBGRID (first "next" row of SURVEY 8f)
     "q19_srt_fp32_f16", "q19_trt_fp16s_f19", "q27_srt_fp16c_f18", "q19_srt_fp16s_f24",  # bit4: MOVING_BOUNDARIES
+    "q19_srt_fp32_f33", "q19_trt_fp16s_f35", "q27_srt_fp16c_f33", "q19_srt_fp32_f34",  # bit5: FORCE_FIELD (with and without VOLUME_FORCE)
 ]
 
 # functions on the hot path; everything else in the program text is dropped
@@ -37,7 +38,9 @@ WANTED = [
     "extract_fi", "insert_fi", "transfer_extract_fi", "transfer__insert_fi",
     "extract_rho_u_flags", "insert_rho_u_flags", "transfer_extract_rho_u_flags", "transfer__insert_rho_u_flags",
     "position", "voxelize_mesh", "unvoxelize_mesh",
+    "update_force_field", "reset_force_field", "extract_F", "insert_F", "transfer_extract_F", "transfer__insert_F",  # SURVEY 8f rank 4 (FORCE_FIELD builds only)
 ]
+FORCE_FIELD_ONLY = ("update_force_field", "reset_force_field", "extract_F", "insert_F", "transfer_extract_F", "transfer__insert_F")
 
 
 def prologue(q, coll, storage, mask):
@@ -70,6 +73,7 @@ def prologue(q, coll, storage, mask):
     if mask & 4: d.append("#define UPDATE_FIELDS")
     if mask & 8: d.append("#define SUBGRID")
     if mask & 16: d.append("#define MOVING_BOUNDARIES")
+    if mask & 32: d.append("#define FORCE_FIELD")
     return "\n".join(d) + "\n"
 
 
@@ -105,8 +109,18 @@ uint ref_bytes_per_ddf() { return (uint)sizeof(fpxx); }
 #define NDRANGE(range, call) _Pragma("omp parallel for schedule(static) num_threads(ref_get_threads())") \
 	for(ulong gid=0ul; gid<(ulong)(range); gid++) { g_gid = gid; call; }
 void ref_initialize(void* fi, const float* rho, float* u, uchar* flags) { NDRANGE(g_N, initialize((fpxx*)fi, rho, u, flags)) }
+#ifndef FORCE_FIELD
 void ref_stream_collide(void* fi, float* rho, float* u, uchar* flags, ulong t, float fx, float fy, float fz) { NDRANGE(g_N, stream_collide((fpxx*)fi, rho, u, flags, t, fx, fy, fz)) }
 void ref_update_fields(const void* fi, float* rho, float* u, const uchar* flags, ulong t, float fx, float fy, float fz) { NDRANGE(g_N, update_fields((const fpxx*)fi, rho, u, flags, t, fx, fy, fz)) }
+#else // FORCE_FIELD: the kernels take the force field as an extra argument (src/kernel.cpp:1455-1457,1795-1797); the object_* reductions are left out
+// (work-group local memory and barriers; their floating-point atomics make the reference's own result order-dependent anyway)
+void ref_stream_collide_F(void* fi, float* rho, float* u, uchar* flags, ulong t, float fx, float fy, float fz, const float* F) { NDRANGE(g_N, stream_collide((fpxx*)fi, rho, u, flags, t, fx, fy, fz, F)) }
+void ref_update_fields_F(const void* fi, float* rho, float* u, const uchar* flags, ulong t, float fx, float fy, float fz, const float* F) { NDRANGE(g_N, update_fields((const fpxx*)fi, rho, u, flags, t, fx, fy, fz, F)) }
+void ref_update_force_field(const void* fi, const uchar* flags, ulong t, float* F) { NDRANGE(g_N, update_force_field((const fpxx*)fi, flags, t, F)) }
+void ref_reset_force_field(float* F) { NDRANGE(g_N, reset_force_field(F)) }
+void ref_transfer_extract_F(uint direction, ulong t, void* bp, void* bm, const float* F) { NDRANGE(get_area(direction), transfer_extract_F(direction, t, (float*)bp, (float*)bm, F)) }
+void ref_transfer_insert_F(uint direction, ulong t, const void* bp, const void* bm, float* F) { NDRANGE(get_area(direction), transfer__insert_F(direction, t, (const float*)bp, (const float*)bm, F)) }
+#endif
 void ref_transfer_extract_fi(uint direction, ulong t, void* bp, void* bm, const void* fi) { NDRANGE(get_area(direction), transfer_extract_fi(direction, t, (fpxx_copy*)bp, (fpxx_copy*)bm, (const fpxx_copy*)fi)) }
 void ref_transfer_insert_fi(uint direction, ulong t, const void* bp, const void* bm, void* fi) { NDRANGE(get_area(direction), transfer__insert_fi(direction, t, (const fpxx_copy*)bp, (const fpxx_copy*)bm, (fpxx_copy*)fi)) }
 void ref_transfer_extract_rho_u_flags(uint direction, ulong t, void* bp, void* bm, const float* rho, const float* u, const uchar* flags) { NDRANGE(get_area(direction), transfer_extract_rho_u_flags(direction, t, (char*)bp, (char*)bm, rho, u, flags)) }
@@ -139,6 +153,8 @@ def build_variant(name, cl_path):
         if fn == "calculate_forcing_terms" and not (mask & 1):
             continue
         if fn in ("apply_moving_boundaries", "update_moving_boundaries") and not (mask & 16):
+            continue
+        if fn in FORCE_FIELD_ONLY and not (mask & 32):
             continue
         if fn not in funcs:
             raise SystemExit(f"{name}: function {fn} not found in the reference program text")

@@ -28,6 +28,7 @@ static inline float3 make_float3(float x, float y, float z) { return float3{ x, 
 // plain expressions (the same ones the reference's host-side float3 uses, src/utilities.hpp:1020-1025)
 static inline float3 operator+(const float3 a, const float3 b) { return float3{ a.x+b.x, a.y+b.y, a.z+b.z }; }
 static inline float3 operator-(const float3 a, const float3 b) { return float3{ a.x-b.x, a.y-b.y, a.z-b.z }; }
+static inline float3 operator*(const float s, const float3 a) { return float3{ s*a.x, s*a.y, s*a.z }; } // scalar times vector (update_force_field, src/kernel.cpp:1883)
 static inline float3 cross(const float3 a, const float3 b) { return float3{ a.y*b.z-a.z*b.y, a.z*b.x-a.x*b.z, a.x*b.y-a.y*b.x }; }
 static inline float dot(const float3 a, const float3 b) { return a.x*b.x+a.y*b.y+a.z*b.z; }
 static inline int clamp(const int x, const int lo, const int hi) { return x<lo ? lo : x>hi ? hi : x; }

@@ -13,7 +13,7 @@ REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 FP32, FP16S, FP16C = 0, 1, 2
 SRT, TRT = 0, 1
-VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID, MOVING_BOUNDARIES = 1, 2, 4, 8, 16
+VOLUME_FORCE, EQUILIBRIUM_BOUNDARIES, UPDATE_FIELDS, SUBGRID, MOVING_BOUNDARIES, FORCE_FIELD = 1, 2, 4, 8, 16, 32
 TYPE_MS = 3
 TYPE_S, TYPE_E = 1, 2
 STORAGE_NAMES = {FP32: "fp32", FP16S: "fp16s", FP16C: "fp16c"}
@@ -70,11 +70,32 @@ class OracleBackend:
     def initialize(self, fi, rho, u, flags):
         self.lib.orc_initialize(C.byref(self.g), _p(fi), _p(rho), _p(u), _p(flags))
 
-    def stream_collide(self, fi, rho, u, flags, t, fx=0.0, fy=0.0, fz=0.0):
-        self.lib.orc_stream_collide(C.byref(self.g), _p(fi), _p(rho), _p(u), _p(flags), C.c_uint64(t), C.c_float(fx), C.c_float(fy), C.c_float(fz))
+    def stream_collide(self, fi, rho, u, flags, t, fx=0.0, fy=0.0, fz=0.0, F=None):
+        if F is not None: self.lib.orc_stream_collide_F(C.byref(self.g), _p(fi), _p(rho), _p(u), _p(flags), C.c_uint64(t), C.c_float(fx), C.c_float(fy), C.c_float(fz), _p(F))
+        else: self.lib.orc_stream_collide(C.byref(self.g), _p(fi), _p(rho), _p(u), _p(flags), C.c_uint64(t), C.c_float(fx), C.c_float(fy), C.c_float(fz))
 
-    def update_fields(self, fi, rho, u, flags, t, fx=0.0, fy=0.0, fz=0.0):
-        self.lib.orc_update_fields(C.byref(self.g), _p(fi), _p(rho), _p(u), _p(flags), C.c_uint64(t), C.c_float(fx), C.c_float(fy), C.c_float(fz))
+    def update_fields(self, fi, rho, u, flags, t, fx=0.0, fy=0.0, fz=0.0, F=None):
+        if F is not None: self.lib.orc_update_fields_F(C.byref(self.g), _p(fi), _p(rho), _p(u), _p(flags), C.c_uint64(t), C.c_float(fx), C.c_float(fy), C.c_float(fz), _p(F))
+        else: self.lib.orc_update_fields(C.byref(self.g), _p(fi), _p(rho), _p(u), _p(flags), C.c_uint64(t), C.c_float(fx), C.c_float(fy), C.c_float(fz))
+
+    # FORCE_FIELD
+    def update_force_field(self, fi, flags, t, F):
+        self.lib.orc_update_force_field(C.byref(self.g), _p(fi), _p(flags), C.c_uint64(t), _p(F))
+
+    def reset_force_field(self, F):
+        self.lib.orc_reset_force_field(C.byref(self.g), _p(F))
+
+    def object_sum(self, kind, F, flags, marker, center=(0.0, 0.0, 0.0), group=64):
+        """kind 0 centre of mass, 1 force, 2 torque; returns float32[4] (x, y, z, cell count as raw bits)"""
+        out = np.zeros(4, np.float32)
+        self.lib.orc_object_sum(C.byref(self.g), C.c_uint32(kind), _p(F) if F is not None else None, _p(flags), C.c_uint8(marker), C.c_float(center[0]), C.c_float(center[1]), C.c_float(center[2]), C.c_uint32(group), _p(out))
+        return out
+
+    def extract_F(self, axis, t, bp, bm, F):
+        self.lib.orc_transfer_extract_F(C.byref(self.g), C.c_uint32(axis), C.c_uint64(t), _p(bp), _p(bm), _p(F))
+
+    def insert_F(self, axis, t, bp, bm, F):
+        self.lib.orc_transfer_insert_F(C.byref(self.g), C.c_uint32(axis), C.c_uint64(t), _p(bp), _p(bm), _p(F))
 
     def update_moving_boundaries(self, u, flags):
         self.lib.orc_update_moving_boundaries(C.byref(self.g), _p(u), _p(flags))
@@ -124,11 +145,25 @@ class RefBackend:
     def initialize(self, fi, rho, u, flags):
         self.lib.ref_initialize(_p(fi), _p(rho), _p(u), _p(flags))
 
-    def stream_collide(self, fi, rho, u, flags, t, fx=0.0, fy=0.0, fz=0.0):
-        self.lib.ref_stream_collide(_p(fi), _p(rho), _p(u), _p(flags), C.c_uint64(t), C.c_float(fx), C.c_float(fy), C.c_float(fz))
+    def stream_collide(self, fi, rho, u, flags, t, fx=0.0, fy=0.0, fz=0.0, F=None):
+        if self.features & FORCE_FIELD: self.lib.ref_stream_collide_F(_p(fi), _p(rho), _p(u), _p(flags), C.c_uint64(t), C.c_float(fx), C.c_float(fy), C.c_float(fz), _p(F))
+        else: self.lib.ref_stream_collide(_p(fi), _p(rho), _p(u), _p(flags), C.c_uint64(t), C.c_float(fx), C.c_float(fy), C.c_float(fz))
 
-    def update_fields(self, fi, rho, u, flags, t, fx=0.0, fy=0.0, fz=0.0):
-        self.lib.ref_update_fields(_p(fi), _p(rho), _p(u), _p(flags), C.c_uint64(t), C.c_float(fx), C.c_float(fy), C.c_float(fz))
+    def update_fields(self, fi, rho, u, flags, t, fx=0.0, fy=0.0, fz=0.0, F=None):
+        if self.features & FORCE_FIELD: self.lib.ref_update_fields_F(_p(fi), _p(rho), _p(u), _p(flags), C.c_uint64(t), C.c_float(fx), C.c_float(fy), C.c_float(fz), _p(F))
+        else: self.lib.ref_update_fields(_p(fi), _p(rho), _p(u), _p(flags), C.c_uint64(t), C.c_float(fx), C.c_float(fy), C.c_float(fz))
+
+    def update_force_field(self, fi, flags, t, F):
+        self.lib.ref_update_force_field(_p(fi), _p(flags), C.c_uint64(t), _p(F))
+
+    def reset_force_field(self, F):
+        self.lib.ref_reset_force_field(_p(F))
+
+    def extract_F(self, axis, t, bp, bm, F):
+        self.lib.ref_transfer_extract_F(C.c_uint32(axis), C.c_uint64(t), _p(bp), _p(bm), _p(F))
+
+    def insert_F(self, axis, t, bp, bm, F):
+        self.lib.ref_transfer_insert_F(C.c_uint32(axis), C.c_uint64(t), _p(bp), _p(bm), _p(F))
 
     def update_moving_boundaries(self, u, flags):
         self.lib.ref_update_moving_boundaries(_p(u), _p(flags))
@@ -151,7 +186,8 @@ class RefBackend:
 
 
 class Domain:
-    def __init__(self, N, Q, storage):
+    def __init__(self, N, Q, storage, force_field=False):
+        self.F = np.zeros(3 * N, dtype=np.float32) if force_field else None  # src/lbm.cpp:132
         self.fi = np.zeros(Q * N, dtype=ddf_dtype(storage))
         self.rho = np.ones(N, dtype=np.float32)          # src/lbm.cpp:124
         self.u = np.zeros(3 * N, dtype=np.float32)
@@ -175,11 +211,13 @@ class HostSim:
         self.f = (fx, fy, fz)
         self.t = 0
         self.initialized = False
-        self.dom = [Domain(self.lN, backend.Q, backend.storage) for _ in range(self.D)]
+        self.ff = bool(backend.features & FORCE_FIELD)
+        self.t_last_force_field = None
+        self.dom = [Domain(self.lN, backend.Q, backend.storage, self.ff) for _ in range(self.D)]
         if self.D > 1:
             A = max([self.lNy * self.lNz] * self.Hx + [self.lNz * self.lNx] * self.Hy + [self.lNx * self.lNy] * self.Hz)
             T = 5 if backend.Q == 19 else 9
-            per = max(T * (4 if backend.storage == FP32 else 2), 17)   # src/lbm.cpp:1314-1315
+            per = max(T * (4 if backend.storage == FP32 else 2), 17)   # src/lbm.cpp:1314-1315 (17 >= the 12 bytes of F)
             for d in self.dom:
                 d.buf_p = np.zeros(A * per, dtype=np.uint8)
                 d.buf_m = np.zeros(A * per, dtype=np.uint8)
@@ -220,6 +258,8 @@ class HostSim:
             for d in self.dom:
                 if field == "fi":
                     self.b.extract_fi(axis, self.t, d.buf_p, d.buf_m, d.fi)
+                elif field == "F":
+                    self.b.extract_F(axis, self.t, d.buf_p, d.buf_m, d.F)
                 else:
                     self.b.extract_ruf(axis, self.t, d.buf_p, d.buf_m, d.rho, d.u, d.flags)
             for di in range(self.D):
@@ -231,10 +271,13 @@ class HostSim:
             for d in self.dom:
                 if field == "fi":
                     self.b.insert_fi(axis, self.t, d.buf_p, d.buf_m, d.fi)
+                elif field == "F":
+                    self.b.insert_F(axis, self.t, d.buf_p, d.buf_m, d.F)
                 else:
                     self.b.insert_ruf(axis, self.t, d.buf_p, d.buf_m, d.rho, d.u, d.flags)
 
     def initialize(self):  # src/lbm.cpp:881-922
+        if self.ff: self._communicate("F")  # :889-892
         self.t = 1
         self._communicate("ruf")
         for d in self.dom:
@@ -249,7 +292,7 @@ class HostSim:
             self.initialize()
         for _ in range(steps):
             for d in self.dom:
-                self.b.stream_collide(d.fi, d.rho, d.u, d.flags, self.t, *self.f)
+                self.b.stream_collide(d.fi, d.rho, d.u, d.flags, self.t, *self.f, **({"F": d.F} if self.ff else {}))
             self._communicate("fi")
             self.t += 1
 
@@ -272,7 +315,23 @@ class HostSim:
 
     def update_fields(self):  # src/lbm.cpp:977-980
         for d in self.dom:
-            self.b.update_fields(d.fi, d.rho, d.u, d.flags, self.t, *self.f)
+            self.b.update_fields(d.fi, d.rho, d.u, d.flags, self.t, *self.f, **({"F": d.F} if self.ff else {}))
+
+    # ---- FORCE_FIELD, src/lbm.cpp:206-239,986-1016 ----
+    def update_force_field(self):
+        if self.t != self.t_last_force_field:  # :207-211
+            for d in self.dom:
+                self.b.update_force_field(d.fi, d.flags, self.t, d.F)
+            self.t_last_force_field = self.t
+
+    def object_sum(self, kind, marker, center=(0.0, 0.0, 0.0), group=64):
+        """LBM::object_center_of_mass / object_force / object_torque: per-domain sums added in domain order (:992-1015); oracle backend only"""
+        if kind != 0: self.update_force_field()
+        parts = [self.b.object_sum(kind, d.F, d.flags, marker, center, group) for d in self.dom]
+        tot = np.zeros(3, np.float32); cells = 0
+        for p in parts:
+            tot = (tot + p[:3]).astype(np.float32); cells += int(p[3:4].view(np.uint32)[0])
+        return (tot / np.float32(cells)).astype(np.float32) if kind == 0 else tot
 
     def fields(self):
         """(rho, ux, uy, uz, flags) on the global grid after update_fields (what lbm.u.read_from_device() returns)"""

@@ -12,6 +12,10 @@
 //   FX3D_REF_BENCH  if set: after FX3D_REF_STEPS warm-up steps time this many steps with the host clock and print MLUPs/s
 //   FX3D_REF_MB     "z,uy": MOVING_BOUNDARIES builds: after half the steps set u.y of the TYPE_S cells in plane z to uy and call
 //                   update_moving_boundaries() (exercises src/lbm.cpp:1018-1027)
+//   FX3D_REF_STL    "path,size": before initialisation voxelise the binary STL file with lbm.voxelize_stl(path, lbm.center(), R, size, TYPE_S|TYPE_X),
+//                   R = rotation by atan2(0.6,0.8) about x (src/lbm.cpp:1130-1135: read_stl, flags to the device, kernel voxelize_mesh, flags back)
+//   FX3D_REF_FF     "1": FORCE_FIELD builds: after the steps append to the output the force field F (x, y, z planes, after update_force_field) and 9
+//                   floats: object_force, object_center_of_mass and object_torque (about the box centre) of the cells flagged TYPE_S|TYPE_X
 #include "setup.hpp"
 #include <cstdio>
 #include <cstdlib>
@@ -43,14 +47,20 @@ void main_setup() {
 	LBM lbm(Nx, Ny, Nz, (uint)D[0], (uint)D[1], (uint)D[2], nu);
 #endif
 	const ulong N = lbm.get_N();
-	if(fin) {
+	const string stl = env_or("FX3D_REF_STL", "");
+	if(stl!="") { // geometry first, as the reference's scenes do: voxelize_stl() before initialisation reads flags AND u back from the device (src/lbm.cpp:1084-1087)
+		const size_t comma = stl.find(',');
+		const float3x3 R(1.0f, 0.0f, 0.0f, 0.0f, 0.8f, -0.6f, 0.0f, 0.6f, 0.8f);
+		lbm.voxelize_stl(stl.substr(0u, comma), lbm.center(), R, (float)atof(stl.substr(comma+1u).c_str()), TYPE_S|TYPE_X);
+	}
+	if(fin) { // the input fields go to every cell outside the voxelised body
 		vector<float> buf(N);
-		if(fread(buf.data(), 4, N, fin)!=N) print_error("short rho"); for(ulong n=0ull; n<N; n++) lbm.rho[n] = buf[n];
-		if(fread(buf.data(), 4, N, fin)!=N) print_error("short ux");  for(ulong n=0ull; n<N; n++) lbm.u.x[n] = buf[n];
-		if(fread(buf.data(), 4, N, fin)!=N) print_error("short uy");  for(ulong n=0ull; n<N; n++) lbm.u.y[n] = buf[n];
-		if(fread(buf.data(), 4, N, fin)!=N) print_error("short uz");  for(ulong n=0ull; n<N; n++) lbm.u.z[n] = buf[n];
+		if(fread(buf.data(), 4, N, fin)!=N) print_error("short rho"); for(ulong n=0ull; n<N; n++) if(!(lbm.flags[n]&TYPE_X)) lbm.rho[n] = buf[n];
+		if(fread(buf.data(), 4, N, fin)!=N) print_error("short ux");  for(ulong n=0ull; n<N; n++) if(!(lbm.flags[n]&TYPE_X)) lbm.u.x[n] = buf[n];
+		if(fread(buf.data(), 4, N, fin)!=N) print_error("short uy");  for(ulong n=0ull; n<N; n++) if(!(lbm.flags[n]&TYPE_X)) lbm.u.y[n] = buf[n];
+		if(fread(buf.data(), 4, N, fin)!=N) print_error("short uz");  for(ulong n=0ull; n<N; n++) if(!(lbm.flags[n]&TYPE_X)) lbm.u.z[n] = buf[n];
 		vector<uchar> fl(N);
-		if(fread(fl.data(), 1, N, fin)!=N) print_error("short flags"); for(ulong n=0ull; n<N; n++) lbm.flags[n] = fl[n];
+		if(fread(fl.data(), 1, N, fin)!=N) print_error("short flags"); for(ulong n=0ull; n<N; n++) if(!(lbm.flags[n]&TYPE_X)) lbm.flags[n] = fl[n];
 		fclose(fin);
 	}
 	lbm.run(0u); // initialize
@@ -85,6 +95,18 @@ void main_setup() {
 		for(ulong n=0ull; n<N; n++) buf[n] = lbm.u.z[n]; fwrite(buf.data(), 4, N, fo);
 		vector<uchar> fl(N);
 		for(ulong n=0ull; n<N; n++) fl[n] = lbm.flags[n]; fwrite(fl.data(), 1, N, fo);
+#ifdef FORCE_FIELD
+		if(env_or("FX3D_REF_FF", "")!="") {
+			lbm.update_force_field();
+			lbm.F.read_from_device();
+			for(ulong n=0ull; n<N; n++) buf[n] = lbm.F.x[n]; fwrite(buf.data(), 4, N, fo);
+			for(ulong n=0ull; n<N; n++) buf[n] = lbm.F.y[n]; fwrite(buf.data(), 4, N, fo);
+			for(ulong n=0ull; n<N; n++) buf[n] = lbm.F.z[n]; fwrite(buf.data(), 4, N, fo);
+			const float3 force = lbm.object_force(TYPE_S|TYPE_X), com = lbm.object_center_of_mass(TYPE_S|TYPE_X), torque = lbm.object_torque(lbm.center(), TYPE_S|TYPE_X);
+			const float sums[9] = { force.x, force.y, force.z, com.x, com.y, com.z, torque.x, torque.y, torque.z };
+			fwrite(sums, 4, 9, fo);
+		}
+#endif
 		fclose(fo);
 	}
 	fflush(stdout);

@@ -144,21 +144,6 @@ SEG_CASES = [((19, SRT, FP16S, 0), (1024, 4, 3), (1, 1, 1)), ((19, SRT, FP16S, 0
 
 
 @pytest.mark.parametrize("v,dims,D", SEG_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in SEG_CASES])
-def test_bulk_copy_segment_kernel_bit_exact(fx, v, dims, D):
-    """rows longer than one tile (periodic wrap across tiles) and x-decomposed domains (halo cells at the row ends) take the
-    segment form of the bulk-copy kernel; it must be the kernel that ran, and every field must match the oracle bit for bit"""
-    from fluidx3d_b200 import capi
-    f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
-    before = capi.lib().kernel_kind_counts()
-    for steps in (1, 2, 7):
-        got, want = product(fx, v, dims, D, steps, f, 16), oracle(v, dims, D, steps, f)
-        for a, b in zip(got, want):
-            assert np.array_equal(bits(a), bits(b)), steps
-    after = capi.lib().kernel_kind_counts()
-    assert after[4] > before[4] and after[:3] == before[:3]
-
-
-@pytest.mark.parametrize("v,dims,D", SEG_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in SEG_CASES])
 def test_hybrid_kernel_bit_exact(fx, v, dims, D):
     """default choice for row segments / x halos: bulk loads, direct stores"""
     from fluidx3d_b200 import capi
@@ -169,7 +154,10 @@ def test_hybrid_kernel_bit_exact(fx, v, dims, D):
         for a, b in zip(got, want):
             assert np.array_equal(bits(a), bits(b)), steps
     after = capi.lib().kernel_kind_counts()
-    assert after[5] > before[5] and after[:5] == before[:5]
+    if (dims[0] // D[0]) > 512:
+        assert after[5] > before[5] and after[:5] == before[:5], "the hybrid kernel must be the one that ran"
+    else:  # x-decomposed domains whose rows fit one tile: the whole-row kernel takes them (halo cells in the row-buffer pads)
+        assert after[3] > before[3] and after[:3] == before[:3] and after[5] == before[5], "the whole-row bulk-copy kernel must be the one that ran"
 
 
 @pytest.mark.parametrize("D", [(2, 1, 1), (1, 2, 1), (1, 1, 2), (2, 2, 1), (2, 2, 2), (4, 1, 2)], ids=lambda d: "d" + "".join(map(str, d)))

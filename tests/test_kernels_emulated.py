@@ -63,7 +63,9 @@ def test_emulated_kernels_match_oracle(emul, v, dims, D, variant):
 
 TMA_CASES = [((19, SRT, FP16S, 0), (32, 16, 4), (1, 1, 1)), ((19, SRT, FP32, 0), (64, 8, 3), (1, 1, 1)), ((19, TRT, FP16C, 3), (16, 32, 3), (1, 1, 1)),
              ((27, TRT, FP32, 3), (32, 16, 3), (1, 1, 1)), ((27, SRT, FP16S, 1), (32, 32, 4), (1, 2, 2)), ((19, SRT, FP16S, 2), (64, 16, 6), (1, 2, 1)),
-             ((19, SRT, FP16S, 0), (512, 3, 3), (1, 1, 1)), ((19, TRT, FP32, 3), (512, 2, 4), (1, 1, 2)), ((27, SRT, FP16C, 0), (512, 2, 2), (1, 1, 1))]  # one-row tiles: compile-time copy lists
+             ((19, SRT, FP16S, 0), (512, 3, 3), (1, 1, 1)), ((19, TRT, FP32, 3), (512, 2, 4), (1, 1, 2)), ((27, SRT, FP16C, 0), (512, 2, 2), (1, 1, 1)),  # one-row tiles: compile-time copy lists
+             # long runs of tiles per block (more than stages + groups): every stage is refilled several times, by a group other than the one that reads it
+             ((19, SRT, FP16S, 0), (16, 32, 40), (1, 1, 1)), ((19, SRT, FP32, 2), (32, 16, 48), (1, 1, 1)), ((19, SRT, FP16S, 0), (512, 2, 20), (1, 1, 1))]
 
 
 @pytest.mark.parametrize("v,dims,D", TMA_CASES, ids=[f"q{c[0][0]}c{c[0][1]}s{c[0][2]}f{c[0][3]}-{'x'.join(map(str, c[1]))}-d{''.join(map(str, c[2]))}" for c in TMA_CASES])
