@@ -11,6 +11,7 @@
 namespace fx3d {
 
 int cuda_fail(cudaError_t e, const char* what) {
+	(void)cudaGetLastError(); // a failed call also leaves its code in the runtime's last-error slot: clear it, or the next launch check reports it as its own
 	set_error(std::string(what)+": "+cudaGetErrorName(e)+" ("+cudaGetErrorString(e)+")");
 	if(e==cudaErrorNoDevice||e==cudaErrorInsufficientDriver||e==cudaErrorInvalidDevice) return FX3D_ERR_NO_DEVICE;
 	if(e==cudaErrorMemoryAllocation) return FX3D_ERR_OUT_OF_MEMORY;

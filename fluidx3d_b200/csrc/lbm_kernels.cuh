@@ -109,6 +109,8 @@ template<> struct Pack<ST_FP32, 4> {
 	FX3D_HD void store_seg_down(float* row, uint32_t x) const { *(row+x-1) = f2_lo(p[0]); *reinterpret_cast<unsigned long long*>(row+x) = bits64(make_f2(f2_hi(p[0]), f2_lo(p[1]))); row[x+2u] = f2_hi(p[1]); } // positions x-1..x+2
 	FX3D_HD void store_row_up(float* row, uint32_t x, uint32_t W) const { row[x+1u] = f2_lo(p[0]); *reinterpret_cast<unsigned long long*>(row+x+2u) = bits64(make_f2(f2_hi(p[0]), f2_lo(p[1]))); row[x+4u==W ? 0u : x+4u] = f2_hi(p[1]); }
 	FX3D_HD void store_row_down(float* row, uint32_t x, uint32_t W) const { row[x==0u ? W-1u : x-1u] = f2_lo(p[0]); *reinterpret_cast<unsigned long long*>(row+x) = bits64(make_f2(f2_hi(p[0]), f2_lo(p[1]))); row[x+2u] = f2_hi(p[1]); }
+	FX3D_HD void store_shift_up(float* q, float* e) const { q[1] = f2_lo(p[0]); *reinterpret_cast<unsigned long long*>(q+2) = bits64(make_f2(f2_hi(p[0]), f2_lo(p[1]))); *e = f2_hi(p[1]); } // q = position of my vector, e = the element right of it
+	FX3D_HD void store_shift_down(float* q, float* e) const { *e = f2_lo(p[0]); *reinterpret_cast<unsigned long long*>(q) = bits64(make_f2(f2_hi(p[0]), f2_lo(p[1]))); q[2] = f2_hi(p[1]); } // e = the element left of it
 	FX3D_HD void push_back(uint32_t b) { p[0] = make_f2(f2_hi(p[0]), f2_lo(p[1])); p[1] = make_f2(f2_hi(p[1]), __uint_as_float(b)); }  // {e1,e2,e3,b}
 	FX3D_HD void push_front(uint32_t b) { p[1] = make_f2(f2_hi(p[0]), f2_lo(p[1])); p[0] = make_f2(__uint_as_float(b), f2_lo(p[0])); } // {b,e0,e1,e2}
 	template<int k> FX3D_HD F2 get_pair() const { return p[k]; }
@@ -154,6 +156,8 @@ template<int ST> struct Pack<ST, 4> {
 	FX3D_HD void store_seg_down(uint16_t* row, uint32_t x) const { *(row+x-1) = (uint16_t)r[0]; *reinterpret_cast<uint32_t*>(row+x) = (r[0]>>16)|(r[1]<<16); row[x+2u] = (uint16_t)(r[1]>>16); }
 	FX3D_HD void store_row_up(uint16_t* row, uint32_t x, uint32_t W) const { row[x+1u] = (uint16_t)r[0]; *reinterpret_cast<uint32_t*>(row+x+2u) = (r[0]>>16)|(r[1]<<16); row[x+4u==W ? 0u : x+4u] = (uint16_t)(r[1]>>16); }
 	FX3D_HD void store_row_down(uint16_t* row, uint32_t x, uint32_t W) const { row[x==0u ? W-1u : x-1u] = (uint16_t)r[0]; *reinterpret_cast<uint32_t*>(row+x) = (r[0]>>16)|(r[1]<<16); row[x+2u] = (uint16_t)(r[1]>>16); }
+	FX3D_HD void store_shift_up(uint16_t* q, uint16_t* e) const { q[1] = (uint16_t)r[0]; *reinterpret_cast<uint32_t*>(q+2) = (r[0]>>16)|(r[1]<<16); *e = (uint16_t)(r[1]>>16); }
+	FX3D_HD void store_shift_down(uint16_t* q, uint16_t* e) const { *e = (uint16_t)r[0]; *reinterpret_cast<uint32_t*>(q) = (r[0]>>16)|(r[1]<<16); q[2] = (uint16_t)(r[1]>>16); }
 	FX3D_HD void push_back(uint32_t b) { r[0] = (r[0]>>16)|(r[1]<<16); r[1] = (r[1]>>16)|(b<<16); }
 	FX3D_HD void push_front(uint32_t b) { r[1] = (r[1]<<16)|(r[0]>>16); r[0] = (r[0]<<16)|(b&0xFFFFu); }
 	template<int k> FX3D_HD F2 get_pair() const { return decode_half_pair<ST>(r[k]); } // to the working scale of Codec<ST>
@@ -174,6 +178,8 @@ template<> struct Pack<ST_FP32, 2> {
 	FX3D_HD void store_head(float* q) const { q[0] = f2_lo(p); }
 	FX3D_HD uint32_t first_bits() const { return __float_as_uint(f2_lo(p)); }
 	FX3D_HD uint32_t last_bits() const { return __float_as_uint(f2_hi(p)); }
+	FX3D_HD void store_shift_up(float* q, float* e) const { q[1] = f2_lo(p); *e = f2_hi(p); }   // q = position of my vector, e = the element right of it
+	FX3D_HD void store_shift_down(float* q, float* e) const { *e = f2_lo(p); q[0] = f2_hi(p); } // e = the element left of it
 	FX3D_HD void push_back(uint32_t b) { p = make_f2(f2_hi(p), __uint_as_float(b)); }
 	FX3D_HD void push_front(uint32_t b) { p = make_f2(__uint_as_float(b), f2_lo(p)); }
 	template<int k> FX3D_HD F2 get_pair() const { return p; }
@@ -191,6 +197,8 @@ template<int ST> struct Pack<ST, 2> {
 	FX3D_HD void store_head(uint16_t* q) const { q[0] = (uint16_t)(r&0xFFFFu); }
 	FX3D_HD uint32_t first_bits() const { return r&0xFFFFu; }
 	FX3D_HD uint32_t last_bits() const { return r>>16; }
+	FX3D_HD void store_shift_up(uint16_t* q, uint16_t* e) const { q[1] = (uint16_t)r; *e = (uint16_t)(r>>16); }
+	FX3D_HD void store_shift_down(uint16_t* q, uint16_t* e) const { *e = (uint16_t)r; q[0] = (uint16_t)(r>>16); }
 	FX3D_HD void push_back(uint32_t b) { r = (r>>16)|(b<<16); }
 	FX3D_HD void push_front(uint32_t b) { r = (r<<16)|(b&0xFFFFu); }
 	template<int k> FX3D_HD F2 get_pair() const { return decode_half_pair<ST>(r); }
@@ -658,17 +666,21 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_col
 // saturate at 5.2 TB/s however deep the ring is, bulk copies reach 6.2 TB/s.
 //
 // Tile = 128/bx whole x-rows of W = 4*bx non-halo cells (bx threads per row, 4 cells per thread). A row of one slot is one
-// contiguous segment, so: one copy per (slot, tile row) in, one out. A row buffer is [16-byte pad | W elements | 16-byte pad]:
-//   * periodic rows (no x halo): the copy fills the middle; the x-shifted directions read and write at wrapped positions
-//   * rows with x halos (x-decomposed domains): the copy covers the pads too -- the halo cell x=0 is the last element of the
-//     head pad, x=Nx-1 the first of the tail pad (the DDF layout puts cell x=1 on a 128-byte line) -- and nothing wraps
+// contiguous segment, so: one copy per (slot, tile row) in, one out. In shared memory the rows of one slot form a SET of a fixed
+// size known at compile time, [16-byte pad | 128 threads x 4 cells | 16-byte pad], so that every per-thread access of the hot loop
+// is register + immediate offset (the tile shape is a launch parameter; a stride that depended on it cost 60 multiply-adds per thread
+// and tile, profiles/r02a_*):
+//   * periodic rows (no x halo): the copies fill the rows; the x-shifted directions read and write at wrapped positions
+//   * rows with x halos (x-decomposed domains, one-row tiles only): one copy covers pad + row + pad -- the halo cell x=0 is the last
+//     element of the head pad, x=Nx-1 the first of the tail pad (the DDF layout puts cell x=1 on a 128-byte line) -- nothing wraps
 // so there are no shuffles, no edge accesses and no per-thread global addresses for the DDFs at all.
 //
-// A block is G compute groups of 128 threads sharing ONE ring of S stages (S > G): tile k of the block's contiguous share goes to
-// group k%G and stage k%S, i.e. S-G stages are loading while G are being worked on. Per tile and group: wait(full[stage]) ->
-// registers <- stage -> group barrier -> refill the stage of the group's previous tile -> collide -> stage <- registers (in place)
-// -> proxy fence + group barrier -> bulk stores. Every row buffer is loaded and stored by the same thread, which waits only for
-// the bulk stores it issued itself before it refills; groups synchronise with named barriers, never block-wide.
+// Ring of S stages per block (S*stage bytes of shared memory; B blocks per SM): tile k of the block's contiguous share uses stage
+// k%S. Per tile: wait(full[stage]) -> registers <- stage -> block barrier -> refill the stage of the previous tile (its bulk stores
+// have had the stream-in to finish reading it) -> collide -> stage <- registers (in place) -> proxy fence + block barrier -> bulk
+// stores. Every row buffer is loaded and stored by the same thread, which waits only for the bulk stores it issued itself. The copies
+// are dealt to the four warps; for one-row tiles lane 0 of warp w issues buffers w, w+4, .. from an unrolled list in which
+// everything but the row position is a compile-time constant and all address arithmetic is warp-uniform.
 //
 // Fused y/z halo delivery (replaces LBM::communicate_fi for those axes, src/lbm.cpp:1355-1387): under Esoteric-Pull every
 // (slot, row) written in step t has exactly one reader in step t+1 -- the tile at the same row for what was written through the
@@ -718,105 +730,93 @@ FX3D_HD void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" 
 
 // y/z neighbours of a domain for the fused halo delivery: fi[(dy+1)+3*(dz+1)], [4] = the domain itself; unused entries null
 struct RowPeers { void* fi[9]; };
-// Block organisation of the whole-row kernel, measured on B200 (profiles/r02_row_kernel_tuning.txt): G compute groups of 128 threads per block sharing
-// one ring, B resident blocks per SM (also the register cap: 65536/(128*G*B)), ring depth = what fits (capped by FX3D_ROW_MAX_STAGES).
-#ifndef FX3D_ROW_GROUPS_16
-#define FX3D_ROW_GROUPS_16 1 // D3Q19 with 16-bit storage
-#endif
+// Resident blocks per SM of the whole-row kernel (also its register cap, 65536/(128*B)) and the ring depth, measured on B200
+// (profiles/r02_row_kernel_tuning.txt).
 #ifndef FX3D_ROW_BLOCKS_16
-#define FX3D_ROW_BLOCKS_16 4
-#endif
-#ifndef FX3D_ROW_GROUPS_32
-#define FX3D_ROW_GROUPS_32 1 // FP32 (both velocity sets)
+#define FX3D_ROW_BLOCKS_16 4 // D3Q19 with 16-bit storage: 128 registers
 #endif
 #ifndef FX3D_ROW_BLOCKS_32
-#define FX3D_ROW_BLOCKS_32 2
-#endif
-#ifndef FX3D_ROW_GROUPS_27
-#define FX3D_ROW_GROUPS_27 1 // D3Q27 with 16-bit storage
+#define FX3D_ROW_BLOCKS_32 2 // FP32 (both velocity sets): 255 registers
 #endif
 #ifndef FX3D_ROW_BLOCKS_27
-#define FX3D_ROW_BLOCKS_27 3
+#define FX3D_ROW_BLOCKS_27 3 // D3Q27 with 16-bit storage: 168 registers
 #endif
 #ifndef FX3D_ROW_MAX_STAGES
-#define FX3D_ROW_MAX_STAGES 15
+#define FX3D_ROW_MAX_STAGES 8
 #endif
-template<int Q, int ST> FX3D_HDC constexpr int row_groups() { return ST==ST_FP32 ? FX3D_ROW_GROUPS_32 : (Q>19 ? FX3D_ROW_GROUPS_27 : FX3D_ROW_GROUPS_16); }
 template<int Q, int ST> FX3D_HDC constexpr int row_blocks() { return ST==ST_FP32 ? FX3D_ROW_BLOCKS_32 : (Q>19 ? FX3D_ROW_BLOCKS_27 : FX3D_ROW_BLOCKS_16); }
-constexpr uint32_t ROW_PAD = 16u, ROW_MAX_STAGES = FX3D_ROW_MAX_STAGES<15 ? FX3D_ROW_MAX_STAGES : 15u, ROW_HEADER = 256u; // header: full[16] | first[4] | unused
-FX3D_HDC constexpr uint32_t row_stage_bytes(uint32_t Q, uint32_t esz, uint32_t bx, uint32_t by) { return Q*by*(bx*4u*esz+2u*ROW_PAD); }
-#if defined(FX3D_HOST_EMULATION)
-// emulation of an mbarrier with an arrival count: bits 0-31 completed phases, 32-47 pending arrivals, 48-63 arrivals per phase.
-// Copies happen at issue, so a copying thread arrives after its copies (mbar_copies_issued), not before them.
-FX3D_HD void mbar_init_n(uint64_t* b, uint32_t n) { __atomic_store_n(b, ((uint64_t)n<<48)|((uint64_t)n<<32), __ATOMIC_SEQ_CST); }
-FX3D_HD void mbar_arrive_expect_tx(uint64_t*, uint32_t) {}
-FX3D_HD void mbar_copies_issued(uint64_t* b) {
-	uint64_t v = __atomic_load_n(b, __ATOMIC_SEQ_CST);
-	for(;;) {
-		const uint64_t n = v>>48, pending = ((v>>32)&0xFFFFull)-1ull, phase = v&0xFFFFFFFFull;
-		const uint64_t nv = pending==0ull ? (n<<48)|(n<<32)|((phase+1ull)&0xFFFFFFFFull) : (n<<48)|(pending<<32)|phase;
-		if(__atomic_compare_exchange_n(b, &v, nv, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) break;
-	}
-}
-FX3D_HD void mbar_wait_n(uint64_t* b, uint32_t parity) { while((__atomic_load_n(b, __ATOMIC_SEQ_CST)&1ull)==(uint64_t)parity) std::this_thread::yield(); }
-FX3D_HD void mbar_arrive(uint64_t* b) { mbar_copies_issued(b); } // a plain arrival
-FX3D_HD void group_sync(uint32_t g) { emul::group_barrier(g); }
-#else
-FX3D_HD void mbar_init_n(uint64_t* b, uint32_t n) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(b)), "r"(n) : "memory"); }
-FX3D_HD void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) { mbar_expect_tx(b, bytes); } // one arrival, `bytes` more to wait for
-FX3D_HD void mbar_copies_issued(uint64_t*) {}
-FX3D_HD void mbar_wait_n(uint64_t* b, uint32_t parity) { mbar_wait(b, parity); }
-FX3D_HD void mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_addr(b)) : "memory"); }
-FX3D_HD void group_sync(uint32_t g) { asm volatile("bar.sync %0, 128;" :: "r"(g+1u) : "memory"); } // named barrier of one compute group
+// Cells per thread K (4 or 2) and threads per block T of the whole-row kernel; a tile is K*T cells. Fewer cells per thread = more warps working on
+// one tile: the tile is turned around sooner for the same bytes of shared memory.
+#ifndef FX3D_ROW_K_16
+#define FX3D_ROW_K_16 4
 #endif
+#ifndef FX3D_ROW_K_32
+#define FX3D_ROW_K_32 4
+#endif
+#ifndef FX3D_ROW_K_27
+#define FX3D_ROW_K_27 4
+#endif
+#ifndef FX3D_ROW_T_16
+#define FX3D_ROW_T_16 (512/FX3D_ROW_K_16)
+#endif
+#ifndef FX3D_ROW_T_32
+#define FX3D_ROW_T_32 (512/FX3D_ROW_K_32)
+#endif
+#ifndef FX3D_ROW_T_27
+#define FX3D_ROW_T_27 (512/FX3D_ROW_K_27)
+#endif
+template<int Q, int ST> FX3D_HDC constexpr int row_cells() { return ST==ST_FP32 ? FX3D_ROW_K_32 : (Q>19 ? FX3D_ROW_K_27 : FX3D_ROW_K_16); }
+template<int Q, int ST> FX3D_HDC constexpr uint32_t row_threads() { return ST==ST_FP32 ? FX3D_ROW_T_32 : (Q>19 ? FX3D_ROW_T_27 : FX3D_ROW_T_16); }
+constexpr uint32_t ROW_PAD = 16u, ROW_MAX_STAGES = FX3D_ROW_MAX_STAGES, ROW_BARRIERS = 128u;
+template<int Q, int ST> FX3D_HDC constexpr uint32_t row_header() { return ROW_BARRIERS+2u*row_threads<Q, ST>()*8u; } // header: full[<=16] mbarriers, then two buffers of T x 2 flag words
+template<int Q, int ST> FX3D_HDC constexpr uint32_t row_set_bytes() { return row_threads<Q, ST>()*(uint32_t)row_cells<Q, ST>()*(ST==ST_FP32 ? 4u : 2u)+2u*ROW_PAD; } // one slot's rows of a tile: [pad | K*T elements | pad]
+template<int Q, int ST> FX3D_HDC constexpr uint32_t row_stage_bytes() { return (uint32_t)Q*row_set_bytes<Q, ST>(); }
 
 template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false>
-__global__ void __launch_bounds__(128*row_groups<Q, ST>(), row_blocks<Q, ST>()) k_stream_collide_tma(const Lattice L, const Region R, const uint32_t tiles_y, const uint32_t S, const RowPeers P) {
-	constexpr int K = 4;
-	constexpr uint32_t G = (uint32_t)row_groups<Q, ST>(), PAD = ROW_PAD;
+__global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_stream_collide_tma(const Lattice L, const Region R, const uint32_t tiles_y, const uint32_t S, const RowPeers P) {
+	constexpr int K = row_cells<Q, ST>();
+	constexpr uint32_t T = row_threads<Q, ST>(), NW = T/32u; // threads and warps per block
 	typedef Codec<ST> C;
 	typedef typename C::elem_t E;
 	typedef Pack<ST, K> PK;
-	constexpr uint32_t VB = (uint32_t)(sizeof(E)*K), ESZ = (uint32_t)sizeof(E);
+	constexpr uint32_t VB = (uint32_t)(sizeof(E)*K), ESZ = (uint32_t)sizeof(E), PAD = ROW_PAD, SET = row_set_bytes<Q, ST>(), STAGE = (uint32_t)Q*SET;
 	unsigned char* const smem = dynamic_smem();
 	uint64_t* const full = reinterpret_cast<uint64_t*>(smem); // full[stage]: the bulk loads of the tile in this stage have landed
-	uint64_t* const first_fill = full+16;                     // first_fill[stage], stage < G: one-shot, the FIRST fill of this stage has landed (see the main loop)
-	unsigned char* const ring = smem+ROW_HEADER;
-	const uint32_t bx = blockDim.x, by = blockDim.y, g = threadIdx.z;
+	unsigned char* const ring = smem+row_header<Q, ST>();
+	const uint32_t bx = blockDim.x, by = blockDim.y;
 	const uint32_t t = threadIdx.x+threadIdx.y*bx, lane = t&31u;
-	const uint32_t warp = __shfl_sync(0xFFFFFFFFu, t>>5, 0); // warp within the group, uniform
-	const uint32_t W = bx*(uint32_t)K, row_bytes = bx*VB, RB = row_bytes+2u*PAD, SET = by*RB, STAGE = (uint32_t)Q*SET;
-	const bool hx = L.Hx!=0u, hy = L.Hy!=0u, hz = L.Hz!=0u;
-	// where a row buffer starts in its pitch row (bytes), how much of it the copies cover, and where that lands in the buffer
-	const uint32_t g_off = hx ? (L.xo+1u)*ESZ-PAD : 0u, copy_bytes = hx ? RB : row_bytes, s_off = hx ? 0u : PAD;
+	const uint32_t warp = __shfl_sync(0xFFFFFFFFu, t>>5, 0); // uniform
+	const uint32_t W = bx*(uint32_t)K, row_bytes = bx*VB;
+	const bool hx = L.Hx!=0u, hy = L.Hy!=0u, hz = L.Hz!=0u; // hx: one-row tiles only (by==1), see the launcher
+	// where a row's copy starts in its pitch row (bytes), how much it covers, and where that lands in the set
+	const uint32_t g_off = hx ? (L.xo+1u)*ESZ-PAD : 0u, copy_bytes = hx ? row_bytes+2u*PAD : row_bytes, s_off = hx ? 0u : PAD;
 	const uint32_t ncopies = (uint32_t)Q*by;
 	const bool one_row = by==1u;
-	const uint32_t first_copy = warp+4u*lane; // multi-row tiles: copy c = ty*Q+j belongs to lane c/4 of warp c%4 (then every 128th)
+	const uint32_t first_copy = warp+NW*lane; // multi-row tiles: copy c = ty*Q+j belongs to lane c/NW of warp c%NW (then every T-th)
 	const bool copier = one_row ? lane==0u : first_copy<ncopies;
-	if(t==0u && g==0u) {
-		for(uint32_t s=0u; s<S; s++) mbar_init_n(full+s, one_row ? 4u : (ncopies<128u ? ncopies : 128u));
-		for(uint32_t s=0u; s<G; s++) mbar_init_n(first_fill+s, 1u);
-	}
+	if(t==0u) { for(uint32_t s=0u; s<S; s++) mbar_init(full+s); }
 	fence_async_smem();
 	__syncthreads();
 
-	// ---- addresses: buffer j of a tile row at (y, z); for stores the row may belong to a y/z neighbour (see the header) ----
+	// ---- global address of the copy of buffer j of the tile row at (y, z); a stored row may belong to a y/z neighbour (see the header) ----
+	const uint32_t plane = L.px*L.Ny; // elements per z plane of one slot (the padded slot holds < 2^32 elements)
+	const bool fused = hy || hz; // some stored rows belong to a y/z neighbour
 	auto row_address = [&](bool store, uint32_t slot, bool local, int ey, int ez, uint32_t y, uint32_t z) -> char* {
 		uint32_t yr = y, zr = z;
-		int dy = 0, dz = 0;
 		if(!local) { yr = step_rt(ey, y, L.Ny); zr = step_rt(ez, z, L.Nz); }
-		if(store) {
+		char* base = reinterpret_cast<char*>(L.fi);
+		if(store && fused) { // (a uniform branch: without y/z halos a store goes where the load came from, and the address stays in uniform registers)
 			// the reader's cell row: the row itself for neighbour-side buffers, row-e for local ones
 			const uint32_t ry = local ? (uint32_t)((int)y-ey) : yr, rz = local ? (uint32_t)((int)z-ez) : zr;
+			int dy = 0, dz = 0;
 			if(hy) dy = ry==0u ? -1 : ry==L.Ny-1u ? 1 : 0;
 			if(hz) dz = rz==0u ? -1 : rz==L.Nz-1u ? 1 : 0;
 			yr = (uint32_t)((int)yr-dy*(int)(L.Ny-2u)); zr = (uint32_t)((int)zr-dz*(int)(L.Nz-2u));
+			if(dy!=0 || dz!=0) base = reinterpret_cast<char*>(P.fi[(dy+1)+3*(dz+1)]);
 		}
-		char* base = reinterpret_cast<char*>(L.fi);
-		if(dy!=0 || dz!=0) base = reinterpret_cast<char*>(P.fi[(dy+1)+3*(dz+1)]);
-		return base+((uint64_t)slot*L.slot+row(L, yr, zr))*ESZ+g_off;
+		return mad_wide(yr*L.px+zr*plane, ESZ, mad_wide(L.slot32, slot*ESZ, base))+g_off; // two IMAD.WIDE: the element offset inside a slot fits 32 bits
 	};
-	auto copy_one_row = [&](auto LOAD, uint32_t y, uint32_t z, uint32_t stage) { // lane 0 of every warp: its share of the Q copies, everything but y and z known at compile time
+	auto copy_one_row = [&](auto LOAD, auto STORE_ELSEWHERE, uint32_t y, uint32_t z, uint32_t stage) { // lane 0 of every warp: its share of the Q copies, everything but y and z known at compile time
 		constexpr bool load = decltype(LOAD)::value;
 		unsigned char* const sb = ring+(size_t)stage*STAGE+s_off;
 		auto one = [&](auto J) {
@@ -825,10 +825,10 @@ __global__ void __launch_bounds__(128*row_groups<Q, ST>(), row_blocks<Q, ST>()) 
 			constexpr uint32_t slot = j==0 ? 0u : (j&1) ? (ODD ? (uint32_t)i : (uint32_t)i+1u) : (ODD ? (uint32_t)i+1u : (uint32_t)i);
 			constexpr bool local = j==0 || (j&1);
 			constexpr int ey = j==0 ? 0 : dir_y(i), ez = j==0 ? 0 : dir_z(i);
-			char* gp = row_address(!load && j!=0, slot, local, ey, ez, y, z);
+			char* gp = row_address(decltype(STORE_ELSEWHERE)::value && j!=0, slot, local, ey, ez, y, z);
 			if constexpr(load) bulk_load(sb+(size_t)j*SET, gp, copy_bytes, full+stage); else bulk_store(gp, sb+(size_t)j*SET, copy_bytes);
 		};
-		if(warp==0u) static_for<0, Q, 4>(one); else if(warp==1u) static_for<1, Q, 4>(one); else if(warp==2u) static_for<2, Q, 4>(one); else static_for<3, Q, 4>(one);
+		static_for<0, (int)NW, 1>([&](auto Wc) { if(warp==(uint32_t)Wc.value) static_for<Wc.value, Q, (int)NW>(one); });
 	};
 	auto copy_any = [&](bool load, uint32_t c, uint32_t y0, uint32_t z, uint32_t stage) { // multi-row tiles: copy c, decoded at run time
 		const uint32_t ty = c/(uint32_t)Q, j = c%(uint32_t)Q;
@@ -840,88 +840,98 @@ __global__ void __launch_bounds__(128*row_groups<Q, ST>(), row_blocks<Q, ST>()) 
 			ey = dir_rt(1, i); ez = dir_rt(2, i);
 		}
 		char* gp = row_address(!load && j!=0u, slot, local, ey, ez, y0+ty, z);
-		unsigned char* sp = ring+(size_t)stage*STAGE+(size_t)j*SET+ty*RB+s_off;
+		unsigned char* sp = ring+(size_t)stage*STAGE+(size_t)j*SET+ty*row_bytes+s_off;
 		if(load) bulk_load(sp, gp, copy_bytes, full+stage); else bulk_store(gp, sp, copy_bytes);
 	};
-	auto load_tile = [&](uint32_t y0, uint32_t z, uint32_t stage) { // every thread of the group calls it
-		if(!copier) return;
-		if(one_row) {
-			uint32_t n = 0u; for(uint32_t j=warp; j<(uint32_t)Q; j+=4u) n++;
-			mbar_arrive_expect_tx(full+stage, n*copy_bytes);
-			copy_one_row(std::true_type{}, y0, z, stage);
-		} else {
-			uint32_t n = 0u; for(uint32_t c=first_copy; c<ncopies; c+=128u) n++;
-			mbar_arrive_expect_tx(full+stage, n*copy_bytes);
-			for(uint32_t c=first_copy; c<ncopies; c+=128u) copy_any(true, c, y0, z, stage);
+	auto load_tile = [&](uint32_t y0, uint32_t z, uint32_t stage) { // every thread of the block calls it
+		if(t==0u) mbar_expect_tx(full+stage, ncopies*copy_bytes);
+		if(copier) {
+			if(one_row) copy_one_row(std::true_type{}, std::false_type{}, y0, z, stage);
+			else for(uint32_t c=first_copy; c<ncopies; c+=T) copy_any(true, c, y0, z, stage);
 		}
-		mbar_copies_issued(full+stage);
+#if defined(FX3D_HOST_EMULATION)
+		__syncthreads(); // (emulation: copies happen at issue; the phase completes once every thread has made its copies)
+		if(t==0u) mbar_phase_done_emulated(full+stage);
+#endif
 	};
 	auto store_tile = [&](uint32_t y0, uint32_t z, uint32_t stage) {
 		if(!copier) return;
-		if(one_row) copy_one_row(std::false_type{}, y0, z, stage);
-		else for(uint32_t c=first_copy; c<ncopies; c+=128u) copy_any(false, c, y0, z, stage);
+		if(one_row) { if(fused) copy_one_row(std::false_type{}, std::true_type{}, y0, z, stage); else copy_one_row(std::false_type{}, std::false_type{}, y0, z, stage); }
+		else for(uint32_t c=first_copy; c<ncopies; c+=T) copy_any(false, c, y0, z, stage);
 		bulk_commit();
 	};
 
-	// ---- this block's contiguous share of the (row group, plane) tiles; tile k of the share: group k%G, stage k%S ----
+	// ---- this block's contiguous share of the (row group, plane) tiles; tile k of the share uses stage k%S ----
 	const uint32_t nz = R.z1-R.z0;
 	const uint64_t ntiles = (uint64_t)tiles_y*nz, T0 = ntiles*blockIdx.x/gridDim.x, T1 = ntiles*(blockIdx.x+1u)/gridDim.x;
 	const uint32_t n = (uint32_t)(T1-T0);
 	struct Pos { uint32_t yb, zo; }; // tile row group and plane offset
 	auto advance = [&](Pos p, uint32_t d) -> Pos { p.zo += d; while(p.zo>=nz) { p.zo -= nz; p.yb++; } return p; };
-	const Pos first = advance(Pos{ (uint32_t)(T0/nz), (uint32_t)(T0%nz) }, 0u);
-	for(uint32_t j=g; j<S && j<n; j+=G) { const Pos p = advance(first, j); load_tile(R.y0+p.yb*by, R.z0+p.zo, j); } // prologue: group j%G loads tile j
+	Pos cur = Pos{ (uint32_t)(T0/nz), (uint32_t)(T0%nz) };
+	for(uint32_t j=0u; j<S && j<n; j++) { const Pos p = advance(cur, j); load_tile(R.y0+p.yb*by, R.z0+p.zo, j); } // prologue: the first S tiles
 	const uint32_t x0 = (uint32_t)K*threadIdx.x;
-	// my 4 flag bytes: two aligned words, requested one tile ahead and only combined when needed
+	// my 4 flag bytes: the two aligned words that hold them travel one tile ahead with per-thread cp.async into a double-buffered corner of
+	// shared memory -- no register holds a load in flight (as plain loads the words were spilled on arrival, and the spill store waited for
+	// them: 17 % of all stall samples, profiles/r02b_*)
 	const uint64_t flag_plane = (uint64_t)L.Nx*L.Ny;
-	uint32_t fw0 = 0u, fw1 = 0u;
-	auto flag_address = [&](Pos p) -> uintptr_t { return reinterpret_cast<uintptr_t>(L.flags+((uint64_t)(L.Hx+x0)+(uint64_t)(R.y0+p.yb*by+threadIdx.y)*L.Nx+(uint64_t)(R.z0+p.zo)*flag_plane)); };
-	auto request_flags = [&](Pos p) { const uintptr_t a = flag_address(p); fw0 = *reinterpret_cast<const uint32_t*>(a&~(uintptr_t)3u); fw1 = (a&3u) ? *reinterpret_cast<const uint32_t*>((a&~(uintptr_t)3u)+4u) : 0u; };
-	auto combine_flags = [&](Pos p) -> uint32_t { const uint32_t sh = 8u*(uint32_t)(flag_address(p)&3u); return sh==0u ? fw0 : (fw0>>sh)|(fw1<<(32u-sh)); };
-	Pos cur = advance(first, g);
-	if(g<n) request_flags(cur);
-	uint32_t stage = g, fill = 0u, prev_stage = 0u; // stage = k%S, fill = k/S (how often the stage has been filled before), prev_stage = (k-G)%S: kept incrementally, S is a run-time value
-	for(uint32_t k=g; k<n; k+=G, cur = advance(cur, G)) {
+	const uint8_t* const my_flags = L.flags+((uint64_t)(L.Hx+x0)+(uint64_t)(R.y0+threadIdx.y)*L.Nx+(uint64_t)R.z0*flag_plane);
+	const uint32_t flag_rows = by*L.Nx; // bytes between consecutive tile row groups
+	uint32_t* const flag_words = reinterpret_cast<uint32_t*>(smem+ROW_BARRIERS)+2u*t; // [2 buffers][T threads][2 words]
+	auto flag_address = [&](Pos p) -> uintptr_t { return reinterpret_cast<uintptr_t>(my_flags+(uint64_t)p.yb*flag_rows+(uint64_t)p.zo*flag_plane); };
+	auto request_flags = [&](Pos p, uint32_t buffer) {
+		const uintptr_t a = flag_address(p);
+		cp_async4(flag_words+2u*T*buffer, reinterpret_cast<const void*>(a&~(uintptr_t)3u));
+		if(a&3u) cp_async4(flag_words+2u*T*buffer+1u, reinterpret_cast<const void*>((a&~(uintptr_t)3u)+4u));
+		cp_async_commit();
+	};
+	auto take_flags = [&](Pos p, uint32_t buffer) -> uint32_t {
+		cp_async_wait<0>();
+		const uint32_t sh = 8u*(uint32_t)(flag_address(p)&3u), w0 = flag_words[2u*T*buffer];
+		return sh==0u ? w0 : (w0>>sh)|(flag_words[2u*T*buffer+1u]<<(32u-sh));
+	};
+	if(n>0u) request_flags(cur, 0u);
+	// my vector in set 0 of a stage, and the elements right / left of it that the x-shifted directions reach: the next / previous thread's,
+	// or -- at the row ends -- the halo element in the pad (x halos) or the other end of the periodic row
+	const uint32_t tb = PAD+t*VB;
+	const bool last = threadIdx.x+1u==bx, firstt = threadIdx.x==0u;
+	const uint32_t up = (!hx && last) ? tb+VB-row_bytes : tb+VB, dn = (!hx && firstt) ? tb+row_bytes-ESZ : tb-ESZ; // byte offsets in the set
+	uint32_t stage = 0u, fill = 0u, prev_stage = 0u; // stage = k%S, fill = k/S (how often the stage has been filled before), prev_stage = (k-1)%S
+	for(uint32_t k=0u; k<n; k++) {
 		const uint32_t y0 = R.y0+cur.yb*by, y = y0+threadIdx.y, z = R.z0+cur.zo;
-		// A parity wait can only tell a phase from its neighbours: waiting for fill m of a stage is sound only once fill m-1 is known to be complete.
-		// From k = S+G on that follows from the schedule (this group's previous tile k-G was loaded by the group that had just consumed fill m-1 of
-		// this very stage). Tiles S..S+G-1 are second fills whose predecessors were prologue loads consumed by ANOTHER group at an unrelated time --
-		// waiting for "phase 0" on full[] would hang if fill 1 has already landed too -- so that group reports on a one-shot barrier of its own.
-		if(k>=S && k<S+G) mbar_wait_n(first_fill+stage, 0u);
-		mbar_wait_n(full+stage, fill&1u);
-		if(k<G && t==0u) mbar_arrive(first_fill+stage);
-		const uint32_t flags4 = combine_flags(cur);
-		unsigned char* const sb = ring+(size_t)stage*STAGE+threadIdx.y*RB+PAD; // element 0 of my row in buffer 0
+		mbar_wait(full+stage, fill&1u);
+		const uint32_t flags4 = take_flags(cur, k&1u);
+		unsigned char* const sb = ring+(size_t)stage*STAGE;
 		// ---- stream in from the stage: my vectors, and for the x-shifted directions the element beyond them ----
 		PK A[Q];
-		static_for<0, Q, 1>([&](auto I) { A[I].load(reinterpret_cast<const E*>(sb+(size_t)I.value*SET)+x0); });
+		static_for<0, Q, 1>([&](auto I) { A[I].load(reinterpret_cast<const E*>(sb+(size_t)I.value*SET+tb)); });
 		static_for<1, Q, 2>([&](auto I) {
 			constexpr int i = I;
-			const E* rowp = reinterpret_cast<const E*>(sb+(size_t)(i+1)*SET);
-			if constexpr(dir_x(i)>0) A[i+1].push_back(PK::bits(hx ? rowp[x0+(uint32_t)K] : rowp[x0+(uint32_t)K==W ? 0u : x0+(uint32_t)K]));
-			else if constexpr(dir_x(i)<0) A[i+1].push_front(PK::bits(hx ? *(rowp+x0-1) : rowp[x0==0u ? W-1u : x0-1u]));
+			if constexpr(dir_x(i)>0) A[i+1].push_back(PK::bits(*reinterpret_cast<const E*>(sb+(size_t)(i+1)*SET+up)));
+			else if constexpr(dir_x(i)<0) A[i+1].push_front(PK::bits(*reinterpret_cast<const E*>(sb+(size_t)(i+1)*SET+dn)));
 		});
-		group_sync(g); // the whole group has read the stage before anybody writes results into it
-		// refill the stage of this group's previous tile now rather than right after its stores: they have had the stream-in above
-		// to finish reading it, so the copying threads rarely wait here
-		if(k>=G && k-G+S<n) { const Pos p = advance(cur, S-G); if(copier) bulk_wait_read(); load_tile(R.y0+p.yb*by, R.z0+p.zo, prev_stage); }
-		if(k+G<n) request_flags(advance(cur, G));
+		__syncthreads(); // everybody has read the stage before anybody writes results into it
+		// refill the stage of the previous tile now rather than right after its stores: they have had the stream-in above to finish
+		// reading it, so the copying threads rarely wait here
+		if(k>=1u && k-1u+S<n) { const Pos p = advance(cur, S-1u); if(copier) bulk_wait_read(); load_tile(R.y0+p.yb*by, R.z0+p.zo, prev_stage); }
+		const Pos next = advance(cur, 1u);
+		if(k+1u<n) request_flags(next, (k+1u)&1u);
 		collide_tile<Q, COLL, ST, VF, K, SG, MB>(L, A, flags4, L.Hx+x0, y, z);
 		// ---- stream out into the same row buffers ----
-		A[0].store(reinterpret_cast<E*>(sb)+x0);
+		A[0].store(reinterpret_cast<E*>(sb+tb));
 		static_for<1, Q, 2>([&](auto I) {
 			constexpr int i = I;
-			A[i].store(reinterpret_cast<E*>(sb+(size_t)i*SET)+x0);
-			E* rowp = reinterpret_cast<E*>(sb+(size_t)(i+1)*SET);
-			if constexpr(dir_x(i)==0) A[i+1].store(rowp+x0);
-			else if constexpr(dir_x(i)>0) { if(hx) A[i+1].store_seg_up(rowp, x0); else A[i+1].store_row_up(rowp, x0, W); }
-			else { if(hx) A[i+1].store_seg_down(rowp, x0); else A[i+1].store_row_down(rowp, x0, W); }
+			A[i].store(reinterpret_cast<E*>(sb+(size_t)i*SET+tb));
+			unsigned char* const q = sb+(size_t)(i+1)*SET;
+			if constexpr(dir_x(i)==0) A[i+1].store(reinterpret_cast<E*>(q+tb));
+			else if constexpr(dir_x(i)>0) A[i+1].store_shift_up(reinterpret_cast<E*>(q+tb), reinterpret_cast<E*>(q+up));
+			else A[i+1].store_shift_down(reinterpret_cast<E*>(q+tb), reinterpret_cast<E*>(q+dn));
 		});
 		fence_async_smem();
-		group_sync(g);
+		__syncthreads();
 		store_tile(y0, z, stage);
-		prev_stage = stage; stage += G;
-		if(stage>=S) { stage -= S; fill++; }
+		cur = next;
+		prev_stage = stage; stage++;
+		if(stage==S) { stage = 0u; fill++; }
 	}
 	if(copier) bulk_wait_all();
 }
@@ -1186,8 +1196,11 @@ __global__ void __launch_bounds__(128) k_stream_collide_v1(const Lattice L, cons
 #ifndef FX3D_OCC_MINBLOCKS
 #define FX3D_OCC_MINBLOCKS 8
 #endif
+#ifndef FX3D_OCC_THREADS
+#define FX3D_OCC_THREADS 128
+#endif
 template<int Q, int COLL, int ST, bool VF, int ODD>
-__global__ void __launch_bounds__(128, FX3D_OCC_MINBLOCKS) k_stream_collide_occ(const Lattice L, const Region R) {
+__global__ void __launch_bounds__(FX3D_OCC_THREADS, FX3D_OCC_MINBLOCKS) k_stream_collide_occ(const Lattice L, const Region R) {
 	typedef Codec<ST> C;
 	typedef typename C::elem_t E;
 	uint32_t x, y, z;

@@ -42,44 +42,49 @@ template<int Q, int COLL, int ST, bool VF> static int launch_pipe(const Lattice&
 	return L.odd ? launch_pipe_parity<Q, COLL, ST, VF, 1>(L, R, block, stream, reserve) : launch_pipe_parity<Q, COLL, ST, VF, 0>(L, R, block, stream, reserve);
 }
 
-// bulk-copy (TMA) kernel: the tile must span whole rows -- see the kernel's header comment. Block = (bx, 128/bx, G), B blocks per SM; the ring
-// depth S is whatever fits this block's share of the SM's shared memory (228 KB, 1 KB of it reserved per resident block), at least G+1.
-template<int Q, int ST> static uint32_t row_stages(const dim3& block) {
-	const uint32_t stage = row_stage_bytes((uint32_t)Q, ST==ST_FP32 ? 4u : 2u, block.x, block.y), B = (uint32_t)row_blocks<Q, ST>();
-	const uint32_t share = std::min<uint32_t>(227u*1024u, (228u*1024u)/B-1024u);
-	return std::min<uint32_t>(ROW_MAX_STAGES, (share-ROW_HEADER)/stage);
+// bulk-copy (TMA) kernel: the tile must span whole rows -- see the kernel's header comment. Block = (bx, T/bx) with bx = row cells / K, B blocks per
+// SM; the ring depth S is whatever fits this block's share of the SM's shared memory (228 KB, 1 KB of it reserved per resident block), at least 2.
+template<int Q, int ST> static uint32_t row_stages() {
+	constexpr uint32_t stage = row_stage_bytes<Q, ST>(), B = (uint32_t)row_blocks<Q, ST>();
+	constexpr uint32_t share = (228u*1024u)/B-1024u<227u*1024u ? (228u*1024u)/B-1024u : 227u*1024u;
+	return std::min<uint32_t>(ROW_MAX_STAGES, (share-row_header<Q, ST>())/stage);
 }
-template<int Q, int ST> static bool tma_eligible(const Lattice& L, const Region& R, const dim3& block) {
+template<int Q, int ST> static dim3 row_block(const Lattice& L) { // (0,0,0) where the row does not divide into the block
+	constexpr uint32_t K = (uint32_t)row_cells<Q, ST>(), T = row_threads<Q, ST>();
+	const uint32_t inner = L.Nx-2u*L.Hx, bx = inner/K;
+	if(inner%K!=0u || bx==0u || bx>T || T%bx!=0u) return dim3(0u, 0u, 0u);
+	return dim3(bx, T/bx, 1u);
+}
+template<int Q, int ST> static bool tma_eligible(const Lattice& L, const Region& R) {
 	const uint32_t esz = ST==ST_FP32 ? 4u : 2u, inner = L.Nx-2u*L.Hx;
-	if(R.g0!=0u || R.g1*4u!=inner || block.x*4u!=inner || block.x*block.y!=128u || (inner*esz)%16u!=0u || (R.y1-R.y0)%block.y!=0u) return false;
-	if(L.Hx ? ((L.xo+1u)*esz)%16u!=0u : L.xo!=0u) return false; // the first non-halo cell of a row starts a 16-byte chunk
-	return row_stages<Q, ST>(block)>=(uint32_t)row_groups<Q, ST>()+1u;
+	const dim3 block = row_block<Q, ST>(L);
+	if(block.x==0u || R.g0!=0u || R.g1*4u!=inner || (inner*esz)%16u!=0u || (R.y1-R.y0)%block.y!=0u) return false;
+	if(L.Hx ? (block.y!=1u || ((L.xo+1u)*esz)%16u!=0u) : L.xo!=0u) return false; // x halos: one-row tiles, the first non-halo cell starts a 16-byte chunk
+	return row_stages<Q, ST>()>=2u;
 }
-// stand-in for the emulation's one-tile-per-call pacing and for regions that are only a few tiles: fewer groups than the kernel was
-// built for would need another instantiation, so small regions simply leave some groups idle
-template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false> static int launch_tma_parity(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve, const RowPeers& peers) {
+template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false> static int launch_tma_parity(const Lattice& L, const Region& R, void* stream, int reserve, const RowPeers& peers) {
+	const dim3 block = row_block<Q, ST>(L);
 	const uint32_t tiles_y = (R.y1-R.y0)/block.y, nz = R.z1-R.z0;
-	constexpr uint32_t G = (uint32_t)row_groups<Q, ST>();
-	const uint32_t S = row_stages<Q, ST>(block);
-	const uint32_t smem = ROW_HEADER+S*row_stage_bytes((uint32_t)Q, ST==ST_FP32 ? 4u : 2u, block.x, block.y);
-	int sms = 148;
+	const uint32_t S = row_stages<Q, ST>();
+	const uint32_t smem = row_header<Q, ST>()+S*row_stage_bytes<Q, ST>();
+	int sms = 148, per_sm = row_blocks<Q, ST>();
 #if !defined(FX3D_HOST_EMULATION)
-	static std::atomic<uint32_t> configured[64]; // per instantiation and device: the opt-in shared memory size that is set (the ring depth depends on the tile shape)
+	static std::atomic<uint64_t> configured{0ull}; // per instantiation: bit d = the opt-in shared memory size is set on device d
 	int dev = 0; cudaGetDevice(&dev);
-	if(dev>=64 || configured[dev].load()!=smem) {
+	if(dev>=64 || !((configured.load()>>dev)&1ull)) {
 		const cudaError_t e = cudaFuncSetAttribute(k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if(e!=cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(stream_collide_tma)");
-		if(dev<64) configured[dev].store(smem);
+		if(dev<64) configured.fetch_or(1ull<<dev);
 	}
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 #else
-	sms = 2;
+	sms = 2; per_sm = 1;
 #endif
-	const uint64_t all_blocks = (uint64_t)sms*(uint64_t)row_blocks<Q, ST>(), take = (uint64_t)std::max(reserve, 0)*(uint64_t)row_blocks<Q, ST>()/4ull, blocks = all_blocks>2ull*take ? all_blocks-take : all_blocks, ntiles = (uint64_t)tiles_y*nz;
+	const uint64_t all_blocks = (uint64_t)sms*(uint64_t)per_sm, blocks = all_blocks>2ull*(uint64_t)std::max(reserve, 0) ? all_blocks-(uint64_t)std::max(reserve, 0) : all_blocks, ntiles = (uint64_t)tiles_y*nz;
 	if(ntiles==0ull) return FX3D_OK;
-	const dim3 grid((uint32_t)std::min<uint64_t>((ntiles+G-1u)/G, blocks), 1u, 1u);
+	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, blocks), 1u, 1u);
 	g_kind_launches[3]++;
-	FX3D_LAUNCH_SMEM((k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG, MB>), grid, dim3(block.x, block.y, G), smem, stream, L, R, tiles_y, S, peers);
+	FX3D_LAUNCH_SMEM((k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG, MB>), grid, block, smem, stream, L, R, tiles_y, S, peers);
 	return check_launch("stream_collide (bulk copies)");
 }
 // row segments (rows longer than 512 cells, shapes the whole-row kernel does not take): bulk loads, direct stores
@@ -118,8 +123,8 @@ template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = f
 template<int Q, int COLL, int ST, bool VF, bool SG = false, bool MB = false> static int launch_hyb(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve) {
 	return L.odd ? launch_hyb_parity<Q, COLL, ST, VF, 1, SG, MB>(L, R, block, stream, reserve) : launch_hyb_parity<Q, COLL, ST, VF, 0, SG, MB>(L, R, block, stream, reserve);
 }
-template<int Q, int COLL, int ST, bool VF, bool SG = false, bool MB = false> static int launch_tma(const Lattice& L, const Region& R, const dim3& block, void* stream, int reserve, const RowPeers& peers) {
-	return L.odd ? launch_tma_parity<Q, COLL, ST, VF, 1, SG, MB>(L, R, block, stream, reserve, peers) : launch_tma_parity<Q, COLL, ST, VF, 0, SG, MB>(L, R, block, stream, reserve, peers);
+template<int Q, int COLL, int ST, bool VF, bool SG = false, bool MB = false> static int launch_tma(const Lattice& L, const Region& R, void* stream, int reserve, const RowPeers& peers) {
+	return L.odd ? launch_tma_parity<Q, COLL, ST, VF, 1, SG, MB>(L, R, stream, reserve, peers) : launch_tma_parity<Q, COLL, ST, VF, 0, SG, MB>(L, R, stream, reserve, peers);
 }
 
 template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region& R, int cells_per_thread, int collision, bool volume_force, void* stream, int reserve, int ext, const RowPeers* fused) {
@@ -129,12 +134,28 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 	peers.fi[4] = L.fi;
 	Lattice Lk = L; // the whole-row kernel routes halo rows by Hy/Hz: unfused launches see no y/z halos (rows then stay where the general rule puts them: here)
 	if(!fused) { Lk.Hy = 0u; Lk.Hz = 0u; }
-	if(cells_per_thread==-100) return tma_eligible<Q, ST>(L, R, block_shape(R.g1-R.g0)) ? FX3D_OK : 1; // query: would the whole-row kernel take this region?
+	if(cells_per_thread==-100) return tma_eligible<Q, ST>(L, R) ? FX3D_OK : 1; // query: would the whole-row kernel take this region?
+#if defined(FX3D_TUNE_ONLY) // tuning builds (tools/build_variant.sh): only the whole-row kernel of the benchmark lines (SRT, no force, no extensions) is instantiated
+	{
+		if(cells_per_thread==32 && ext==0 && collision==COLL_SRT && !volume_force) { // the occupancy form, block shape from FX3D_OCC_BX
+#ifndef FX3D_OCC_BX
+#define FX3D_OCC_BX 128
+#endif
+			const dim3 block(FX3D_OCC_BX, 1u, 1u), grid((R.g1-R.g0+block.x-1u)/block.x, R.y1-R.y0, R.z1-R.z0);
+			g_kind_launches[6]++;
+			if(L.odd) FX3D_LAUNCH((k_stream_collide_occ<Q, COLL_SRT, ST, false, 1>), grid, block, stream, L, R); else FX3D_LAUNCH((k_stream_collide_occ<Q, COLL_SRT, ST, false, 0>), grid, block, stream, L, R);
+			return check_launch("stream_collide (one cell per thread, high occupancy)");
+		}
+		const dim3 block = block_shape(R.g1-R.g0);
+		if(ext!=0 || cells_per_thread>0 || collision!=COLL_SRT || volume_force || !tma_eligible<Q, ST>(L, R)) { set_error("tuning build: whole-row SRT kernel only"); return FX3D_ERR_INVALID; }
+		return launch_tma<Q, COLL_SRT, ST, false>(Lk, R, stream, reserve, peers);
+	}
+#else
 	if(ext!=0) { // SUBGRID (bit 0) and/or MOVING_BOUNDARIES (bit 1): the whole-row bulk-copy kernel (cells_per_thread 0, regions in groups of 4) or the general kernel (1)
 		const dim3 block = block_shape(R.g1-R.g0);
 		const bool sg = (ext&1)!=0, mb = (ext&2)!=0;
 		if(cells_per_thread==0) {
-			if(!tma_eligible<Q, ST>(L, R, block)) { // row segments: bulk loads + direct stores; else nothing launched, the caller falls back to the general kernel
+			if(!tma_eligible<Q, ST>(L, R)) { // row segments: bulk loads + direct stores; else nothing launched, the caller falls back to the general kernel
 				if(!tmaseg_eligible<Q, ST>(L, R, block)) return 1;
 #define FX3D_HYB_EXT(COLL, VF) (sg ? (mb ? launch_hyb<Q, COLL, ST, VF, true, true>(L, R, block, stream, reserve) : launch_hyb<Q, COLL, ST, VF, true, false>(L, R, block, stream, reserve)) \
                                    : launch_hyb<Q, COLL, ST, VF, false, true>(L, R, block, stream, reserve))
@@ -142,8 +163,8 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 				return volume_force ? FX3D_HYB_EXT(COLL_TRT, true) : FX3D_HYB_EXT(COLL_TRT, false);
 #undef FX3D_HYB_EXT
 			}
-#define FX3D_TMA_EXT(COLL, VF) (sg ? (mb ? launch_tma<Q, COLL, ST, VF, true, true>(Lk, R, block, stream, reserve, peers) : launch_tma<Q, COLL, ST, VF, true, false>(Lk, R, block, stream, reserve, peers)) \
-                                   : launch_tma<Q, COLL, ST, VF, false, true>(Lk, R, block, stream, reserve, peers))
+#define FX3D_TMA_EXT(COLL, VF) (sg ? (mb ? launch_tma<Q, COLL, ST, VF, true, true>(Lk, R, stream, reserve, peers) : launch_tma<Q, COLL, ST, VF, true, false>(Lk, R, stream, reserve, peers)) \
+                                   : launch_tma<Q, COLL, ST, VF, false, true>(Lk, R, stream, reserve, peers))
 			if(collision==COLL_SRT) return volume_force ? FX3D_TMA_EXT(COLL_SRT, true) : FX3D_TMA_EXT(COLL_SRT, false);
 			return volume_force ? FX3D_TMA_EXT(COLL_TRT, true) : FX3D_TMA_EXT(COLL_TRT, false);
 #undef FX3D_TMA_EXT
@@ -158,11 +179,11 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 	}
 	if(cells_per_thread<=0) { // persistent kernels; R.g0/g1 are in groups of pipe_cells<Q,ST>() cells. 0: bulk copies where the tile spans the row, else cp.async; -1: cp.async
 		const dim3 block = block_shape(R.g1-R.g0);
-		const bool rows = tma_eligible<Q, ST>(L, R, block);
+		const bool rows = tma_eligible<Q, ST>(L, R);
 		if(cells_per_thread==-2 && !rows) return 1; // -2: bulk copies of whole rows or nothing (regions in groups of 4 cells); 1 = "not eligible", no launch
 		if(rows && (cells_per_thread==-2 || ((cells_per_thread==0 || cells_per_thread==-3) && pipe_cells<Q, ST>()==4))) {
-			if(collision==COLL_SRT) return volume_force ? launch_tma<Q, COLL_SRT, ST, true>(Lk, R, block, stream, reserve, peers) : launch_tma<Q, COLL_SRT, ST, false>(Lk, R, block, stream, reserve, peers);
-			return volume_force ? launch_tma<Q, COLL_TRT, ST, true>(Lk, R, block, stream, reserve, peers) : launch_tma<Q, COLL_TRT, ST, false>(Lk, R, block, stream, reserve, peers);
+			if(collision==COLL_SRT) return volume_force ? launch_tma<Q, COLL_SRT, ST, true>(Lk, R, stream, reserve, peers) : launch_tma<Q, COLL_SRT, ST, false>(Lk, R, stream, reserve, peers);
+			return volume_force ? launch_tma<Q, COLL_TRT, ST, true>(Lk, R, stream, reserve, peers) : launch_tma<Q, COLL_TRT, ST, false>(Lk, R, stream, reserve, peers);
 		}
 		if(fused) return 1; // the caller asked for fused halo delivery, which only the whole-row kernel provides
 		if((cells_per_thread==0 || cells_per_thread==-3) && pipe_cells<Q, ST>()==4 && tmaseg_eligible<Q, ST>(L, R, block)) { // row segments: bulk loads, direct stores
@@ -196,6 +217,7 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 #undef FX3D_SCV
 #undef FX3D_SC
 	return check_launch("stream_collide");
+#endif
 }
 template int launch_stream_collide<FX3D_Q, FX3D_ST>(const Lattice&, const Region&, int, int, bool, void*, int, int, const RowPeers*);
 

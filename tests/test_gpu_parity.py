@@ -154,9 +154,9 @@ def test_hybrid_kernel_bit_exact(fx, v, dims, D):
         for a, b in zip(got, want):
             assert np.array_equal(bits(a), bits(b)), steps
     after = capi.lib().kernel_kind_counts()
-    if (dims[0] // D[0]) > 512:
+    if (dims[0] // D[0]) != 512:
         assert after[5] > before[5] and after[:5] == before[:5], "the hybrid kernel must be the one that ran"
-    else:  # x-decomposed domains whose rows fit one tile: the whole-row kernel takes them (halo cells in the row-buffer pads)
+    else:  # x-decomposed domains whose rows are exactly one tile: the whole-row kernel takes them (halo cells in the row-buffer pads)
         assert after[3] > before[3] and after[:3] == before[:3] and after[5] == before[5], "the whole-row bulk-copy kernel must be the one that ran"
 
 
