@@ -728,8 +728,36 @@ FX3D_HD void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "m
 FX3D_HD void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); } // my shared-memory writes become visible to the bulk-copy engine
 #endif
 
+// one lane of a converged warp (always the same one for the full mask): the form of "lane 0 only" that lets ptxas issue a uniform-datapath
+// instruction (UBLKCP) once instead of looping over the lanes it believes may be active
+FX3D_HD bool elect_one(uint32_t lane) {
+#if defined(FX3D_HOST_EMULATION) || defined(FX3D_ROW_NO_ELECT)
+	return lane==0u;
+#else
+	uint32_t p; asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xFFFFFFFF;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(p)); (void)lane; return p!=0u;
+#endif
+}
+// The lambdas of the whole-row kernel capture the kernel's locals by reference; if the compiler decides not to inline one of them (it did, for the
+// D3Q27 FP32 instances inside the full translation unit: 736 bytes of stack, the wind-tunnel line at half speed) every captured local and the
+// Lattice parameter are forced into local memory. Hence: always inline.
+#define FX3D_LAMBDA __attribute__((always_inline))
 // y/z neighbours of a domain for the fused halo delivery: fi[(dy+1)+3*(dz+1)], [4] = the domain itself; unused entries null
 struct RowPeers { void* fi[9]; };
+// Byte offset of buffer j of a tile from the tile's own address (slot 0, first tile row), for tiles none of whose rows or neighbour rows wrap
+// around or belong to another domain -- all but the tiles next to the y/z faces. Worked out on the host per launch (the slot of a buffer depends
+// on the step parity); the kernel reads them from constant memory, one 64-bit uniform load per copy.
+struct RowOffsets { long long c[27]; };
+template<int Q> inline RowOffsets row_offsets(const Lattice& L, uint32_t esz) {
+	RowOffsets O;
+	for(int j=0; j<27; j++) {
+		const int i = j==0 ? 0 : (j&1) ? j : j-1;
+		const bool local = j==0 || (j&1);
+		const long long slot = j==0 ? 0 : local ? (L.odd ? i : i+1) : (L.odd ? i+1 : i);
+		const long long ey = (local || j>=Q) ? 0 : dir_c(1, i), ez = (local || j>=Q) ? 0 : dir_c(2, i);
+		O.c[j] = j<Q ? (slot*(long long)L.slot+ey*(long long)L.px+ez*(long long)L.px*(long long)L.Ny)*(long long)esz : 0ll;
+	}
+	return O;
+}
 // Resident blocks per SM of the whole-row kernel (also its register cap, 65536/(128*B)) and the ring depth, measured on B200
 // (profiles/r02_row_kernel_tuning.txt).
 #ifndef FX3D_ROW_BLOCKS_16
@@ -741,8 +769,11 @@ struct RowPeers { void* fi[9]; };
 #ifndef FX3D_ROW_BLOCKS_27
 #define FX3D_ROW_BLOCKS_27 3 // D3Q27 with 16-bit storage: 168 registers
 #endif
+#ifndef FX3D_ROW_STRIDED
+#define FX3D_ROW_STRIDED 1 // tile order: 1 = y-fastest, dealt round-robin to the blocks; 0 = one contiguous z-fastest share per block
+#endif
 #ifndef FX3D_ROW_MAX_STAGES
-#define FX3D_ROW_MAX_STAGES 8
+#define FX3D_ROW_MAX_STAGES 16
 #endif
 template<int Q, int ST> FX3D_HDC constexpr int row_blocks() { return ST==ST_FP32 ? FX3D_ROW_BLOCKS_32 : (Q>19 ? FX3D_ROW_BLOCKS_27 : FX3D_ROW_BLOCKS_16); }
 // Cells per thread K (4 or 2) and threads per block T of the whole-row kernel; a tile is K*T cells. Fewer cells per thread = more warps working on
@@ -767,19 +798,20 @@ template<int Q, int ST> FX3D_HDC constexpr int row_blocks() { return ST==ST_FP32
 #endif
 template<int Q, int ST> FX3D_HDC constexpr int row_cells() { return ST==ST_FP32 ? FX3D_ROW_K_32 : (Q>19 ? FX3D_ROW_K_27 : FX3D_ROW_K_16); }
 template<int Q, int ST> FX3D_HDC constexpr uint32_t row_threads() { return ST==ST_FP32 ? FX3D_ROW_T_32 : (Q>19 ? FX3D_ROW_T_27 : FX3D_ROW_T_16); }
-constexpr uint32_t ROW_PAD = 16u, ROW_MAX_STAGES = FX3D_ROW_MAX_STAGES, ROW_BARRIERS = 128u;
-template<int Q, int ST> FX3D_HDC constexpr uint32_t row_header() { return ROW_BARRIERS+2u*row_threads<Q, ST>()*8u; } // header: full[<=16] mbarriers, then two buffers of T x 2 flag words
+constexpr uint32_t ROW_PAD = 16u, ROW_MAX_STAGES = FX3D_ROW_MAX_STAGES<16 ? FX3D_ROW_MAX_STAGES : 16u, ROW_BARRIERS = 128u;
+template<int Q, int ST> FX3D_HDC constexpr uint32_t row_header() { return ROW_BARRIERS+2u*row_threads<Q, ST>()*8u; } // header: full[<=16] mbarriers, then two buffers of T x 2 flag words (rows whose flags cannot travel by bulk copy)
 template<int Q, int ST> FX3D_HDC constexpr uint32_t row_set_bytes() { return row_threads<Q, ST>()*(uint32_t)row_cells<Q, ST>()*(ST==ST_FP32 ? 4u : 2u)+2u*ROW_PAD; } // one slot's rows of a tile: [pad | K*T elements | pad]
-template<int Q, int ST> FX3D_HDC constexpr uint32_t row_stage_bytes() { return (uint32_t)Q*row_set_bytes<Q, ST>(); }
+template<int Q, int ST> FX3D_HDC constexpr uint32_t row_stage_bytes() { return (uint32_t)Q*row_set_bytes<Q, ST>()+row_threads<Q, ST>()*(uint32_t)row_cells<Q, ST>(); } // Q sets + the flag bytes of the tile
 
 template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false>
-__global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_stream_collide_tma(const Lattice L, const Region R, const uint32_t tiles_y, const uint32_t S, const RowPeers P) {
+__global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_stream_collide_tma(const Lattice L, const Region R, const uint32_t tiles_y, const uint32_t S, const RowPeers P, const RowOffsets O) {
 	constexpr int K = row_cells<Q, ST>();
 	constexpr uint32_t T = row_threads<Q, ST>(), NW = T/32u; // threads and warps per block
+	static_assert(K==4 && T==128u, "measured on B200: two cells per thread (256 threads per tile) gains nothing for FP32 and loses a third for 16-bit storage; 64-thread blocks for 256-cell rows are no faster either");
 	typedef Codec<ST> C;
 	typedef typename C::elem_t E;
 	typedef Pack<ST, K> PK;
-	constexpr uint32_t VB = (uint32_t)(sizeof(E)*K), ESZ = (uint32_t)sizeof(E), PAD = ROW_PAD, SET = row_set_bytes<Q, ST>(), STAGE = (uint32_t)Q*SET;
+	constexpr uint32_t VB = (uint32_t)(sizeof(E)*K), ESZ = (uint32_t)sizeof(E), PAD = ROW_PAD, SET = row_set_bytes<Q, ST>(), STAGE = row_stage_bytes<Q, ST>();
 	unsigned char* const smem = dynamic_smem();
 	uint64_t* const full = reinterpret_cast<uint64_t*>(smem); // full[stage]: the bulk loads of the tile in this stage have landed
 	unsigned char* const ring = smem+row_header<Q, ST>();
@@ -791,9 +823,6 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 	// where a row's copy starts in its pitch row (bytes), how much it covers, and where that lands in the set
 	const uint32_t g_off = hx ? (L.xo+1u)*ESZ-PAD : 0u, copy_bytes = hx ? row_bytes+2u*PAD : row_bytes, s_off = hx ? 0u : PAD;
 	const uint32_t ncopies = (uint32_t)Q*by;
-	const bool one_row = by==1u;
-	const uint32_t first_copy = warp+NW*lane; // multi-row tiles: copy c = ty*Q+j belongs to lane c/NW of warp c%NW (then every T-th)
-	const bool copier = one_row ? lane==0u : first_copy<ncopies;
 	if(t==0u) { for(uint32_t s=0u; s<S; s++) mbar_init(full+s); }
 	fence_async_smem();
 	__syncthreads();
@@ -801,7 +830,7 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 	// ---- global address of the copy of buffer j of the tile row at (y, z); a stored row may belong to a y/z neighbour (see the header) ----
 	const uint32_t plane = L.px*L.Ny; // elements per z plane of one slot (the padded slot holds < 2^32 elements)
 	const bool fused = hy || hz; // some stored rows belong to a y/z neighbour
-	auto row_address = [&](bool store, uint32_t slot, bool local, int ey, int ez, uint32_t y, uint32_t z) -> char* {
+	auto row_address = [&](bool store, uint32_t slot, bool local, int ey, int ez, uint32_t y, uint32_t z) FX3D_LAMBDA -> char* {
 		uint32_t yr = y, zr = z;
 		if(!local) { yr = step_rt(ey, y, L.Ny); zr = step_rt(ez, z, L.Nz); }
 		char* base = reinterpret_cast<char*>(L.fi);
@@ -814,61 +843,88 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 			yr = (uint32_t)((int)yr-dy*(int)(L.Ny-2u)); zr = (uint32_t)((int)zr-dz*(int)(L.Nz-2u));
 			if(dy!=0 || dz!=0) base = reinterpret_cast<char*>(P.fi[(dy+1)+3*(dz+1)]);
 		}
+#if defined(FX3D_ROW_ADDR_CXX)
+		return base+((uint64_t)slot*L.slot+(uint64_t)(yr*L.px+zr*plane))*ESZ+g_off;
+#else
 		return mad_wide(yr*L.px+zr*plane, ESZ, mad_wide(L.slot32, slot*ESZ, base))+g_off; // two IMAD.WIDE: the element offset inside a slot fits 32 bits
+#endif
 	};
-	auto copy_one_row = [&](auto LOAD, auto STORE_ELSEWHERE, uint32_t y, uint32_t z, uint32_t stage) { // lane 0 of every warp: its share of the Q copies, everything but y and z known at compile time
+	auto copy_rows = [&](auto LOAD, auto STORE_ELSEWHERE, uint32_t y0, uint32_t z, uint32_t stage) FX3D_LAMBDA { // one lane of every warp: its share of the Q buffers, everything but y and z known at compile time
 		constexpr bool load = decltype(LOAD)::value;
 		unsigned char* const sb = ring+(size_t)stage*STAGE+s_off;
-		auto one = [&](auto J) {
+		auto one = [&](auto J) FX3D_LAMBDA {
 			constexpr int j = J;
 			constexpr int i = j==0 ? 0 : (j&1) ? j : j-1; // odd member of the direction pair
 			constexpr uint32_t slot = j==0 ? 0u : (j&1) ? (ODD ? (uint32_t)i : (uint32_t)i+1u) : (ODD ? (uint32_t)i+1u : (uint32_t)i);
 			constexpr bool local = j==0 || (j&1);
 			constexpr int ey = j==0 ? 0 : dir_y(i), ez = j==0 ? 0 : dir_z(i);
-			char* gp = row_address(decltype(STORE_ELSEWHERE)::value && j!=0, slot, local, ey, ez, y, z);
+			_Pragma("unroll 1") for(uint32_t ty=0u; ty<by; ty++) { // (a uniform loop; one pass for one-row tiles)
+				char* gp = row_address(decltype(STORE_ELSEWHERE)::value && j!=0, slot, local, ey, ez, y0+ty, z);
+				if constexpr(load) bulk_load(sb+(size_t)j*SET+ty*row_bytes, gp, copy_bytes, full+stage); else bulk_store(gp, sb+(size_t)j*SET+ty*row_bytes, copy_bytes);
+			}
+		};
+		// one-row tiles away from the y/z faces (no row wraps, none is delivered to a neighbour): tile address + a per-buffer constant. (For many-row tiles
+		// the same shortcut measured 9 % SLOWER on 256^3 grids than the general addresses -- not understood, left out.)
+		auto plain_one_row = [&](auto J) FX3D_LAMBDA {
+			constexpr int j = J;
+			char* gp = reinterpret_cast<char*>(L.fi)+((uint64_t)(y0*L.px+z*plane)*ESZ+g_off)+O.c[j];
 			if constexpr(load) bulk_load(sb+(size_t)j*SET, gp, copy_bytes, full+stage); else bulk_store(gp, sb+(size_t)j*SET, copy_bytes);
 		};
-		static_for<0, (int)NW, 1>([&](auto Wc) { if(warp==(uint32_t)Wc.value) static_for<Wc.value, Q, (int)NW>(one); });
+#if defined(FX3D_ROW_NO_OFFSETS)
+		const bool inner_tile = false;
+#else
+		const bool inner_tile = by==1u && y0>=2u && y0+3u<=L.Ny && z>=2u && z+3u<=L.Nz;
+#endif
+		if(inner_tile) static_for<0, (int)NW, 1>([&](auto Wc) FX3D_LAMBDA { if(warp==(uint32_t)Wc.value) static_for<Wc.value, Q, (int)NW>(plain_one_row); });
+		else static_for<0, (int)NW, 1>([&](auto Wc) FX3D_LAMBDA { if(warp==(uint32_t)Wc.value) static_for<Wc.value, Q, (int)NW>(one); });
 	};
-	auto copy_any = [&](bool load, uint32_t c, uint32_t y0, uint32_t z, uint32_t stage) { // multi-row tiles: copy c, decoded at run time
-		const uint32_t ty = c/(uint32_t)Q, j = c%(uint32_t)Q;
-		uint32_t slot = 0u; bool local = true; int ey = 0, ez = 0;
-		if(j>0u) {
-			const uint32_t i = (j&1u) ? j : j-1u;
-			local = (j&1u)!=0u;
-			slot = local ? (ODD ? i : i+1u) : (ODD ? i+1u : i);
-			ey = dir_rt(1, i); ez = dir_rt(2, i);
-		}
-		char* gp = row_address(!load && j!=0u, slot, local, ey, ez, y0+ty, z);
-		unsigned char* sp = ring+(size_t)stage*STAGE+(size_t)j*SET+ty*row_bytes+s_off;
-		if(load) bulk_load(sp, gp, copy_bytes, full+stage); else bulk_store(gp, sp, copy_bytes);
-	};
-	auto load_tile = [&](uint32_t y0, uint32_t z, uint32_t stage) { // every thread of the block calls it
-		if(t==0u) mbar_expect_tx(full+stage, ncopies*copy_bytes);
-		if(copier) {
-			if(one_row) copy_one_row(std::true_type{}, std::false_type{}, y0, z, stage);
-			else for(uint32_t c=first_copy; c<ncopies; c+=T) copy_any(true, c, y0, z, stage);
+	// flag bytes: where the rows of the flag array start on 16-byte boundaries (no x halo, Nx a multiple of 16) they travel with the tile, one bulk
+	// copy per tile row into the tail of the stage; otherwise per thread, see below
+#if defined(FX3D_ROW_NO_FLAGS_BULK)
+	const bool flags_bulk = false;
+#else
+	const bool flags_bulk = !hx && (L.Nx&15u)==0u;
+#endif
+	auto load_tile = [&](uint32_t y0, uint32_t z, uint32_t stage) FX3D_LAMBDA { // every thread of the block calls it
+		if(t==0u) mbar_expect_tx(full+stage, ncopies*copy_bytes+(flags_bulk ? by*W : 0u));
+		if(elect_one(lane)) {
+			copy_rows(std::true_type{}, std::false_type{}, y0, z, stage);
+			if(flags_bulk && warp==(uint32_t)Q%NW) {
+				const uint8_t* gp = L.flags+((uint64_t)y0+(uint64_t)z*L.Ny)*L.Nx;
+				unsigned char* sp = ring+(size_t)stage*STAGE+(size_t)Q*SET;
+				_Pragma("unroll 1") for(uint32_t ty=0u; ty<by; ty++, gp += L.Nx, sp += W) bulk_load(sp, gp, W, full+stage);
+			}
 		}
 #if defined(FX3D_HOST_EMULATION)
 		__syncthreads(); // (emulation: copies happen at issue; the phase completes once every thread has made its copies)
 		if(t==0u) mbar_phase_done_emulated(full+stage);
 #endif
 	};
-	auto store_tile = [&](uint32_t y0, uint32_t z, uint32_t stage) {
-		if(!copier) return;
-		if(one_row) { if(fused) copy_one_row(std::false_type{}, std::true_type{}, y0, z, stage); else copy_one_row(std::false_type{}, std::false_type{}, y0, z, stage); }
-		else for(uint32_t c=first_copy; c<ncopies; c+=T) copy_any(false, c, y0, z, stage);
-		bulk_commit();
+	auto store_tile = [&](uint32_t y0, uint32_t z, uint32_t stage) FX3D_LAMBDA {
+		if(elect_one(lane)) {
+			if(fused) copy_rows(std::false_type{}, std::true_type{}, y0, z, stage); else copy_rows(std::false_type{}, std::false_type{}, y0, z, stage);
+			bulk_commit();
+		}
 	};
 
-	// ---- this block's contiguous share of the (row group, plane) tiles; tile k of the share uses stage k%S ----
+	// ---- this block's share of the (row group, plane) tiles; tile k of the share uses stage k%S ----
 	const uint32_t nz = R.z1-R.z0;
+	struct Pos { uint32_t yb, zo; }; // tile row group and plane offset
+#if FX3D_ROW_STRIDED
+	// tiles are numbered y-fastest and dealt round-robin to the blocks: at any moment the resident blocks work on ~gridDim.x neighbouring rows,
+	// i.e. every one of the 2Q copy streams of the device sweeps one contiguous window of memory (DRAM page locality across blocks)
+	const uint64_t ntiles = (uint64_t)tiles_y*nz;
+	const uint32_t n = ntiles>blockIdx.x ? (uint32_t)((ntiles-blockIdx.x+gridDim.x-1u)/gridDim.x) : 0u;
+	auto advance = [&](Pos p, uint32_t d) FX3D_LAMBDA -> Pos { const uint32_t yb = p.yb+d*gridDim.x; p.zo += yb/tiles_y; p.yb = yb%tiles_y; return p; }; // (d <= 16 stages, a few hundred blocks: no overflow)
+	const Pos first = Pos{ blockIdx.x%tiles_y, blockIdx.x/tiles_y };
+#else
 	const uint64_t ntiles = (uint64_t)tiles_y*nz, T0 = ntiles*blockIdx.x/gridDim.x, T1 = ntiles*(blockIdx.x+1u)/gridDim.x;
 	const uint32_t n = (uint32_t)(T1-T0);
-	struct Pos { uint32_t yb, zo; }; // tile row group and plane offset
-	auto advance = [&](Pos p, uint32_t d) -> Pos { p.zo += d; while(p.zo>=nz) { p.zo -= nz; p.yb++; } return p; };
-	Pos cur = Pos{ (uint32_t)(T0/nz), (uint32_t)(T0%nz) };
-	for(uint32_t j=0u; j<S && j<n; j++) { const Pos p = advance(cur, j); load_tile(R.y0+p.yb*by, R.z0+p.zo, j); } // prologue: the first S tiles
+	auto advance = [&](Pos p, uint32_t d) FX3D_LAMBDA -> Pos { p.zo += d; while(p.zo>=nz) { p.zo -= nz; p.yb++; } return p; };
+	const Pos first = advance(Pos{ (uint32_t)(T0/nz), (uint32_t)(T0%nz) }, 0u);
+#endif
+	for(uint32_t j=0u; j<S && j<n; j++) { const Pos p = advance(first, j); load_tile(R.y0+p.yb*by, R.z0+p.zo, j); } // prologue: the first S tiles
+	Pos cur = first;
 	const uint32_t x0 = (uint32_t)K*threadIdx.x;
 	// my 4 flag bytes: the two aligned words that hold them travel one tile ahead with per-thread cp.async into a double-buffered corner of
 	// shared memory -- no register holds a load in flight (as plain loads the words were spilled on arrival, and the spill store waited for
@@ -877,19 +933,19 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 	const uint8_t* const my_flags = L.flags+((uint64_t)(L.Hx+x0)+(uint64_t)(R.y0+threadIdx.y)*L.Nx+(uint64_t)R.z0*flag_plane);
 	const uint32_t flag_rows = by*L.Nx; // bytes between consecutive tile row groups
 	uint32_t* const flag_words = reinterpret_cast<uint32_t*>(smem+ROW_BARRIERS)+2u*t; // [2 buffers][T threads][2 words]
-	auto flag_address = [&](Pos p) -> uintptr_t { return reinterpret_cast<uintptr_t>(my_flags+(uint64_t)p.yb*flag_rows+(uint64_t)p.zo*flag_plane); };
-	auto request_flags = [&](Pos p, uint32_t buffer) {
+	auto flag_address = [&](Pos p) FX3D_LAMBDA -> uintptr_t { return reinterpret_cast<uintptr_t>(my_flags+(uint64_t)p.yb*flag_rows+(uint64_t)p.zo*flag_plane); };
+	auto request_flags = [&](Pos p, uint32_t buffer) FX3D_LAMBDA {
 		const uintptr_t a = flag_address(p);
 		cp_async4(flag_words+2u*T*buffer, reinterpret_cast<const void*>(a&~(uintptr_t)3u));
 		if(a&3u) cp_async4(flag_words+2u*T*buffer+1u, reinterpret_cast<const void*>((a&~(uintptr_t)3u)+4u));
 		cp_async_commit();
 	};
-	auto take_flags = [&](Pos p, uint32_t buffer) -> uint32_t {
+	auto take_flags = [&](Pos p, uint32_t buffer) FX3D_LAMBDA -> uint32_t {
 		cp_async_wait<0>();
 		const uint32_t sh = 8u*(uint32_t)(flag_address(p)&3u), w0 = flag_words[2u*T*buffer];
 		return sh==0u ? w0 : (w0>>sh)|(flag_words[2u*T*buffer+1u]<<(32u-sh));
 	};
-	if(n>0u) request_flags(cur, 0u);
+	if(n>0u && !flags_bulk) request_flags(cur, 0u);
 	// my vector in set 0 of a stage, and the elements right / left of it that the x-shifted directions reach: the next / previous thread's,
 	// or -- at the row ends -- the halo element in the pad (x halos) or the other end of the periodic row
 	const uint32_t tb = PAD+t*VB;
@@ -899,26 +955,26 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 	for(uint32_t k=0u; k<n; k++) {
 		const uint32_t y0 = R.y0+cur.yb*by, y = y0+threadIdx.y, z = R.z0+cur.zo;
 		mbar_wait(full+stage, fill&1u);
-		const uint32_t flags4 = take_flags(cur, k&1u);
 		unsigned char* const sb = ring+(size_t)stage*STAGE;
+		const uint32_t flags4 = flags_bulk ? (K==4 ? *reinterpret_cast<const uint32_t*>(sb+(size_t)Q*SET+t*4u) : (uint32_t)*reinterpret_cast<const uint16_t*>(sb+(size_t)Q*SET+t*2u)) : take_flags(cur, k&1u);
 		// ---- stream in from the stage: my vectors, and for the x-shifted directions the element beyond them ----
 		PK A[Q];
-		static_for<0, Q, 1>([&](auto I) { A[I].load(reinterpret_cast<const E*>(sb+(size_t)I.value*SET+tb)); });
-		static_for<1, Q, 2>([&](auto I) {
+		static_for<0, Q, 1>([&](auto I) FX3D_LAMBDA { A[I].load(reinterpret_cast<const E*>(sb+(size_t)I.value*SET+tb)); });
+		static_for<1, Q, 2>([&](auto I) FX3D_LAMBDA {
 			constexpr int i = I;
 			if constexpr(dir_x(i)>0) A[i+1].push_back(PK::bits(*reinterpret_cast<const E*>(sb+(size_t)(i+1)*SET+up)));
 			else if constexpr(dir_x(i)<0) A[i+1].push_front(PK::bits(*reinterpret_cast<const E*>(sb+(size_t)(i+1)*SET+dn)));
 		});
 		__syncthreads(); // everybody has read the stage before anybody writes results into it
 		// refill the stage of the previous tile now rather than right after its stores: they have had the stream-in above to finish
-		// reading it, so the copying threads rarely wait here
-		if(k>=1u && k-1u+S<n) { const Pos p = advance(cur, S-1u); if(copier) bulk_wait_read(); load_tile(R.y0+p.yb*by, R.z0+p.zo, prev_stage); }
+		// reading it, so the copying thread rarely waits here
+		if(k>=1u && k-1u+S<n) { const Pos p = advance(cur, S-1u); if(elect_one(lane)) bulk_wait_read(); load_tile(R.y0+p.yb*by, R.z0+p.zo, prev_stage); } // (stepping the positions without the divisions measured 4 % slower for FP16S: two more live values, more spills)
 		const Pos next = advance(cur, 1u);
-		if(k+1u<n) request_flags(next, (k+1u)&1u);
+		if(k+1u<n && !flags_bulk) request_flags(next, (k+1u)&1u);
 		collide_tile<Q, COLL, ST, VF, K, SG, MB>(L, A, flags4, L.Hx+x0, y, z);
 		// ---- stream out into the same row buffers ----
 		A[0].store(reinterpret_cast<E*>(sb+tb));
-		static_for<1, Q, 2>([&](auto I) {
+		static_for<1, Q, 2>([&](auto I) FX3D_LAMBDA {
 			constexpr int i = I;
 			A[i].store(reinterpret_cast<E*>(sb+(size_t)i*SET+tb));
 			unsigned char* const q = sb+(size_t)(i+1)*SET;
@@ -933,7 +989,7 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 		prev_stage = stage; stage++;
 		if(stage==S) { stage = 0u; fill++; }
 	}
-	if(copier) bulk_wait_all();
+	if(elect_one(lane)) bulk_wait_all();
 }
 
 // ---- row-segment tiles (rows longer than a tile, or shapes the whole-row kernel does not take) ----

@@ -84,7 +84,7 @@ template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = f
 	if(ntiles==0ull) return FX3D_OK;
 	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, blocks), 1u, 1u);
 	g_kind_launches[3]++;
-	FX3D_LAUNCH_SMEM((k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG, MB>), grid, block, smem, stream, L, R, tiles_y, S, peers);
+	FX3D_LAUNCH_SMEM((k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG, MB>), grid, block, smem, stream, L, R, tiles_y, S, peers, row_offsets<Q>(L, ST==ST_FP32 ? 4u : 2u));
 	return check_launch("stream_collide (bulk copies)");
 }
 // row segments (rows longer than 512 cells, shapes the whole-row kernel does not take): bulk loads, direct stores
@@ -147,8 +147,13 @@ template<int Q, int ST> int launch_stream_collide(const Lattice& L, const Region
 			return check_launch("stream_collide (one cell per thread, high occupancy)");
 		}
 		const dim3 block = block_shape(R.g1-R.g0);
+#if defined(FX3D_TUNE_TRT_VF) // ... or of the wind-tunnel line (TRT with VOLUME_FORCE)
+		if(ext!=0 || cells_per_thread>0 || collision!=COLL_TRT || !volume_force || !tma_eligible<Q, ST>(L, R)) { set_error("tuning build: whole-row TRT+VOLUME_FORCE kernel only"); return FX3D_ERR_INVALID; }
+		return launch_tma<Q, COLL_TRT, ST, true>(Lk, R, stream, reserve, peers);
+#else
 		if(ext!=0 || cells_per_thread>0 || collision!=COLL_SRT || volume_force || !tma_eligible<Q, ST>(L, R)) { set_error("tuning build: whole-row SRT kernel only"); return FX3D_ERR_INVALID; }
 		return launch_tma<Q, COLL_SRT, ST, false>(Lk, R, stream, reserve, peers);
+#endif
 	}
 #else
 	if(ext!=0) { // SUBGRID (bit 0) and/or MOVING_BOUNDARIES (bit 1): the whole-row bulk-copy kernel (cells_per_thread 0, regions in groups of 4) or the general kernel (1)

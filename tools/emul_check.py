@@ -16,9 +16,9 @@ out = f"/tmp/fx3d_emul_{tag}"
 subprocess.run(["make", "-j8", "-C", os.path.join(ROOT, "tests", "emul"), f"OUT={out}", f"EXTRA={extra}"], check=True, capture_output=True)
 lib = capi.Lib(os.path.join(out, "libfx3d_emul.so"))
 bits = lambda a: a.view(np.uint32) if a.dtype == np.float32 else a
-CASES = [((19, SRT, FP16S, 0), (512, 2, 3), (1, 1, 1)), ((19, SRT, FP32, 0), (512, 2, 2), (1, 1, 1)), ((19, TRT, FP16C, 3), (256, 4, 3), (1, 1, 1)),
-         ((27, TRT, FP32, 3), (64, 16, 3), (1, 1, 1)), ((19, SRT, FP32, 1), (1024, 2, 4), (2, 1, 2)), ((19, SRT, FP16S, 2), (1024, 4, 2), (2, 2, 1)),
-         ((19, SRT, FP32, 0), (64, 32, 8), (1, 2, 2)), ((19, SRT, FP16S, 24), (64, 32, 8), (1, 2, 2)), ((27, SRT, FP16S, 0), (128, 8, 4), (1, 1, 2))]
+CASES = [((19, SRT, FP16S, 0), (512, 6, 7), (1, 1, 1)), ((19, SRT, FP32, 0), (512, 7, 6), (1, 1, 1)), ((19, TRT, FP16C, 3), (256, 12, 6), (1, 1, 1)),
+         ((27, TRT, FP32, 3), (64, 16, 6), (1, 1, 1)), ((19, SRT, FP32, 1), (1024, 6, 12), (2, 1, 2)), ((19, SRT, FP16S, 2), (1024, 12, 6), (2, 2, 1)),
+         ((19, SRT, FP32, 0), (64, 32, 12), (1, 2, 2)), ((19, SRT, FP16S, 24), (64, 32, 12), (1, 2, 2)), ((27, SRT, FP16S, 0), (128, 8, 12), (1, 1, 2))]
 bad = 0
 for v, dims, D in CASES:
     f = (1e-4, -2e-4, 3e-4) if v[3] & 1 else (0.0, 0.0, 0.0)
