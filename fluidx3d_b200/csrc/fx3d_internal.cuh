@@ -27,9 +27,13 @@ int check_launch(const char* what);           // cudaGetLastError with error tra
 int cuda_fail(cudaError_t e, const char* what);
 #endif
 
-// DDF layout rules (see lbm_kernels.cuh): pitch multiple of 64 elements, x offset 63 when the x axis has a halo so that
-// the first non-halo cell (x=1) lands on element 64 of its row: every warp's vector access then starts on a 128-byte line
-// (with offset 7 / 16-byte alignment a 512^3 FP16S domain moved 15 % more sectors and ran 25 % slower)
+// DDF layout rules (see lbm_kernels.cuh). Without an x halo: rows of Nx elements, pitch rounded up to 64 elements. With an x halo the NON-HALO cells
+// of a row (x = 1 .. Nx-2) start on a pitch boundary: x = 1 is element 0 of pitch row r+1, the halo cell x = Nx-1 follows the row, and the halo cell
+// x = 0 is the last element of pitch row r (xo = px-1; the slot carries one extra pitch row). For rows of 512 cells and more the pitch is a multiple of
+// 512 elements, so that every row of non-halo cells starts on a multiple of its own length in bytes -- measured on B200 (profiles/r02_row_kernel_tuning.txt):
+// bulk copies of 1-KB rows that start 128 bytes into a 1280-byte pitch (the first layout: xo = 63) ran the collide kernel of a 514x512x512 domain at
+// 2.08 ms (FP16S) / 3.55 ms (FP32); the same rows on 2-KB boundaries 1.89 / 3.37 ms (periodic 512^3: 1.73 / 3.32 ms). The price is memory: an
+// x-decomposed 514-cell row occupies 1024 elements.
 inline bool make_lattice(const fx3d_lattice* in, uint64_t t, float fx, float fy, float fz, Lattice& L) {
 	if(!in) { set_error("lattice is null"); return false; }
 	if(in->Nx==0u||in->Ny==0u||in->Nz==0u) { set_error("lattice size is 0"); return false; }
@@ -38,9 +42,10 @@ inline bool make_lattice(const fx3d_lattice* in, uint64_t t, float fx, float fy,
 	L.Nx = in->Nx; L.Ny = in->Ny; L.Nz = in->Nz;
 	L.Hx = in->Dx>1u; L.Hy = in->Dy>1u; L.Hz = in->Dz>1u;
 	if((L.Hx&&in->Nx<3u)||(L.Hy&&in->Ny<3u)||(L.Hz&&in->Nz<3u)) { set_error("a decomposed axis needs at least 3 cells (halo + 1 + halo)"); return false; }
-	L.xo = L.Hx ? 63u : 0u;
-	L.px = ((in->Nx+L.xo+63u)/64u)*64u;
-	L.slot = (uint64_t)L.px*in->Ny*in->Nz;
+	const uint32_t align = (L.Hx && in->Nx-2u>=512u) ? 512u : 64u;
+	L.px = ((in->Nx+align-1u)/align)*align;
+	L.xo = L.Hx ? L.px-1u : 0u;
+	L.slot = (uint64_t)L.px*((uint64_t)in->Ny*in->Nz+(L.Hx ? 1ull : 0ull));
 	if(L.slot>0xFFFFFFFFull) { set_error("a domain may hold at most 2^32-1 (padded) cells"); return false; }
 	L.slot32 = (uint32_t)L.slot;
 	L.fi = in->fi; L.rho = in->rho; L.u = in->u; L.flags = in->flags;

@@ -159,7 +159,7 @@ int fx3d_malloc(int device, size_t bytes, void** ptr) {
 	if(!ptr) return FX3D_ERR_INVALID;
 	*ptr = nullptr;
 	if(int rc = use_device(device)) return rc;
-	FX3D_CUDA(cudaMalloc(ptr, bytes ? bytes : 1u), "cudaMalloc");
+	FX3D_CUDA(cudaMalloc(ptr, bytes+256u), "cudaMalloc"); // 256 bytes of slack: bulk copies of rows that start off a 16-byte boundary (flag rows of x-decomposed domains) round their end up
 	cudaError_t e = cudaMemset(*ptr, 0, bytes);
 	if(e==cudaSuccess) e = cudaStreamSynchronize(0); // the library's streams are non-blocking: the zero fill must have landed before any of them touches the buffer
 	if(e!=cudaSuccess) { cudaFree(*ptr); *ptr = nullptr; return cuda_fail(e, "cudaMemset"); }

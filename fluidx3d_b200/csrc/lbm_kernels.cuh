@@ -667,20 +667,23 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_col
 //
 // Tile = 128/bx whole x-rows of W = 4*bx non-halo cells (bx threads per row, 4 cells per thread). A row of one slot is one
 // contiguous segment, so: one copy per (slot, tile row) in, one out. In shared memory the rows of one slot form a SET of a fixed
-// size known at compile time, [16-byte pad | 128 threads x 4 cells | 16-byte pad], so that every per-thread access of the hot loop
-// is register + immediate offset (the tile shape is a launch parameter; a stride that depended on it cost 60 multiply-adds per thread
-// and tile, profiles/r02a_*):
+// size known at compile time, [pad | 128 threads x 4 cells | pad], so that every per-thread access of the hot loop is register +
+// immediate offset (the tile shape is a launch parameter; a stride that depended on it cost 60 multiply-adds per thread and tile):
 //   * periodic rows (no x halo): the copies fill the rows; the x-shifted directions read and write at wrapped positions
-//   * rows with x halos (x-decomposed domains, one-row tiles only): one copy covers pad + row + pad -- the halo cell x=0 is the last
-//     element of the head pad, x=Nx-1 the first of the tail pad (the DDF layout puts cell x=1 on a 128-byte line) -- nothing wraps
+//   * rows with x halos (x-decomposed domains, one-row tiles only): the row of non-halo cells starts on a pitch boundary (see
+//     make_lattice) and is copied as it is; only the neighbour-side buffer of a direction with an x component reaches a halo cell,
+//     on the side the direction points to, and its copy is [row | pad] (the halo cell x=Nx-1 is the first element of the tail pad)
+//     or [pad | row] (x=0 is the last element of the head pad) -- nothing wraps
 // so there are no shuffles, no edge accesses and no per-thread global addresses for the DDFs at all.
 //
-// Ring of S stages per block (S*stage bytes of shared memory; B blocks per SM): tile k of the block's contiguous share uses stage
-// k%S. Per tile: wait(full[stage]) -> registers <- stage -> block barrier -> refill the stage of the previous tile (its bulk stores
-// have had the stream-in to finish reading it) -> collide -> stage <- registers (in place) -> proxy fence + block barrier -> bulk
-// stores. Every row buffer is loaded and stored by the same thread, which waits only for the bulk stores it issued itself. The copies
-// are dealt to the four warps; for one-row tiles lane 0 of warp w issues buffers w, w+4, .. from an unrolled list in which
-// everything but the row position is a compile-time constant and all address arithmetic is warp-uniform.
+// Ring of S stages per block (S*stage bytes of shared memory; B blocks per SM): tile k of the block's share uses stage k%S. Per
+// tile: wait(full[stage]) -> registers <- stage -> block barrier -> refill the stage of the previous tile (its bulk stores have had
+// the stream-in to finish reading it) -> collide -> stage <- registers (in place) -> proxy fence + block barrier -> bulk stores.
+// Every row buffer is loaded and stored by the same thread, which waits only for the bulk stores it issued itself. The buffers are
+// dealt to the four warps; ONE ELECTED LANE of warp w issues buffers w, w+4, .. from an unrolled list in which everything but the
+// row position is a compile-time constant (elect.sync: ptxas then emits each UBLKCP once, with uniform-register addresses, instead
+// of a loop over the lanes it believes active). Tiles are numbered y-fastest and dealt round-robin to the blocks, so that the
+// resident blocks sweep neighbouring rows together (DRAM page locality across blocks).
 //
 // Fused y/z halo delivery (replaces LBM::communicate_fi for those axes, src/lbm.cpp:1355-1387): under Esoteric-Pull every
 // (slot, row) written in step t has exactly one reader in step t+1 -- the tile at the same row for what was written through the
@@ -798,10 +801,13 @@ template<int Q, int ST> FX3D_HDC constexpr int row_blocks() { return ST==ST_FP32
 #endif
 template<int Q, int ST> FX3D_HDC constexpr int row_cells() { return ST==ST_FP32 ? FX3D_ROW_K_32 : (Q>19 ? FX3D_ROW_K_27 : FX3D_ROW_K_16); }
 template<int Q, int ST> FX3D_HDC constexpr uint32_t row_threads() { return ST==ST_FP32 ? FX3D_ROW_T_32 : (Q>19 ? FX3D_ROW_T_27 : FX3D_ROW_T_16); }
-constexpr uint32_t ROW_PAD = 16u, ROW_MAX_STAGES = FX3D_ROW_MAX_STAGES<16 ? FX3D_ROW_MAX_STAGES : 16u, ROW_BARRIERS = 128u;
+constexpr uint32_t ROW_MAX_STAGES = FX3D_ROW_MAX_STAGES<16 ? FX3D_ROW_MAX_STAGES : 16u, ROW_BARRIERS = 128u;
+// pad on either side of a row buffer: a whole 32-byte sector, so that a store that ends in a pad ends on a sector boundary -- except for D3Q27 FP32, whose
+// two stages of 27 sets fit the shared memory of two blocks per SM only with 16-byte pads
+template<int Q, int ST> FX3D_HDC constexpr uint32_t row_pad() { return (Q>19 && ST==ST_FP32) ? 16u : 32u; }
 template<int Q, int ST> FX3D_HDC constexpr uint32_t row_header() { return ROW_BARRIERS+2u*row_threads<Q, ST>()*8u; } // header: full[<=16] mbarriers, then two buffers of T x 2 flag words (rows whose flags cannot travel by bulk copy)
-template<int Q, int ST> FX3D_HDC constexpr uint32_t row_set_bytes() { return row_threads<Q, ST>()*(uint32_t)row_cells<Q, ST>()*(ST==ST_FP32 ? 4u : 2u)+2u*ROW_PAD; } // one slot's rows of a tile: [pad | K*T elements | pad]
-template<int Q, int ST> FX3D_HDC constexpr uint32_t row_stage_bytes() { return (uint32_t)Q*row_set_bytes<Q, ST>()+row_threads<Q, ST>()*(uint32_t)row_cells<Q, ST>(); } // Q sets + the flag bytes of the tile
+template<int Q, int ST> FX3D_HDC constexpr uint32_t row_set_bytes() { return row_threads<Q, ST>()*(uint32_t)row_cells<Q, ST>()*(ST==ST_FP32 ? 4u : 2u)+2u*row_pad<Q, ST>(); } // one slot's rows of a tile: [pad | K*T elements | pad]
+template<int Q, int ST> FX3D_HDC constexpr uint32_t row_stage_bytes() { return (uint32_t)Q*row_set_bytes<Q, ST>()+row_threads<Q, ST>()*(uint32_t)row_cells<Q, ST>()+16u; } // Q sets + the flag bytes of the tile (+16: a flag row that starts off a 16-byte boundary)
 
 template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false>
 __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_stream_collide_tma(const Lattice L, const Region R, const uint32_t tiles_y, const uint32_t S, const RowPeers P, const RowOffsets O) {
@@ -811,7 +817,7 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 	typedef Codec<ST> C;
 	typedef typename C::elem_t E;
 	typedef Pack<ST, K> PK;
-	constexpr uint32_t VB = (uint32_t)(sizeof(E)*K), ESZ = (uint32_t)sizeof(E), PAD = ROW_PAD, SET = row_set_bytes<Q, ST>(), STAGE = row_stage_bytes<Q, ST>();
+	constexpr uint32_t VB = (uint32_t)(sizeof(E)*K), ESZ = (uint32_t)sizeof(E), PAD = row_pad<Q, ST>(), SET = row_set_bytes<Q, ST>(), STAGE = row_stage_bytes<Q, ST>();
 	unsigned char* const smem = dynamic_smem();
 	uint64_t* const full = reinterpret_cast<uint64_t*>(smem); // full[stage]: the bulk loads of the tile in this stage have landed
 	unsigned char* const ring = smem+row_header<Q, ST>();
@@ -821,7 +827,10 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 	const uint32_t W = bx*(uint32_t)K, row_bytes = bx*VB;
 	const bool hx = L.Hx!=0u, hy = L.Hy!=0u, hz = L.Hz!=0u; // hx: one-row tiles only (by==1), see the launcher
 	// where a row's copy starts in its pitch row (bytes), how much it covers, and where that lands in the set
-	const uint32_t g_off = hx ? (L.xo+1u)*ESZ-PAD : 0u, copy_bytes = hx ? row_bytes+2u*PAD : row_bytes, s_off = hx ? 0u : PAD;
+	// Only the neighbour-side buffer of a direction with an x component reaches a halo cell, and only on the side the direction points to: its copy is
+	// [row | pad] (e_x > 0) or [pad | row] (e_x < 0); every other buffer moves the row alone, which starts on a 128-byte line. (Copying pad + row + pad for
+	// all buffers, as the first version did, touched 10 lines per copy instead of 8: x-decomposed domains ran 25 % behind periodic ones.)
+	const uint32_t g_row = hx ? (L.xo+1u)*ESZ : 0u, x_pad = hx ? PAD : 0u;
 	const uint32_t ncopies = (uint32_t)Q*by;
 	if(t==0u) { for(uint32_t s=0u; s<S; s++) mbar_init(full+s); }
 	fence_async_smem();
@@ -844,31 +853,34 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 			if(dy!=0 || dz!=0) base = reinterpret_cast<char*>(P.fi[(dy+1)+3*(dz+1)]);
 		}
 #if defined(FX3D_ROW_ADDR_CXX)
-		return base+((uint64_t)slot*L.slot+(uint64_t)(yr*L.px+zr*plane))*ESZ+g_off;
+		return base+((uint64_t)slot*L.slot+(uint64_t)(yr*L.px+zr*plane))*ESZ+g_row;
 #else
-		return mad_wide(yr*L.px+zr*plane, ESZ, mad_wide(L.slot32, slot*ESZ, base))+g_off; // two IMAD.WIDE: the element offset inside a slot fits 32 bits
+		return mad_wide(yr*L.px+zr*plane, ESZ, mad_wide(L.slot32, slot*ESZ, base))+g_row; // two IMAD.WIDE: the element offset inside a slot fits 32 bits (address of the first non-halo cell of the row)
 #endif
 	};
 	auto copy_rows = [&](auto LOAD, auto STORE_ELSEWHERE, uint32_t y0, uint32_t z, uint32_t stage) FX3D_LAMBDA { // one lane of every warp: its share of the Q buffers, everything but y and z known at compile time
 		constexpr bool load = decltype(LOAD)::value;
-		unsigned char* const sb = ring+(size_t)stage*STAGE+s_off;
+		unsigned char* const sb = ring+(size_t)stage*STAGE+PAD; // the row inside set 0
 		auto one = [&](auto J) FX3D_LAMBDA {
 			constexpr int j = J;
 			constexpr int i = j==0 ? 0 : (j&1) ? j : j-1; // odd member of the direction pair
 			constexpr uint32_t slot = j==0 ? 0u : (j&1) ? (ODD ? (uint32_t)i : (uint32_t)i+1u) : (ODD ? (uint32_t)i+1u : (uint32_t)i);
 			constexpr bool local = j==0 || (j&1);
-			constexpr int ey = j==0 ? 0 : dir_y(i), ez = j==0 ? 0 : dir_z(i);
+			constexpr int ey = j==0 ? 0 : dir_y(i), ez = j==0 ? 0 : dir_z(i), ex = local ? 0 : dir_x(i);
+			const uint32_t before = ex<0 ? x_pad : 0u, bytes = row_bytes+(ex!=0 ? x_pad : 0u);
 			_Pragma("unroll 1") for(uint32_t ty=0u; ty<by; ty++) { // (a uniform loop; one pass for one-row tiles)
-				char* gp = row_address(decltype(STORE_ELSEWHERE)::value && j!=0, slot, local, ey, ez, y0+ty, z);
-				if constexpr(load) bulk_load(sb+(size_t)j*SET+ty*row_bytes, gp, copy_bytes, full+stage); else bulk_store(gp, sb+(size_t)j*SET+ty*row_bytes, copy_bytes);
+				char* gp = row_address(decltype(STORE_ELSEWHERE)::value && j!=0, slot, local, ey, ez, y0+ty, z)-before;
+				if constexpr(load) bulk_load(sb+(size_t)j*SET+ty*row_bytes-before, gp, bytes, full+stage); else bulk_store(gp, sb+(size_t)j*SET+ty*row_bytes-before, bytes);
 			}
 		};
 		// one-row tiles away from the y/z faces (no row wraps, none is delivered to a neighbour): tile address + a per-buffer constant. (For many-row tiles
 		// the same shortcut measured 9 % SLOWER on 256^3 grids than the general addresses -- not understood, left out.)
 		auto plain_one_row = [&](auto J) FX3D_LAMBDA {
 			constexpr int j = J;
-			char* gp = reinterpret_cast<char*>(L.fi)+((uint64_t)(y0*L.px+z*plane)*ESZ+g_off)+O.c[j];
-			if constexpr(load) bulk_load(sb+(size_t)j*SET, gp, copy_bytes, full+stage); else bulk_store(gp, sb+(size_t)j*SET, copy_bytes);
+			constexpr int ex = (j==0 || (j&1)) ? 0 : dir_x(j-1);
+			const uint32_t before = ex<0 ? x_pad : 0u, bytes = row_bytes+(ex!=0 ? x_pad : 0u);
+			char* gp = reinterpret_cast<char*>(L.fi)+((uint64_t)(y0*L.px+z*plane)*ESZ+g_row)+O.c[j]-before;
+			if constexpr(load) bulk_load(sb+(size_t)j*SET-before, gp, bytes, full+stage); else bulk_store(gp, sb+(size_t)j*SET-before, bytes);
 		};
 #if defined(FX3D_ROW_NO_OFFSETS)
 		const bool inner_tile = false;
@@ -878,21 +890,26 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 		if(inner_tile) static_for<0, (int)NW, 1>([&](auto Wc) FX3D_LAMBDA { if(warp==(uint32_t)Wc.value) static_for<Wc.value, Q, (int)NW>(plain_one_row); });
 		else static_for<0, (int)NW, 1>([&](auto Wc) FX3D_LAMBDA { if(warp==(uint32_t)Wc.value) static_for<Wc.value, Q, (int)NW>(one); });
 	};
-	// flag bytes: where the rows of the flag array start on 16-byte boundaries (no x halo, Nx a multiple of 16) they travel with the tile, one bulk
-	// copy per tile row into the tail of the stage; otherwise per thread, see below
+	// flag bytes travel with the tile, one bulk copy per tile row into the tail of the stage: rows that start on 16-byte boundaries (no x halo, Nx a
+	// multiple of 16) as they are; the flag row of a one-row tile with x halos as the 16-byte-aligned stretch that contains it (threads then read their 4
+	// bytes from two words). Other shapes: per thread, see below.
 #if defined(FX3D_ROW_NO_FLAGS_BULK)
-	const bool flags_bulk = false;
+	const bool flags_bulk = false, flags_skew = false;
 #else
-	const bool flags_bulk = !hx && (L.Nx&15u)==0u;
+	const bool flags_skew = hx && by==1u;                       // bulk copy of an unaligned flag row
+	const bool flags_bulk = flags_skew || (!hx && (L.Nx&15u)==0u);
 #endif
+	auto flag_row = [&](uint32_t y0, uint32_t z) FX3D_LAMBDA -> uint64_t { return ((uint64_t)y0+(uint64_t)z*L.Ny)*L.Nx+L.Hx; }; // index of the first non-halo flag of the tile
 	auto load_tile = [&](uint32_t y0, uint32_t z, uint32_t stage) FX3D_LAMBDA { // every thread of the block calls it
-		if(t==0u) mbar_expect_tx(full+stage, ncopies*copy_bytes+(flags_bulk ? by*W : 0u));
+		const uint32_t skew = flags_skew ? (uint32_t)(reinterpret_cast<uintptr_t>(L.flags+flag_row(y0, z))&15u) : 0u; // bytes between the 16-byte boundary before the row and the row
+		const uint32_t flag_bytes = flags_skew ? ((skew+W+15u)&~15u) : W;
+		if(t==0u) mbar_expect_tx(full+stage, ncopies*row_bytes+by*(uint32_t)x_dirs<Q>()*x_pad+(flags_bulk ? by*flag_bytes : 0u));
 		if(elect_one(lane)) {
 			copy_rows(std::true_type{}, std::false_type{}, y0, z, stage);
 			if(flags_bulk && warp==(uint32_t)Q%NW) {
-				const uint8_t* gp = L.flags+((uint64_t)y0+(uint64_t)z*L.Ny)*L.Nx;
+				const uint8_t* gp = L.flags+flag_row(y0, z)-skew;
 				unsigned char* sp = ring+(size_t)stage*STAGE+(size_t)Q*SET;
-				_Pragma("unroll 1") for(uint32_t ty=0u; ty<by; ty++, gp += L.Nx, sp += W) bulk_load(sp, gp, W, full+stage);
+				_Pragma("unroll 1") for(uint32_t ty=0u; ty<by; ty++, gp += L.Nx, sp += W) bulk_load(sp, gp, flag_bytes, full+stage);
 			}
 		}
 #if defined(FX3D_HOST_EMULATION)
@@ -956,7 +973,12 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 		const uint32_t y0 = R.y0+cur.yb*by, y = y0+threadIdx.y, z = R.z0+cur.zo;
 		mbar_wait(full+stage, fill&1u);
 		unsigned char* const sb = ring+(size_t)stage*STAGE;
-		const uint32_t flags4 = flags_bulk ? (K==4 ? *reinterpret_cast<const uint32_t*>(sb+(size_t)Q*SET+t*4u) : (uint32_t)*reinterpret_cast<const uint16_t*>(sb+(size_t)Q*SET+t*2u)) : take_flags(cur, k&1u);
+		uint32_t flags4;
+		if(flags_skew) { // my 4 bytes start `skew` bytes into the copied stretch: two aligned words and a funnel shift
+			const uint32_t skew = (uint32_t)(reinterpret_cast<uintptr_t>(L.flags+flag_row(y0, z))&15u), sh = 8u*(skew&3u);
+			const uint32_t* w = reinterpret_cast<const uint32_t*>(sb+(size_t)Q*SET+(skew&~3u)+t*4u);
+			flags4 = sh==0u ? w[0] : (w[0]>>sh)|(w[1]<<(32u-sh));
+		} else flags4 = flags_bulk ? *reinterpret_cast<const uint32_t*>(sb+(size_t)Q*SET+t*4u) : take_flags(cur, k&1u);
 		// ---- stream in from the stage: my vectors, and for the x-shifted directions the element beyond them ----
 		PK A[Q];
 		static_for<0, Q, 1>([&](auto I) FX3D_LAMBDA { A[I].load(reinterpret_cast<const E*>(sb+(size_t)I.value*SET+tb)); });
@@ -1695,11 +1717,20 @@ __global__ void __launch_bounds__(128) k_exchange_fi_rows(const Lattice L, const
 	uint32_t xe = 0u, ye = axis==1u ? (plus ? 1u : len-2u) : r, ze = axis==1u ? r : (plus ? 1u : len-2u);
 	uint32_t xi = 0u, yi = axis==1u ? (plus ? len-1u : 0u) : r, zi = axis==1u ? r : (plus ? len-1u : 0u);
 	const uint64_t src = extract_addr(L, L.odd, plus ? im : ip, xe, ye, ze), dst = insert_addr(L, L.odd, plus ? ip : im, xi, yi, zi);
-	const uint64_t src_row = src-src%L.px, dst_row = dst-dst%L.px; // slot and rows are multiples of the pitch
-	const uint4* sp = reinterpret_cast<const uint4*>(reinterpret_cast<const E*>(plus ? fi_plus : fi_minus)+src_row);
-	uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<E*>(L.fi)+dst_row);
-	const uint32_t nvec = L.px*(uint32_t)sizeof(E)/16u;
-	for(uint32_t v=threadIdx.x; v<nvec; v+=blockDim.x) dp[v] = sp[v];
+	// the cell row that holds the element: its pitch row, and with an x halo (where the cell x=0 is the LAST element of a pitch row and x=1 the first of
+	// the next one) the Nx elements from that last element on; the addresses above may have been stepped from x=0 to x=1 or x=Nx-1, which lie one pitch row later
+	const uint64_t src_pitch = (src-src%L.px)-((L.Hx && src%L.px!=L.px-1u) ? L.px : 0u), dst_pitch = (dst-dst%L.px)-((L.Hx && dst%L.px!=L.px-1u) ? L.px : 0u);
+	const E* sp = reinterpret_cast<const E*>(plus ? fi_plus : fi_minus)+src_pitch+L.xo;
+	E* dp = reinterpret_cast<E*>(L.fi)+dst_pitch+L.xo;
+	const uint32_t n = L.Hx ? L.Nx : L.px; // elements to copy (source and destination have the same alignment: the domains share one layout)
+	uint32_t head = (uint32_t)(((16u-(uint32_t)(reinterpret_cast<uintptr_t>(sp)&15u))&15u)/sizeof(E));
+	if(head>n) head = n;
+	const uint32_t nvec = (n-head)*(uint32_t)sizeof(E)/16u, tail = head+nvec*(16u/(uint32_t)sizeof(E));
+	for(uint32_t k=threadIdx.x; k<head; k+=blockDim.x) dp[k] = sp[k];
+	const uint4* sv = reinterpret_cast<const uint4*>(sp+head);
+	uint4* dv = reinterpret_cast<uint4*>(dp+head);
+	for(uint32_t v=threadIdx.x; v<nvec; v+=blockDim.x) dv[v] = sv[v];
+	for(uint32_t k=tail+threadIdx.x; k<n; k+=blockDim.x) dp[k] = sp[k];
 }
 struct PeerFields { const float* rho; const float* u; const uint8_t* flags; };
 #if defined(FX3D_TU_LBM) // non-template kernels are defined in exactly one translation unit

@@ -55,7 +55,7 @@ int fx3d_stream_wait_event(int, fx3d_stream, fx3d_event) { return FX3D_OK; }
 
 int fx3d_malloc(int, size_t bytes, void** ptr) {
 	if(!ptr) return FX3D_ERR_INVALID;
-	const size_t n = ((bytes ? bytes : 1u)+4095u)&~(size_t)4095u;
+	const size_t n = ((bytes ? bytes : 1u)+256u+4095u)&~(size_t)4095u; // 256 bytes of slack like the product's fx3d_malloc
 	char name[64];
 	std::snprintf(name, sizeof(name), "/fx3d_emul_%d_%llu", (int)getpid(), (unsigned long long)g_counter++);
 	const int fd = shm_open(name, O_CREAT|O_EXCL|O_RDWR, 0600);

@@ -39,7 +39,11 @@ def exch():
             p, m = sim._peers[sim._neighbour(d0, axis, +1)], sim._peers[sim._neighbour(d0, axis, -1)]
             lib.exchange_fi(C.byref(dom.lat), axis, dom.t, p["fi"], m["fi"], dom.stream)
 def full(): sim.do_time_step()
-for name, body in [("collide only", collide), ("rendezvous only", rdv), ("collide + rendezvous", collide_rdv), ("exchange only (direct pull)", exch), ("full step", full), ("collide only (again)", collide)]:
+def fused():
+    if sim._fused: lib.stream_collide_fused(C.byref(dom.lat), dom.t, dom.fx, dom.fy, dom.fz, sim._fused[d0], dom.stream)
+def xfaces():
+    if sim.Dx > 1: sim._communicate("fi", axes=(0,))
+for name, body in [("collide only", collide), ("rendezvous only", rdv), ("collide + rendezvous", collide_rdv), ("exchange only (direct pull)", exch), ("fused collide only", fused), ("x faces only (staged)", xfaces), ("full step", full), ("collide only (again)", collide)]:
     timed(name, body)
 sim.close()
 dist.destroy_process_group()
