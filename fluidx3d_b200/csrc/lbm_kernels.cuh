@@ -1653,7 +1653,7 @@ __global__ void __launch_bounds__(128) k_transfer_fi(const Lattice L, const uint
 		bp[k] = vp; bm[k] = vm;
 	} else {
 		const E vp = bp[k], vm = bm[k];
-		fi[insert_addr(L, L.odd, ip, xp, yp, zp)] = vp; fi[insert_addr(L, L.odd, im, xm, ym, zm)] = vm;
+		fi[insert_addr(L, L.odd, ip, xp, yp, zp)] = vp; fi[insert_addr(L, L.odd, im, xm, ym, zm)] = vm; // (writing the halo cells' whole 32-byte sectors instead changed nothing: 119 us either way for two 512^2 faces -- the kernel is bound by the 32 separate transactions of every warp access, not by partial sectors)
 	}
 }
 // rho/u/flags halo: 4 float planes then one byte plane at byte 16*A, src/kernel.cpp:2133-2158
