@@ -775,6 +775,9 @@ template<int Q> inline RowOffsets row_offsets(const Lattice& L, uint32_t esz) {
 #ifndef FX3D_ROW_STRIDED
 #define FX3D_ROW_STRIDED 1 // tile order: 1 = y-fastest, dealt round-robin to the blocks; 0 = one contiguous z-fastest share per block
 #endif
+#ifndef FX3D_ROW_DYNAMIC
+#define FX3D_ROW_DYNAMIC 1 // 1: blocks claim their tiles from a device counter instead of taking every gridDim.x-th one
+#endif
 #ifndef FX3D_ROW_MAX_STAGES
 #define FX3D_ROW_MAX_STAGES 16
 #endif
@@ -805,12 +808,13 @@ constexpr uint32_t ROW_MAX_STAGES = FX3D_ROW_MAX_STAGES<16 ? FX3D_ROW_MAX_STAGES
 // pad on either side of a row buffer: a whole 32-byte sector, so that a store that ends in a pad ends on a sector boundary -- except for D3Q27 FP32, whose
 // two stages of 27 sets fit the shared memory of two blocks per SM only with 16-byte pads
 template<int Q, int ST> FX3D_HDC constexpr uint32_t row_pad() { return (Q>19 && ST==ST_FP32) ? 16u : 32u; }
-template<int Q, int ST> FX3D_HDC constexpr uint32_t row_header() { return ROW_BARRIERS+2u*row_threads<Q, ST>()*8u; } // header: full[<=16] mbarriers, then two buffers of T x 2 flag words (rows whose flags cannot travel by bulk copy)
+constexpr uint32_t ROW_CLAIMS = 128u; // ring of 32 claimed tile numbers (FX3D_ROW_DYNAMIC)
+template<int Q, int ST> FX3D_HDC constexpr uint32_t row_header() { return ROW_BARRIERS+ROW_CLAIMS+2u*row_threads<Q, ST>()*8u; } // header: full[<=16] mbarriers, then two buffers of T x 2 flag words (rows whose flags cannot travel by bulk copy)
 template<int Q, int ST> FX3D_HDC constexpr uint32_t row_set_bytes() { return row_threads<Q, ST>()*(uint32_t)row_cells<Q, ST>()*(ST==ST_FP32 ? 4u : 2u)+2u*row_pad<Q, ST>(); } // one slot's rows of a tile: [pad | K*T elements | pad]
 template<int Q, int ST> FX3D_HDC constexpr uint32_t row_stage_bytes() { return (uint32_t)Q*row_set_bytes<Q, ST>()+row_threads<Q, ST>()*(uint32_t)row_cells<Q, ST>()+16u; } // Q sets + the flag bytes of the tile (+16: a flag row that starts off a 16-byte boundary)
 
 template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false>
-__global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_stream_collide_tma(const Lattice L, const Region R, const uint32_t tiles_y, const uint32_t S, const RowPeers P, const RowOffsets O) {
+__global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_stream_collide_tma(const Lattice L, const Region R, const uint32_t tiles_y, const uint32_t S, const RowPeers P, const RowOffsets O, uint32_t* const tile_counter) {
 	constexpr int K = row_cells<Q, ST>();
 	constexpr uint32_t T = row_threads<Q, ST>(), NW = T/32u; // threads and warps per block
 	static_assert(K==4 && T==128u, "measured on B200: two cells per thread (256 threads per tile) gains nothing for FP32 and loses a third for 16-bit storage; 64-thread blocks for 256-cell rows are no faster either");
@@ -927,6 +931,21 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 	// ---- this block's share of the (row group, plane) tiles; tile k of the share uses stage k%S ----
 	const uint32_t nz = R.z1-R.z0;
 	struct Pos { uint32_t yb, zo; }; // tile row group and plane offset
+#if FX3D_ROW_DYNAMIC
+	// tiles are numbered y-fastest (neighbouring rows in flight together: DRAM page locality across blocks) and CLAIMED from a device counter that the
+	// launcher zeroes: S tiles at the start, one more per tile processed, always S tiles ahead of the tile in hand. SMs that run a little faster simply take
+	// more tiles; with a fixed deal the slowest SM finished 2-4 % after the average one (profiles/r02_row_fp16s_512.txt). The claimed numbers travel from
+	// thread 0 to the block through a ring of 32 words in shared memory, ordered by the two block barriers of every tile.
+	const uint32_t ntiles = tiles_y*nz; // (< 2^32-16: checked by the launcher)
+	uint32_t* const claims = reinterpret_cast<uint32_t*>(smem+ROW_BARRIERS);
+	auto pos_of = [&](uint32_t tile) FX3D_LAMBDA -> Pos { return Pos{ tile%tiles_y, tile/tiles_y }; };
+	if(t==0u) { const uint32_t base = atomicAdd(tile_counter, S); for(uint32_t j=0u; j<S; j++) claims[j] = base+j<ntiles ? base+j : ntiles; }
+	__syncthreads();
+	for(uint32_t j=0u; j<S; j++) { const uint32_t tile = claims[j]; if(tile<ntiles) { const Pos p = pos_of(tile); load_tile(R.y0+p.yb*by, R.z0+p.zo, j); } } // prologue: the first S tiles
+	uint32_t tile_now = claims[0];
+	Pos cur = pos_of(tile_now<ntiles ? tile_now : 0u);
+	const uint32_t n = tile_now<ntiles ? 1u : 0u; // (only "is there a first tile" is known in advance)
+#else
 #if FX3D_ROW_STRIDED
 	// tiles are numbered y-fastest and dealt round-robin to the blocks: at any moment the resident blocks work on ~gridDim.x neighbouring rows,
 	// i.e. every one of the 2Q copy streams of the device sweeps one contiguous window of memory (DRAM page locality across blocks)
@@ -942,6 +961,7 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 #endif
 	for(uint32_t j=0u; j<S && j<n; j++) { const Pos p = advance(first, j); load_tile(R.y0+p.yb*by, R.z0+p.zo, j); } // prologue: the first S tiles
 	Pos cur = first;
+#endif // FX3D_ROW_DYNAMIC
 	const uint32_t x0 = (uint32_t)K*threadIdx.x;
 	// my 4 flag bytes: the two aligned words that hold them travel one tile ahead with per-thread cp.async into a double-buffered corner of
 	// shared memory -- no register holds a load in flight (as plain loads the words were spilled on arrival, and the spill store waited for
@@ -949,7 +969,7 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 	const uint64_t flag_plane = (uint64_t)L.Nx*L.Ny;
 	const uint8_t* const my_flags = L.flags+((uint64_t)(L.Hx+x0)+(uint64_t)(R.y0+threadIdx.y)*L.Nx+(uint64_t)R.z0*flag_plane);
 	const uint32_t flag_rows = by*L.Nx; // bytes between consecutive tile row groups
-	uint32_t* const flag_words = reinterpret_cast<uint32_t*>(smem+ROW_BARRIERS)+2u*t; // [2 buffers][T threads][2 words]
+	uint32_t* const flag_words = reinterpret_cast<uint32_t*>(smem+ROW_BARRIERS+ROW_CLAIMS)+2u*t; // [2 buffers][T threads][2 words]
 	auto flag_address = [&](Pos p) FX3D_LAMBDA -> uintptr_t { return reinterpret_cast<uintptr_t>(my_flags+(uint64_t)p.yb*flag_rows+(uint64_t)p.zo*flag_plane); };
 	auto request_flags = [&](Pos p, uint32_t buffer) FX3D_LAMBDA {
 		const uintptr_t a = flag_address(p);
@@ -969,7 +989,11 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 	const bool last = threadIdx.x+1u==bx, firstt = threadIdx.x==0u;
 	const uint32_t up = (!hx && last) ? tb+VB-row_bytes : tb+VB, dn = (!hx && firstt) ? tb+row_bytes-ESZ : tb-ESZ; // byte offsets in the set
 	uint32_t stage = 0u, fill = 0u, prev_stage = 0u; // stage = k%S, fill = k/S (how often the stage has been filled before), prev_stage = (k-1)%S
+#if FX3D_ROW_DYNAMIC
+	for(uint32_t k=0u; tile_now<ntiles; k++) {
+#else
 	for(uint32_t k=0u; k<n; k++) {
+#endif
 		const uint32_t y0 = R.y0+cur.yb*by, y = y0+threadIdx.y, z = R.z0+cur.zo;
 		mbar_wait(full+stage, fill&1u);
 		unsigned char* const sb = ring+(size_t)stage*STAGE;
@@ -990,9 +1014,18 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 		__syncthreads(); // everybody has read the stage before anybody writes results into it
 		// refill the stage of the previous tile now rather than right after its stores: they have had the stream-in above to finish
 		// reading it, so the copying thread rarely waits here
+#if FX3D_ROW_DYNAMIC
+		uint32_t claimed = 0u;
+		if(t==0u) claimed = atomicAdd(tile_counter, 1u); // the tile this block will take S tiles from now (its number is published before the second barrier)
+		const uint32_t tile_refill = claims[(k+S-1u)&31u], tile_next = claims[(k+1u)&31u];
+		if(k>=1u && tile_refill<ntiles) { const Pos p = pos_of(tile_refill); if(elect_one(lane)) bulk_wait_read(); load_tile(R.y0+p.yb*by, R.z0+p.zo, prev_stage); }
+		const Pos next = pos_of(tile_next<ntiles ? tile_next : 0u);
+		if(tile_next<ntiles && !flags_bulk) request_flags(next, (k+1u)&1u);
+#else
 		if(k>=1u && k-1u+S<n) { const Pos p = advance(cur, S-1u); if(elect_one(lane)) bulk_wait_read(); load_tile(R.y0+p.yb*by, R.z0+p.zo, prev_stage); } // (stepping the positions without the divisions measured 4 % slower for FP16S: two more live values, more spills)
 		const Pos next = advance(cur, 1u);
 		if(k+1u<n && !flags_bulk) request_flags(next, (k+1u)&1u);
+#endif
 		collide_tile<Q, COLL, ST, VF, K, SG, MB>(L, A, flags4, L.Hx+x0, y, z);
 		// ---- stream out into the same row buffers ----
 		A[0].store(reinterpret_cast<E*>(sb+tb));
@@ -1005,9 +1038,15 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 			else A[i+1].store_shift_down(reinterpret_cast<E*>(q+tb), reinterpret_cast<E*>(q+dn));
 		});
 		fence_async_smem();
+#if FX3D_ROW_DYNAMIC
+		if(t==0u) claims[(k+S)&31u] = claimed<ntiles ? claimed : ntiles;
+#endif
 		__syncthreads();
 		store_tile(y0, z, stage);
 		cur = next;
+#if FX3D_ROW_DYNAMIC
+		tile_now = tile_next;
+#endif
 		prev_stage = stage; stage++;
 		if(stage==S) { stage = 0u; fill++; }
 	}

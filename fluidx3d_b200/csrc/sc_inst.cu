@@ -1,6 +1,9 @@
 // sc_inst.cu -- stream_collide instantiations for one (velocity set, storage) pair; compiled once per pair with
 // -DFX3D_Q=19|27 -DFX3D_ST=0|1|2 so that the six heavy translation units build in parallel.
 #include <atomic>
+#include <mutex>
+#include <vector>
+#include <utility>
 #include "fx3d_internal.cuh"
 #include <algorithm>
 
@@ -62,6 +65,22 @@ template<int Q, int ST> static bool tma_eligible(const Lattice& L, const Region&
 	if(L.Hx ? (block.y!=1u || ((L.xo+1u)*esz)%16u!=0u) : L.xo!=0u) return false; // x halos: one-row tiles, the first non-halo cell starts a 16-byte chunk
 	return row_stages<Q, ST>()>=2u;
 }
+// FX3D_ROW_DYNAMIC: the counter the blocks of one launch claim their tiles from -- one word per (device, stream), zeroed on the stream before every launch
+// (launches on one stream are ordered, so one word per stream is enough)
+static uint32_t* tile_counter_for(int dev, void* stream) {
+#if defined(FX3D_HOST_EMULATION)
+	static uint32_t word; (void)dev; (void)stream; word = 0u; return &word;
+#else
+	static std::mutex mu;
+	static std::vector<std::pair<std::pair<int, void*>, uint32_t*>> table;
+	std::lock_guard<std::mutex> lock(mu);
+	for(auto& e : table) if(e.first.first==dev && e.first.second==stream) return e.second;
+	uint32_t* p = nullptr;
+	if(cudaMalloc(&p, 256u)!=cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+	table.push_back({ { dev, stream }, p });
+	return p;
+#endif
+}
 template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = false> static int launch_tma_parity(const Lattice& L, const Region& R, void* stream, int reserve, const RowPeers& peers) {
 	const dim3 block = row_block<Q, ST>(L);
 	const uint32_t tiles_y = (R.y1-R.y0)/block.y, nz = R.z1-R.z0;
@@ -83,8 +102,21 @@ template<int Q, int COLL, int ST, bool VF, int ODD, bool SG = false, bool MB = f
 	const uint64_t all_blocks = (uint64_t)sms*(uint64_t)per_sm, blocks = all_blocks>2ull*(uint64_t)std::max(reserve, 0) ? all_blocks-(uint64_t)std::max(reserve, 0) : all_blocks, ntiles = (uint64_t)tiles_y*nz;
 	if(ntiles==0ull) return FX3D_OK;
 	const dim3 grid((uint32_t)std::min<uint64_t>(ntiles, blocks), 1u, 1u);
+	uint32_t* counter = nullptr;
+#if FX3D_ROW_DYNAMIC
+	if(ntiles>0xFFFF0000ull) { set_error("region has too many tiles"); return FX3D_ERR_INVALID; }
+#if defined(FX3D_HOST_EMULATION)
+	counter = tile_counter_for(0, stream);
+#else
+	counter = tile_counter_for(dev, stream);
+#endif
+	if(!counter) { set_error("stream_collide: no memory for the tile counter"); return FX3D_ERR_OUT_OF_MEMORY; }
+#if !defined(FX3D_HOST_EMULATION)
+	{ const cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(uint32_t), (cudaStream_t)stream); if(e!=cudaSuccess) return cuda_fail(e, "cudaMemsetAsync(tile counter)"); }
+#endif
+#endif
 	g_kind_launches[3]++;
-	FX3D_LAUNCH_SMEM((k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG, MB>), grid, block, smem, stream, L, R, tiles_y, S, peers, row_offsets<Q>(L, ST==ST_FP32 ? 4u : 2u));
+	FX3D_LAUNCH_SMEM((k_stream_collide_tma<Q, COLL, ST, VF, ODD, SG, MB>), grid, block, smem, stream, L, R, tiles_y, S, peers, row_offsets<Q>(L, ST==ST_FP32 ? 4u : 2u), counter);
 	return check_launch("stream_collide (bulk copies)");
 }
 // row segments (rows longer than 512 cells, shapes the whole-row kernel does not take): bulk loads, direct stores

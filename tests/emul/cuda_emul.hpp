@@ -101,6 +101,7 @@ template<class F> void launch(dim3 grid, dim3 block, F&& body, size_t smem_bytes
 }
 
 static inline void __syncthreads() { emul::tctx.block_bar->arrive_and_wait(); }
+static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline uint32_t __float_as_uint(float x) { uint32_t u; std::memcpy(&u, &x, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float x; std::memcpy(&x, &u, 4); return x; }
 static inline uint32_t __shfl_down_sync(unsigned, uint32_t v, unsigned d) { return emul::exchange(v, (int)emul::tctx.lane+(int)d, emul::tctx.lane+d<32u); }
