@@ -682,8 +682,9 @@ __global__ void __launch_bounds__(128, pipe_blocks_per_sm<Q, ST>()) k_stream_col
 // Every row buffer is loaded and stored by the same thread, which waits only for the bulk stores it issued itself. The buffers are
 // dealt to the four warps; ONE ELECTED LANE of warp w issues buffers w, w+4, .. from an unrolled list in which everything but the
 // row position is a compile-time constant (elect.sync: ptxas then emits each UBLKCP once, with uniform-register addresses, instead
-// of a loop over the lanes it believes active). Tiles are numbered y-fastest and dealt round-robin to the blocks, so that the
-// resident blocks sweep neighbouring rows together (DRAM page locality across blocks).
+// of a loop over the lanes it believes active). Tiles are numbered y-fastest and CLAIMED by the blocks from a device counter (S tiles
+// ahead of the tile in hand), so that the resident blocks sweep neighbouring rows together (DRAM page locality across blocks) and no
+// launch waits for its slowest SM (FX3D_ROW_DYNAMIC=0 falls back to a fixed round-robin deal).
 //
 // Fused y/z halo delivery (replaces LBM::communicate_fi for those axes, src/lbm.cpp:1355-1387): under Esoteric-Pull every
 // (slot, row) written in step t has exactly one reader in step t+1 -- the tile at the same row for what was written through the
@@ -773,7 +774,7 @@ template<int Q> inline RowOffsets row_offsets(const Lattice& L, uint32_t esz) {
 #define FX3D_ROW_BLOCKS_27 3 // D3Q27 with 16-bit storage: 168 registers
 #endif
 #ifndef FX3D_ROW_STRIDED
-#define FX3D_ROW_STRIDED 1 // tile order: 1 = y-fastest, dealt round-robin to the blocks; 0 = one contiguous z-fastest share per block
+#define FX3D_ROW_STRIDED 1 // tile order of the fixed deal (FX3D_ROW_DYNAMIC=0): 1 = y-fastest, dealt round-robin to the blocks; 0 = one contiguous z-fastest share per block
 #endif
 #ifndef FX3D_ROW_DYNAMIC
 #define FX3D_ROW_DYNAMIC 1 // 1: blocks claim their tiles from a device counter instead of taking every gridDim.x-th one
@@ -965,7 +966,7 @@ __global__ void __launch_bounds__(row_threads<Q, ST>(), row_blocks<Q, ST>()) k_s
 	const uint32_t x0 = (uint32_t)K*threadIdx.x;
 	// my 4 flag bytes: the two aligned words that hold them travel one tile ahead with per-thread cp.async into a double-buffered corner of
 	// shared memory -- no register holds a load in flight (as plain loads the words were spilled on arrival, and the spill store waited for
-	// them: 17 % of all stall samples, profiles/r02b_*)
+	// them: 17 % of all stall samples in an ncu capture of that version)
 	const uint64_t flag_plane = (uint64_t)L.Nx*L.Ny;
 	const uint8_t* const my_flags = L.flags+((uint64_t)(L.Hx+x0)+(uint64_t)(R.y0+threadIdx.y)*L.Nx+(uint64_t)R.z0*flag_plane);
 	const uint32_t flag_rows = by*L.Nx; // bytes between consecutive tile row groups

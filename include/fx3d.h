@@ -143,8 +143,8 @@ int fx3d_set_kernel_variant(int variant);
 int fx3d_set_interior_reserve(int blocks);
 /* stream_collide launches so far by kernel kind: 0 general (1 cell/thread), 1 vector (2/4 cells/thread), 2 persistent with a
  * cp.async ring, 3 persistent with bulk copies of whole rows, 4 persistent with bulk copies of row segments, 5 persistent with bulk loads
- * of row segments and direct stores, 6 one cell per thread at high occupancy, 7 bulk copies of whole rows through a ring shared by
- * several compute groups (with fused y/z halo delivery) */
+ * of row segments and direct stores, 6 one cell per thread at high occupancy, 7 unused (a form of kind 3 with several compute groups
+ * sharing one ring of stages: measured slower and removed; kind 3 carries the fused y/z halo delivery) */
 int fx3d_stream_collide_launches(int kind, uint64_t* launches);
 int fx3d_launch_count(uint64_t* launches);                            /* kernels launched by this library so far */
 
