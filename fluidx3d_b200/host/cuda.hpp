@@ -84,12 +84,18 @@ template<typename T> class Memory { // host (page-locked) + device buffer of N*d
 	}
 	void take(Memory& m) {
 		N = m.N; d = m.d; host_buffer_exists = m.host_buffer_exists; device_buffer_exists = m.device_buffer_exists; external_host_buffer = m.external_host_buffer;
-		host_buffer = m.host_buffer; device_buffer = m.device_buffer; device = m.device; x = m.x; y = m.y; z = m.z; w = m.w;
+		host_buffer = m.host_buffer; device_buffer = m.device_buffer; device = m.device;
 		m.host_buffer = nullptr; m.device_buffer = nullptr; m.host_buffer_exists = m.device_buffer_exists = false;
+		set_pointers(); m.set_pointers();
 	}
-	void set_pointers() { x = host_buffer; if(d>1u) y = host_buffer+N; if(d>2u) z = host_buffer+2ull*N; if(d>3u) w = host_buffer+3ull*N; }
+	void set_pointers() { // component planes of the host buffer (structure of arrays): x..w and s0..sF as in the reference's Memory<T> (src/opencl.hpp:356-359,392-393)
+		T** const s[16] = { &s0, &s1, &s2, &s3, &s4, &s5, &s6, &s7, &s8, &s9, &sA, &sB, &sC, &sD, &sE, &sF };
+		for(uint k=0u; k<16u; k++) *s[k] = (host_buffer && k<d) ? host_buffer+(ulong)k*N : nullptr;
+		x = s0; y = s1; z = s2; w = s3;
+	}
 public:
 	T *x=nullptr, *y=nullptr, *z=nullptr, *w=nullptr; // host pointers to the component planes (SoA)
+	T *s0=nullptr, *s1=nullptr, *s2=nullptr, *s3=nullptr, *s4=nullptr, *s5=nullptr, *s6=nullptr, *s7=nullptr, *s8=nullptr, *s9=nullptr, *sA=nullptr, *sB=nullptr, *sC=nullptr, *sD=nullptr, *sE=nullptr, *sF=nullptr;
 	Memory() {}
 	Memory(Device& dev, const ulong N_, const uint dimensions=1u, const bool allocate_host=true, const bool allocate_device=true, const T value=(T)0) : N(N_), d(dimensions), device(&dev) {
 		if(N*(ulong)d==0ull) print_error("Memory size must be larger than 0.");
@@ -127,6 +133,10 @@ public:
 	T* device_data() const { return device_buffer; } // device pointer, handed to the fx3d_lattice of the owning domain
 	T& operator[](const ulong i) { return host_buffer[i]; }
 	const T& operator[](const ulong i) const { return host_buffer[i]; }
+	T* operator()() { return host_buffer; } // (src/opencl.hpp:504-509)
+	const T* operator()() const { return host_buffer; }
+	T operator()(const ulong i) const { return host_buffer[i]; }
+	T operator()(const ulong i, const uint dimension) const { return host_buffer[i+(ulong)dimension*N]; } // component `dimension` of element i
 	T* exchange_host_buffer(T* other) { T* mine = host_buffer; host_buffer = other; external_host_buffer = true; set_pointers(); return mine; }
 	void reset(const T value=(T)0) {
 		if(host_buffer_exists) for(ulong i=0ull; i<range(); i++) host_buffer[i] = value;
