@@ -103,7 +103,8 @@ def test_emulated_hybrid_kernel_matches_oracle(emul, v, dims, D):
         assert after[3] > before[3] and after[:3] == before[:3] and after[5] == before[5], "the whole-row bulk-copy kernel must be the one that ran"
 
 
-XROW_CASES = [((19, SRT, FP16S, 1), (1024, 4, 4), (2, 1, 2)), ((19, TRT, FP32, 3), (1024, 2, 3), (2, 2, 1)), ((27, SRT, FP16C, 2), (1024, 2, 2), (2, 1, 1)),  # x halos: one-row tiles
+XROW_CASES = [((27, TRT, FP32, 3), (1024, 4, 6), (2, 1, 2)),  # D3Q27 FP32: 16-byte pads, and the one direction pair whose neighbour side reaches the LEFT halo cell
+              ((19, SRT, FP16S, 1), (1024, 4, 4), (2, 1, 2)), ((19, TRT, FP32, 3), (1024, 2, 3), (2, 2, 1)), ((27, SRT, FP16C, 2), (1024, 2, 2), (2, 1, 1)),  # x halos: one-row tiles
               ((19, SRT, FP32, 0), (32, 32, 8), (1, 2, 2)), ((19, TRT, FP16C, 11), (32, 32, 6), (1, 2, 1)), ((27, TRT, FP32, 3), (64, 16, 6), (1, 2, 2)),
               ((19, SRT, FP16S, 24), (64, 32, 8), (1, 2, 2)), ((19, SRT, FP16S, 0), (512, 2, 6), (1, 2, 2))]  # (rows per domain: a multiple of the rows per tile)
 
